@@ -1,0 +1,199 @@
+/*
+ * rt_b200.h -- C ABI of librt_b200.so, the B200 (sm_100a) implementation of the
+ * traditional sphere ray-tracing inner loop of JoaquinRodriguezph/ray-tracer-v1.
+ *
+ * The reference is pure Python and has NO FFI/plugin boundary: its
+ * callers build Python objects and call Ray.nearestSphereIntersect /
+ * Intersection.terminalRGB / TraditionalRenderer.render / RayTracerEnv.step
+ * directly.  This header is the boundary a maintainer would bind underneath
+ * those methods (ctypes stub shown in INTEGRATION.md); each entry cites the
+ * reference interface it replaces (path:line relative to the reference root).
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no C++/torch types.  Every function returns an
+ *     int status (RT_OK == 0); rt_last_error() gives the message of the last
+ *     failure on the calling thread.
+ *   - "_dev" pointers are device pointers on the handle's GPU, everything else is
+ *     host memory.  `stream` is a cudaStream_t passed as void* (NULL = default
+ *     stream).  Calls are asynchronous on that stream unless stated otherwise.
+ *   - precision: RT_F32 = the FP32 product path; RT_F64 = the FP64 parity build
+ *     (same algorithms in double, compiled without FMA contraction, following the
+ *     reference's operation order; <= 1e-9 relative parity, north_star).
+ *   - no hidden global state: one rt_scene handle per GPU / rank.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { RT_OK = 0, RT_ERR_INVALID = 1, RT_ERR_CUDA = 2, RT_ERR_NOMEM = 3, RT_ERR_UNSUPPORTED = 4 };
+enum { RT_F32 = 0, RT_F64 = 1 };
+/* RayTracerEnv info['reason'] codes (RL/ray_tracer_env.py:316-397, FB/ray_tracer_env.py:393-507) */
+enum { RT_REASON_NONE = 0, RT_REASON_RAY_MISSED = 1, RT_REASON_RAY_ESCAPED = 2, RT_REASON_MAX_BOUNCES = 3,
+       RT_REASON_HIT_SUN = 4, RT_REASON_ALREADY_ON_SUN = 5 };
+enum { RT_ENV_RL = 0, RT_ENV_FB = 1 };
+#define RT_NO_ID INT32_MIN  /* "no suppressed id" */
+
+typedef struct rt_scene rt_scene; /* flattened scene resident in HBM (both precisions) */
+typedef struct rt_env rt_env;     /* SoA state of a batch of RayTracerEnv episodes */
+
+/* ---- scene graph, flattened (replaces list[Sphere] + light lists: object.py:4-9,
+ *      material.py:4-8, light.py:12-37; TraditionalRenderer.scene/.light_sources/.small_lights,
+ *      FB/fb_vs_traditional_chandelier.py:394-403).  All arrays row-major, host memory. */
+typedef struct rt_scene_desc {
+    int32_t n;               /* spheres */
+    const double *centre;    /* [n,3] */
+    const double *radius;    /* [n]   */
+    const double *material;  /* [n,4] reflective, transparent, emitive, refractive_index */
+    const double *colour;    /* [n,3] 0-255 scale */
+    const int32_t *ids;      /* [n]   Sphere.id */
+    int32_t nG;              /* GlobalLight */
+    const double *g_vec;     /* [nG,3] */
+    const double *g_col;     /* [nG,3] */
+    const double *g_strength;
+    const double *g_max_angle;
+    const int32_t *g_func;
+    int32_t nP;              /* PointLight */
+    const int32_t *p_id;
+    const double *p_pos;     /* [nP,3] */
+    const double *p_col;     /* [nP,3] */
+    const double *p_strength;
+    const double *p_max_angle;
+    const int32_t *p_func;   /* -1 no fall-off, 0 divide by distance */
+    double bg[3];            /* background_colour */
+    int32_t nL;              /* Algorithm B light spheres */
+    const double *l_centre;  /* [nL,3] */
+    const double *l_colour;  /* [nL,3] */
+    const int32_t *l_index;  /* [nL] scene index of the light sphere or -1 */
+    const uint8_t *small;    /* [n] member of small_lights (may be NULL) */
+} rt_scene_desc;
+
+/* ---- library / device ------------------------------------------------------------ */
+const char *rt_last_error(void);
+int rt_version(void);
+int rt_device_count(int *count);
+/* props[0..5] = SM count, cc major, cc minor, max SM clock kHz, L2 bytes, max smem/block (opt-in) */
+int rt_device_props(int device, int64_t *props6, size_t *total_mem);
+int rt_dev_alloc(int device, size_t bytes, void **out_dev);
+int rt_dev_free(int device, void *ptr_dev);
+int rt_host_alloc_pinned(size_t bytes, void **out_host);
+int rt_host_free_pinned(void *ptr_host);
+int rt_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream);
+int rt_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream);
+int rt_memset_dev(int device, void *dst_dev, int value, size_t bytes, void *stream);
+int rt_stream_sync(int device, void *stream);
+/* FP32 roofline denominator: dependent-free FFMA loop on every SM, timed with CUDA events (synchronous). */
+int rt_measure_fp32_peak(int device, int repeats, double *tflops_out, double *ms_out);
+
+/* ---- scene ------------------------------------------------------------------------ */
+int rt_scene_create(int device, const rt_scene_desc *desc, rt_scene **out);
+int rt_scene_update(rt_scene *scene, const rt_scene_desc *desc, void *stream); /* re-flatten a mutated scene */
+int rt_scene_destroy(rt_scene *scene);
+int rt_scene_info(const rt_scene *scene, int32_t *n_spheres, int32_t *device, int32_t *has_lbvh);
+/* On-device LBVH (Morton codes -> radix sort -> Karras hierarchy -> AABB refit) over the spheres; spheres whose
+ * radius exceeds `huge_radius` (walls) stay in a brute-force side list.  Renders use it when present. */
+int rt_lbvh_build(rt_scene *scene, double huge_radius, void *stream);
+int rt_lbvh_drop(rt_scene *scene);
+
+/* ---- batched primitives (replace Ray.sphereDiscriminant ray.py:73-107, Ray.nearestSphereIntersect
+ *      ray.py:160-231, Intersection.terminalRGB ray.py:37-65) ------------------------------------ */
+/* m independent ray/sphere pairs.  rays [m,6] origin+raw direction, spheres [m,4] centre+radius (double, device).
+ * out [m,8] = hit, t, point(3), normal(3). */
+int rt_sphere_discriminant(int device, int precision, int m, const double *rays_dev, const double *spheres_dev,
+                           int point, double *out_dev, void *stream);
+/* m rays through nearestSphereIntersect (+ terminalRGB when rgb_dev != NULL).
+ * suppress_dev [m] Sphere.id to suppress or RT_NO_ID (NULL = none); bounces0_dev [m] initial `bounces` (NULL = 0);
+ * through0_dev [m] initial through_count (NULL = 0).
+ * term_dev [m,10] = hit, scene index, bounces, through_count, point(3), normal(3); rgb_dev [m,3] (miss -> miss[3]). */
+int rt_trace_rays(rt_scene *scene, int precision, int m, const double *rays_dev, const int32_t *suppress_dev,
+                  const int32_t *bounces0_dev, const int32_t *through0_dev, int max_bounces, int shadow_max_bounces,
+                  const double miss[3], double *term_dev, double *rgb_dev, void *stream);
+
+/* ---- Algorithm A frame: deterministic Whitted-style trace + terminalRGB (drivers: RL/output5.py:416-533
+ *      render_true_original, :1420-1525 render_custom_scene('traditional'), notebooks' cell-0 loops) ---------- */
+typedef struct rt_whitted_params {
+    double cam[3];          /* ray origin */
+    const double *X;        /* [W] host: x component of direction (X, Y, -1)  */
+    const double *Y;        /* [H] host */
+    int32_t W, H;
+    int32_t y0, y1;         /* row band [y0,y1) rendered by this call (tile sharding) */
+    int32_t s0, s1;         /* sample range [s0,s1) accumulated by this call (sample sharding) */
+    int32_t spp;            /* total samples per pixel of the frame; jitter iff spp > 1 (output5.py:1463-1470) */
+    int32_t max_bounces;
+    int32_t shadow_max_bounces; /* terminalRGB(max_bounces=...) default 0 */
+    double miss[3];         /* colour of a ray that terminates nowhere */
+    uint64_t seed;          /* Philox key */
+    int32_t prenormalise;   /* output5.py:1476-1483 normalises before Ray() normalises again */
+    int32_t accumulate;     /* 0: overwrite accum rows [y0,y1); 1: add into them */
+} rt_whitted_params;
+/* accum_dev: [H,W,4] float (RT_F32) or double (RT_F64): sum r,g,b over the sample range + sample count.
+ * hit_dev (optional) [H,W] int32 terminal scene index of the last sample (-1 miss).
+ * stats_dev (optional) uint64[8]: [0] nearest-hit/occlusion queries, [1] primary rays. */
+int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted_params *p, void *accum_dev, int32_t *hit_dev,
+                      uint64_t *stats_dev, void *stream);
+
+/* ---- Algorithm B frame: TraditionalRenderer.render / trace_ray_traditional
+ *      (FB/fb_vs_traditional_chandelier.py:417-554, FB/fb_vs_traditional_complex.py:285-422) ------------------ */
+typedef struct rt_path_params {
+    double cam[3];
+    int32_t W, H;
+    double fov_deg;         /* 60 in the reference (:415) */
+    int32_t y0, y1;         /* row band */
+    int32_t s0, s1;         /* sample range */
+    int32_t max_bounces;
+    double mirror_threshold;/* material.reflective > threshold mirrors: 0.9 complex (:349), 0 chandelier (:481) */
+    uint64_t seed;
+    int32_t accumulate;
+} rt_path_params;
+/* accum_dev as above.  stats_dev (optional) uint64[8]: [0] total_rays (trace calls, reference-compatible),
+ * [1] total_intersections, [2] light_hits, [3] small_light_hits, [4] nearest-hit queries,
+ * [5] sphere tests, [6] AABB tests (LBVH only). */
+int rt_render_path(rt_scene *scene, int precision, const rt_path_params *p, void *accum_dev, uint64_t *stats_dev,
+                   void *stream);
+
+/* accum [H,W,4] -> image [H,W,3] float32 = min(1, floor(sum/spp)/255) (chandelier.py:540-549; output5.py:1500-1512).
+ * rows [y0,y1) only. */
+int rt_resolve(int device, int precision, const void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1,
+               int32_t spp, float *image_dev, void *stream);
+
+/* Host-buffer convenience entries (what a ctypes/cffi binding of the reference's render() calls): upload nothing
+ * but the parameters, render, resolve, copy the float32 [H,W,3] image (and optionally the raw sums [H,W,4] in the
+ * accum type, and stats) back to HOST memory.  Synchronous. */
+int rt_render_whitted_host(rt_scene *scene, int precision, const rt_whitted_params *p, float *image_host,
+                           void *accum_host, int32_t *hit_host, uint64_t *stats_host);
+int rt_render_path_host(rt_scene *scene, int precision, const rt_path_params *p, float *image_host, void *accum_host,
+                        uint64_t *stats_host);
+
+/* ---- batched RayTracerEnv (RL/ray_tracer_env.py:21-425, FB/ray_tracer_env.py:21-538) ------------------------ */
+typedef struct rt_env_desc {
+    int32_t B;              /* parallel episodes */
+    int32_t W, H;           /* image_width / image_height */
+    double cam[3];          /* camera_position */
+    double cam_angle[3];    /* camera_angle (Euler, vector.py:117-127) */
+    double fov;             /* degrees */
+    int32_t max_bounces;
+    int32_t flavour;        /* RT_ENV_RL | RT_ENV_FB */
+    int32_t sun_id;         /* FB flavour: 7 (FB/ray_tracer_env.py:256) */
+} rt_env_desc;
+int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out);
+int rt_env_destroy(rt_env *env);
+/* reset(): pixels_dev [B,2] int32 (x,y) or NULL = draw uniformly with Philox(seed) on device.
+ * mask_dev (optional) [B] uint8: reset only envs with mask != 0 (auto-reset of finished episodes).
+ * obs_dev [B,18] float32.  pixels_out_dev (optional) [B,2] receives the pixels used. */
+int rt_env_reset(rt_env *env, const int32_t *pixels_dev, const uint8_t *mask_dev, uint64_t seed, float *obs_dev,
+                 int32_t *pixels_out_dev, void *stream);
+/* step(): actions_dev [B,2] float32 -> obs [B,18] f32, reward [B] f64, terminated/truncated [B] u8,
+ * reason [B] int32 (RT_REASON_*), info_dev (optional) [B,4] f64 = bounce_count, through_count, total_reward,
+ * hit_sun.  stats_dev (optional) uint64[8]: [0] nearest-hit/occlusion queries. */
+int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev, double *reward_dev, uint8_t *terminated_dev,
+                uint8_t *truncated_dev, int32_t *reason_dev, double *info_dev, uint64_t *stats_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
