@@ -1,0 +1,410 @@
+"""ctypes binding of ``csrc/librt_b200.so`` (C ABI: include/rt_b200.h).
+
+This is the only door between the Python scene API and the CUDA kernels.  There is
+NO CPU fallback: if the shared library is missing, or no CUDA device is present, every
+tracing call raises ``NativeLibraryError``.
+
+Device memory handed across the ABI is either owned by the library helpers below
+(``DeviceBuffer``: ``rt_dev_alloc``) or a torch CUDA tensor's ``data_ptr()``
+(the batched env hands observations to agents as tensors).
+"""
+import ctypes as C
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+__all__ = ["NativeLibraryError", "lib", "build", "DeviceBuffer", "DeviceScene", "device_count", "device_props",
+           "measure_fp32_peak", "F32", "F64", "NO_ID", "REASONS", "LIB_PATH"]
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(CSRC, "librt_b200.so")
+
+F32, F64 = 0, 1
+NO_ID = -(2 ** 31)
+REASONS = {0: None, 1: "ray_missed", 2: "ray_escaped", 3: "max_bounces", 4: "hit_sun", 5: "already_on_sun"}
+ENV_RL, ENV_FB = 0, 1
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int32)
+c_u8p = C.POINTER(C.c_uint8)
+vp = C.c_void_p
+
+
+class NativeLibraryError(RuntimeError):
+    """librt_b200.so is missing / failed to load / reported an error.  Never caught to fall back to the CPU."""
+
+
+class SceneDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("centre", c_dp), ("radius", c_dp), ("material", c_dp), ("colour", c_dp), ("ids", c_ip),
+        ("nG", C.c_int32), ("g_vec", c_dp), ("g_col", c_dp), ("g_strength", c_dp), ("g_max_angle", c_dp), ("g_func", c_ip),
+        ("nP", C.c_int32), ("p_id", c_ip), ("p_pos", c_dp), ("p_col", c_dp), ("p_strength", c_dp), ("p_max_angle", c_dp),
+        ("p_func", c_ip),
+        ("bg", C.c_double * 3),
+        ("nL", C.c_int32), ("l_centre", c_dp), ("l_colour", c_dp), ("l_index", c_ip), ("small", c_u8p),
+    ]
+
+
+class WhittedParams(C.Structure):
+    _fields_ = [("cam", C.c_double * 3), ("X", c_dp), ("Y", c_dp), ("W", C.c_int32), ("H", C.c_int32),
+                ("y0", C.c_int32), ("y1", C.c_int32), ("s0", C.c_int32), ("s1", C.c_int32), ("spp", C.c_int32),
+                ("max_bounces", C.c_int32), ("shadow_max_bounces", C.c_int32), ("miss", C.c_double * 3),
+                ("seed", C.c_uint64), ("prenormalise", C.c_int32), ("accumulate", C.c_int32)]
+
+
+class PathParams(C.Structure):
+    _fields_ = [("cam", C.c_double * 3), ("W", C.c_int32), ("H", C.c_int32), ("fov_deg", C.c_double),
+                ("y0", C.c_int32), ("y1", C.c_int32), ("s0", C.c_int32), ("s1", C.c_int32), ("max_bounces", C.c_int32),
+                ("mirror_threshold", C.c_double), ("seed", C.c_uint64), ("accumulate", C.c_int32)]
+
+
+class EnvDesc(C.Structure):
+    _fields_ = [("B", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("cam", C.c_double * 3),
+                ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("max_bounces", C.c_int32),
+                ("flavour", C.c_int32), ("sun_id", C.c_int32)]
+
+
+# every symbol include/rt_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "rt_last_error": (C.c_char_p, []),
+    "rt_version": (C.c_int, []),
+    "rt_device_count": (C.c_int, [c_ip]),
+    "rt_device_props": (C.c_int, [C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_size_t)]),
+    "rt_dev_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp)]),
+    "rt_dev_free": (C.c_int, [C.c_int, vp]),
+    "rt_host_alloc_pinned": (C.c_int, [C.c_size_t, C.POINTER(vp)]),
+    "rt_host_free_pinned": (C.c_int, [vp]),
+    "rt_memcpy_h2d": (C.c_int, [C.c_int, vp, vp, C.c_size_t, vp]),
+    "rt_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, C.c_size_t, vp]),
+    "rt_memset_dev": (C.c_int, [C.c_int, vp, C.c_int, C.c_size_t, vp]),
+    "rt_stream_sync": (C.c_int, [C.c_int, vp]),
+    "rt_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
+    "rt_scene_create": (C.c_int, [C.c_int, C.POINTER(SceneDesc), C.POINTER(vp)]),
+    "rt_scene_update": (C.c_int, [vp, C.POINTER(SceneDesc), vp]),
+    "rt_scene_destroy": (C.c_int, [vp]),
+    "rt_scene_info": (C.c_int, [vp, c_ip, c_ip, c_ip]),
+    "rt_lbvh_build": (C.c_int, [vp, C.c_double, vp]),
+    "rt_lbvh_drop": (C.c_int, [vp]),
+    "rt_sphere_discriminant": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
+    "rt_trace_rays": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, c_dp, vp, vp, vp]),
+    "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
+    "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
+    "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "rt_render_whitted_host": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
+    "rt_render_path_host": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
+    "rt_env_create": (C.c_int, [vp, C.c_int, C.POINTER(EnvDesc), C.POINTER(vp)]),
+    "rt_env_destroy": (C.c_int, [vp]),
+    "rt_env_reset": (C.c_int, [vp, vp, vp, C.c_uint64, vp, vp, vp]),
+    "rt_env_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/ for sm_100a with the committed Makefile (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j4"] + (["-B"] if force else [])
+    res = subprocess.run(cmd, capture_output=not verbose, text=True)
+    if res.returncode != 0:
+        raise NativeLibraryError("building librt_b200.so failed:\n" + (res.stdout or "") + (res.stderr or ""))
+    return LIB_PATH
+
+
+def load_symbols():
+    """dlopen the library and bind every declared symbol.  Needs no GPU (used by the CPU-side ABI test)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise NativeLibraryError(
+                    f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(there is no CPU fallback)")
+            try:
+                handle = C.CDLL(LIB_PATH)
+            except OSError as e:
+                raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+            for name, (res, args) in SIGNATURES.items():
+                try:
+                    fn = getattr(handle, name)
+                except AttributeError as e:
+                    raise NativeLibraryError(f"{LIB_PATH} does not export {name}") from e
+                fn.restype, fn.argtypes = res, args
+            _lib = handle
+    return _lib
+
+
+def lib():
+    """The loaded library, after checking that a CUDA device is present."""
+    h = load_symbols()
+    if not getattr(h, "_rt_checked", False):
+        n = C.c_int32(0)
+        rc = h.rt_device_count(C.byref(n))
+        if rc != 0 or n.value <= 0:
+            raise NativeLibraryError("no CUDA device: the B200 kernels cannot run here and there is no CPU fallback "
+                                     f"({h.rt_last_error().decode()})")
+        h._rt_checked = True
+    return h
+
+
+def check(rc):
+    if rc != 0:
+        raise NativeLibraryError(f"librt_b200 error {rc}: {load_symbols().rt_last_error().decode()}")
+
+
+def device_count():
+    n = C.c_int32(0)
+    load_symbols().rt_device_count(C.byref(n))
+    return int(n.value)
+
+
+def device_props(device=0):
+    p = (C.c_int64 * 6)()
+    mem = C.c_size_t(0)
+    check(lib().rt_device_props(device, p, C.byref(mem)))
+    return {"sm_count": int(p[0]), "cc": (int(p[1]), int(p[2])), "sm_clock_khz": int(p[3]), "l2_bytes": int(p[4]),
+            "smem_optin": int(p[5]), "total_mem": int(mem.value)}
+
+
+def measure_fp32_peak(device=0, repeats=5):
+    """FFMA micro-benchmark -> (TFLOP/s, ms).  The FP32 roofline denominator measured on the box."""
+    tf, ms = C.c_double(0), C.c_double(0)
+    check(lib().rt_measure_fp32_peak(device, repeats, C.byref(tf), C.byref(ms)))
+    return float(tf.value), float(ms.value)
+
+
+def _ptr(x):
+    """Device pointer of a DeviceBuffer / torch tensor / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, DeviceBuffer):
+        return x.ptr
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    raise TypeError(f"not a device buffer: {type(x)!r}")
+
+
+class DeviceBuffer:
+    """A typed block of HBM owned through rt_dev_alloc / rt_dev_free."""
+
+    def __init__(self, shape, dtype, device=0, zero=True):
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.device = device
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = vp()
+        check(lib().rt_dev_alloc(device, max(self.nbytes, 1), C.byref(p)))
+        self.ptr = p.value
+        if zero and self.nbytes:
+            check(lib().rt_memset_dev(device, self.ptr, 0, self.nbytes, None))
+
+    @classmethod
+    def from_host(cls, array, dtype=None, device=0):
+        a = np.ascontiguousarray(array, dtype)
+        buf = cls(a.shape, a.dtype, device, zero=False)
+        buf.upload(a)
+        return buf
+
+    def upload(self, array, stream=None):
+        a = np.ascontiguousarray(array, self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        if self.nbytes:
+            check(lib().rt_memcpy_h2d(self.device, self.ptr, a.ctypes.data, self.nbytes, stream))
+            check(lib().rt_stream_sync(self.device, stream))
+
+    def fill(self, byte=0, stream=None):
+        if self.nbytes:
+            check(lib().rt_memset_dev(self.device, self.ptr, byte, self.nbytes, stream))
+
+    def download(self, stream=None):
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            check(lib().rt_memcpy_d2h(self.device, out.ctypes.data, self.ptr, self.nbytes, stream))
+            check(lib().rt_stream_sync(self.device, stream))
+        return out
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            try:
+                load_symbols().rt_dev_free(self.device, self.ptr)
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def _d(a, shape=None):
+    a = np.ascontiguousarray(a, np.float64)
+    return a if shape is None else a.reshape(shape)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def make_desc(fs):
+    """FlatScene (scene.py) -> (SceneDesc, keep-alive dict)."""
+    k = {name: _d(getattr(fs, name)) for name in ("centre", "radius", "material", "colour", "g_vec", "g_col", "g_strength",
+                                                  "g_max_angle", "p_pos", "p_col", "p_strength", "p_max_angle",
+                                                  "l_centre", "l_colour")}
+    k.update({name: _i(getattr(fs, name)) for name in ("ids", "g_func", "p_id", "p_func", "l_index")})
+    n = int(k["radius"].shape[0])
+    small = getattr(fs, "small", None)
+    k["small"] = np.ascontiguousarray(small if small is not None else np.zeros(n), np.uint8)
+    d = SceneDesc()
+    d.n, d.nG, d.nP, d.nL = n, int(k["g_strength"].shape[0]), int(k["p_strength"].shape[0]), int(k["l_index"].shape[0])
+    for name in ("centre", "radius", "material", "colour", "g_vec", "g_col", "g_strength", "g_max_angle", "p_pos", "p_col",
+                 "p_strength", "p_max_angle", "l_centre", "l_colour"):
+        setattr(d, name, k[name].ctypes.data_as(c_dp))
+    for name in ("ids", "g_func", "p_id", "p_func", "l_index"):
+        setattr(d, name, k[name].ctypes.data_as(c_ip))
+    d.small = k["small"].ctypes.data_as(c_u8p)
+    d.bg[:] = [float(x) for x in np.asarray(fs.bg, np.float64).reshape(3)]
+    return d, k
+
+
+class DeviceScene:
+    """A flattened scene resident in HBM (``rt_scene``): one per GPU / rank."""
+
+    def __init__(self, fs, device=0):
+        self.device = device
+        self.handle = None
+        d, keep = make_desc(fs)
+        h = vp()
+        check(lib().rt_scene_create(device, C.byref(d), C.byref(h)))
+        self.handle = h.value
+        self.n = int(d.n)
+        self.flat = fs
+
+    def update(self, fs, stream=None):
+        """Re-flatten after the Python scene was mutated (the reference's scenes are mutable lists)."""
+        d, keep = make_desc(fs)
+        check(lib().rt_scene_update(self.handle, C.byref(d), stream))
+        self.n = int(d.n)
+        self.flat = fs
+
+    def build_lbvh(self, huge_radius=50.0, stream=None):
+        check(lib().rt_lbvh_build(self.handle, float(huge_radius), stream))
+
+    def drop_lbvh(self):
+        check(lib().rt_lbvh_drop(self.handle))
+
+    @property
+    def has_lbvh(self):
+        n, dev, has = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(lib().rt_scene_info(self.handle, C.byref(n), C.byref(dev), C.byref(has)))
+        return bool(has.value)
+
+    # ---- frames ----------------------------------------------------------------------------------
+    def whitted_params(self, cam, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0, miss=None, seed=0, prenorm=False,
+                       rows=None, samples=None, accumulate=False):
+        X, Y = _d(X), _d(Y)
+        p = WhittedParams()
+        p.cam[:] = [float(c) for c in cam]
+        p.X, p.Y = X.ctypes.data_as(c_dp), Y.ctypes.data_as(c_dp)
+        p.W, p.H = int(X.shape[0]), int(Y.shape[0])
+        p.y0, p.y1 = (0, p.H) if rows is None else (int(rows[0]), int(rows[1]))
+        p.s0, p.s1 = (0, int(spp)) if samples is None else (int(samples[0]), int(samples[1]))
+        p.spp, p.max_bounces, p.shadow_max_bounces = int(spp), int(max_bounces), int(shadow_max_bounces)
+        miss = np.asarray(self.flat.bg if miss is None else miss, np.float64).reshape(3)
+        p.miss[:] = [float(c) for c in miss]
+        p.seed, p.prenormalise, p.accumulate = int(seed), int(bool(prenorm)), int(bool(accumulate))
+        p._keep = (X, Y)
+        return p
+
+    def path_params(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, rows=None, samples=None,
+                    accumulate=False):
+        p = PathParams()
+        p.cam[:] = [float(c) for c in cam]
+        p.W, p.H, p.fov_deg = int(W), int(H), float(fov)
+        p.y0, p.y1 = (0, p.H) if rows is None else (int(rows[0]), int(rows[1]))
+        p.s0, p.s1 = (0, int(spp)) if samples is None else (int(samples[0]), int(samples[1]))
+        p.max_bounces, p.mirror_threshold, p.seed = int(max_bounces), float(mirror_threshold), int(seed)
+        p.accumulate = int(bool(accumulate))
+        return p
+
+    def render_whitted(self, params, accum, precision=F32, hit=None, stats=None, stream=None):
+        """Asynchronous launch into device buffers (accum [H,W,4] of the precision's float type)."""
+        check(lib().rt_render_whitted(self.handle, precision, C.byref(params), _ptr(accum), _ptr(hit), _ptr(stats), stream))
+
+    def render_path(self, params, accum, precision=F32, stats=None, stream=None):
+        check(lib().rt_render_path(self.handle, precision, C.byref(params), _ptr(accum), _ptr(stats), stream))
+
+    def resolve(self, accum, W, H, spp, image, precision=F32, rows=None, stream=None):
+        y0, y1 = (0, H) if rows is None else rows
+        check(lib().rt_resolve(self.device, precision, _ptr(accum), int(W), int(H), int(y0), int(y1), int(spp),
+                               _ptr(image), stream))
+
+    def render_whitted_host(self, params, precision=F32, want_accum=True, want_hit=True):
+        """Host-buffer entry: -> (image [H,W,3] f32, sums [H,W,4], hit [H,W] i32, stats u64[8])."""
+        W, H = params.W, params.H
+        ft = np.float64 if precision == F64 else np.float32
+        image = np.zeros((H, W, 3), np.float32)
+        accum = np.zeros((H, W, 4), ft) if want_accum else None
+        hit = np.full((H, W), -1, np.int32) if want_hit else None
+        stats = np.zeros(8, np.uint64)
+        check(lib().rt_render_whitted_host(self.handle, precision, C.byref(params), image.ctypes.data,
+                                           None if accum is None else accum.ctypes.data,
+                                           None if hit is None else hit.ctypes.data, stats.ctypes.data))
+        return image, accum, hit, stats
+
+    def render_path_host(self, params, precision=F32, want_accum=True):
+        W, H = params.W, params.H
+        ft = np.float64 if precision == F64 else np.float32
+        image = np.zeros((H, W, 3), np.float32)
+        accum = np.zeros((H, W, 4), ft) if want_accum else None
+        stats = np.zeros(8, np.uint64)
+        check(lib().rt_render_path_host(self.handle, precision, C.byref(params), image.ctypes.data,
+                                        None if accum is None else accum.ctypes.data, stats.ctypes.data))
+        return image, accum, stats
+
+    # ---- batched primitives ----------------------------------------------------------------------
+    def trace_rays(self, rays, suppress=None, bounces0=None, through0=None, max_bounces=1, shadow_max_bounces=0,
+                   miss=(0, 0, 0), shade=True, precision=F64):
+        """Batch of ``Ray.nearestSphereIntersect`` (+ ``terminalRGB``): rays [m,6] -> (term [m,10], rgb [m,3] | None)."""
+        rays = _d(rays).reshape(-1, 6)
+        m = rays.shape[0]
+        dev = self.device
+        r = DeviceBuffer.from_host(rays, np.float64, dev)
+        sup = None if suppress is None else DeviceBuffer.from_host(np.asarray(suppress).reshape(m), np.int32, dev)
+        b0 = None if bounces0 is None else DeviceBuffer.from_host(np.asarray(bounces0).reshape(m), np.int32, dev)
+        t0 = None if through0 is None else DeviceBuffer.from_host(np.asarray(through0).reshape(m), np.int32, dev)
+        term = DeviceBuffer((m, 10), np.float64, dev)
+        rgb = DeviceBuffer((m, 3), np.float64, dev) if shade else None
+        missv = (C.c_double * 3)(*[float(c) for c in miss])
+        check(lib().rt_trace_rays(self.handle, precision, m, r.ptr, _ptr(sup), _ptr(b0), _ptr(t0), int(max_bounces),
+                                  int(shadow_max_bounces), missv, term.ptr, _ptr(rgb), None))
+        return term.download(), (rgb.download() if shade else None)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            try:
+                load_symbols().rt_scene_destroy(self.handle)
+            finally:
+                self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sphere_discriminant(rays, spheres, point=0, precision=F64, device=0):
+    """Batch of ``Ray.sphereDiscriminant``: rays [m,6], spheres [m,4] -> out [m,8] = hit, t, point(3), normal(3)."""
+    rays = _d(rays).reshape(-1, 6)
+    sph = _d(spheres).reshape(-1, 4)
+    m = rays.shape[0]
+    r, s = DeviceBuffer.from_host(rays, np.float64, device), DeviceBuffer.from_host(sph, np.float64, device)
+    out = DeviceBuffer((m, 8), np.float64, device)
+    check(lib().rt_sphere_discriminant(device, precision, m, r.ptr, s.ptr, int(point), out.ptr, None))
+    return out.download()

@@ -1,0 +1,613 @@
+// rt_api.cu -- the C ABI of librt_b200.so (include/rt_b200.h): scene handles resident in HBM, parameter marshalling
+// and stream-ordered launches of the kernels in rt_f32.cu / rt_f64.cu / rt_lbvh.cu.  No compute happens on the host.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_launch.h"
+#include "rt_lbvh_build.h"
+
+using namespace rt;
+
+#define RT_EXPORT extern "C" __attribute__((visibility("default")))
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what) {
+    return fail(RT_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// ------------------------------------------------------------------ handles
+template <typename T> struct SceneBufs {
+    void *blob = nullptr;
+    size_t bytes = 0;
+    SceneDev<T> view;
+};
+
+struct rt_scene {
+    int device = 0;
+    int n = 0, nG = 0, nP = 0, nL = 0;
+    SceneBufs<float> f;
+    SceneBufs<double> d;
+    uint8_t *small_dev = nullptr;
+    void *scratch = nullptr;      // X/Y grids of whitted frames
+    size_t scratch_bytes = 0;
+    LbvhStorage bvh;              // rt_lbvh_build.h
+};
+
+struct rt_env {
+    rt_scene *scene = nullptr;
+    int precision = RT_F32;
+    rt_env_desc desc;
+    void *blob = nullptr;
+    EnvDev<float> f;
+    EnvDev<double> d;
+};
+
+template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
+    const size_t v = sizeof(typename M<T>::v4);
+    size_t b = v * (3 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
+    b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
+    return (b + 255) & ~size_t(255);
+}
+
+// Pack the double SoA description into the vec4 arrays of one precision (layout: rt_common.cuh "scene views").
+template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector<unsigned char> &host, size_t bytes) {
+    using v4 = typename M<T>::v4;
+    host.assign(bytes, 0);
+    v4 *p = reinterpret_cast<v4 *>(host.data());
+    const int n = s->n, nG = s->nG, nP = s->nP, nL = s->nL;
+    v4 *sph = p; p += n;
+    v4 *mat = p; p += n;
+    v4 *col = p; p += n;
+    v4 *g_vec = p; p += nG;
+    v4 *g_col = p; p += nG;
+    v4 *p_pos = p; p += nP;
+    v4 *p_col = p; p += nP;
+    v4 *l_pos = p; p += nL;
+    v4 *l_col = p; p += nL;
+    int *q = reinterpret_cast<int *>(p);
+    int *ids = q; q += n;
+    int *g_func = q; q += nG;
+    int *p_id = q; q += nP;
+    int *p_func = q; q += nP;
+    int *l_index = q; q += nL;
+    for (int i = 0; i < n; ++i) {
+        sph[i].x = (T)s->centre[3 * i]; sph[i].y = (T)s->centre[3 * i + 1]; sph[i].z = (T)s->centre[3 * i + 2];
+        sph[i].w = (T)s->radius[i];
+        mat[i].x = (T)s->material[4 * i]; mat[i].y = (T)s->material[4 * i + 1]; mat[i].z = (T)s->material[4 * i + 2];
+        mat[i].w = (T)s->material[4 * i + 3];
+        col[i].x = (T)s->colour[3 * i]; col[i].y = (T)s->colour[3 * i + 1]; col[i].z = (T)s->colour[3 * i + 2];
+        col[i].w = (T)0;
+        ids[i] = s->ids[i];
+    }
+    for (int i = 0; i < nG; ++i) {
+        g_vec[i].x = (T)s->g_vec[3 * i]; g_vec[i].y = (T)s->g_vec[3 * i + 1]; g_vec[i].z = (T)s->g_vec[3 * i + 2];
+        g_vec[i].w = (T)s->g_max_angle[i];
+        g_col[i].x = (T)s->g_col[3 * i]; g_col[i].y = (T)s->g_col[3 * i + 1]; g_col[i].z = (T)s->g_col[3 * i + 2];
+        g_col[i].w = (T)s->g_strength[i];
+        g_func[i] = s->g_func[i];
+    }
+    for (int i = 0; i < nP; ++i) {
+        p_pos[i].x = (T)s->p_pos[3 * i]; p_pos[i].y = (T)s->p_pos[3 * i + 1]; p_pos[i].z = (T)s->p_pos[3 * i + 2];
+        p_pos[i].w = (T)s->p_max_angle[i];
+        p_col[i].x = (T)s->p_col[3 * i]; p_col[i].y = (T)s->p_col[3 * i + 1]; p_col[i].z = (T)s->p_col[3 * i + 2];
+        p_col[i].w = (T)s->p_strength[i];
+        p_id[i] = s->p_id[i]; p_func[i] = s->p_func[i];
+    }
+    for (int i = 0; i < nL; ++i) {
+        l_pos[i].x = (T)s->l_centre[3 * i]; l_pos[i].y = (T)s->l_centre[3 * i + 1]; l_pos[i].z = (T)s->l_centre[3 * i + 2];
+        l_pos[i].w = (T)0;
+        l_col[i].x = (T)s->l_colour[3 * i]; l_col[i].y = (T)s->l_colour[3 * i + 1]; l_col[i].z = (T)s->l_colour[3 * i + 2];
+        l_col[i].w = (T)0;
+        l_index[i] = s->l_index[i];
+    }
+}
+
+template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc *s, const uint8_t *small_dev) {
+    using v4 = typename M<T>::v4;
+    SceneDev<T> &v = b.view;
+    const int n = s->n, nG = s->nG, nP = s->nP, nL = s->nL;
+    v.n = n; v.nG = nG; v.nP = nP; v.nL = nL;
+    v4 *p = reinterpret_cast<v4 *>(b.blob);
+    v.sph = p; p += n;
+    v.mat = p; p += n;
+    v.col = p; p += n;
+    v.g_vec = p; p += nG;
+    v.g_col = p; p += nG;
+    v.p_pos = p; p += nP;
+    v.p_col = p; p += nP;
+    v.l_pos = p; p += nL;
+    v.l_col = p; p += nL;
+    int *q = reinterpret_cast<int *>(p);
+    v.ids = q; q += n;
+    v.g_func = q; q += nG;
+    v.p_id = q; q += nP;
+    v.p_func = q; q += nP;
+    v.l_index = q; q += nL;
+    v.small = small_dev;
+    v.bg[0] = (T)s->bg[0]; v.bg[1] = (T)s->bg[1]; v.bg[2] = (T)s->bg[2];
+    std::memset(&v.bvh, 0, sizeof v.bvh);
+}
+
+static int validate_desc(const rt_scene_desc *s) {
+    if (!s) return fail(RT_ERR_INVALID, "scene description is NULL");
+    if (s->n < 0 || s->nG < 0 || s->nP < 0 || s->nL < 0) return fail(RT_ERR_INVALID, "negative count in scene description");
+    if (s->n > 0 && (!s->centre || !s->radius || !s->material || !s->colour || !s->ids))
+        return fail(RT_ERR_INVALID, "sphere arrays missing");
+    if (s->nG > 0 && (!s->g_vec || !s->g_col || !s->g_strength || !s->g_max_angle || !s->g_func))
+        return fail(RT_ERR_INVALID, "global light arrays missing");
+    if (s->nP > 0 && (!s->p_id || !s->p_pos || !s->p_col || !s->p_strength || !s->p_max_angle || !s->p_func))
+        return fail(RT_ERR_INVALID, "point light arrays missing");
+    if (s->nL > 0 && (!s->l_centre || !s->l_colour || !s->l_index)) return fail(RT_ERR_INVALID, "light sphere arrays missing");
+    for (int i = 0; i < s->nL; ++i)
+        if (s->l_index[i] >= s->n) return fail(RT_ERR_INVALID, "l_index out of range");
+    return RT_OK;
+}
+
+static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
+    CU(cudaSetDevice(sc->device));
+    const bool same = sc->n == s->n && sc->nG == s->nG && sc->nP == s->nP && sc->nL == s->nL && sc->f.blob;
+    if (!same) {
+        if (sc->f.blob) CU(cudaFree(sc->f.blob));
+        if (sc->d.blob) CU(cudaFree(sc->d.blob));
+        if (sc->small_dev) CU(cudaFree(sc->small_dev));
+        sc->f.blob = sc->d.blob = nullptr; sc->small_dev = nullptr;
+        sc->f.bytes = scene_blob_bytes<float>(s->n, s->nG, s->nP, s->nL);
+        sc->d.bytes = scene_blob_bytes<double>(s->n, s->nG, s->nP, s->nL);
+        CU(cudaMalloc(&sc->f.blob, sc->f.bytes));
+        CU(cudaMalloc(&sc->d.blob, sc->d.bytes));
+        CU(cudaMalloc((void **)&sc->small_dev, (size_t)(s->n > 0 ? s->n : 1)));
+    }
+    sc->n = s->n; sc->nG = s->nG; sc->nP = s->nP; sc->nL = s->nL;
+    std::vector<unsigned char> hf, hd;
+    pack_scene<float>(s, hf, sc->f.bytes);
+    pack_scene<double>(s, hd, sc->d.bytes);
+    CU(cudaMemcpyAsync(sc->f.blob, hf.data(), sc->f.bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sc->d.blob, hd.data(), sc->d.bytes, cudaMemcpyHostToDevice, st));
+    std::vector<uint8_t> small((size_t)(s->n > 0 ? s->n : 1), 0);
+    if (s->small) std::memcpy(small.data(), s->small, (size_t)s->n);
+    CU(cudaMemcpyAsync(sc->small_dev, small.data(), small.size(), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));          // the staging vectors die at return
+    bind_view<float>(sc->f, s, sc->small_dev);
+    bind_view<double>(sc->d, s, sc->small_dev);
+    lbvh_drop(sc->bvh);                     // geometry changed: any hierarchy is stale
+    return RT_OK;
+}
+
+static int ensure_scratch(rt_scene *sc, size_t bytes) {
+    if (bytes <= sc->scratch_bytes) return RT_OK;
+    if (sc->scratch) CU(cudaFree(sc->scratch));
+    sc->scratch = nullptr; sc->scratch_bytes = 0;
+    size_t want = (bytes + 4095) & ~size_t(4095);
+    CU(cudaMalloc(&sc->scratch, want));
+    sc->scratch_bytes = want;
+    return RT_OK;
+}
+
+static inline cudaStream_t S(void *stream) { return reinterpret_cast<cudaStream_t>(stream); }
+
+// ------------------------------------------------------------------ library / device
+RT_EXPORT const char *rt_last_error(void) { return g_err.c_str(); }
+RT_EXPORT int rt_version(void) { return 100; }
+
+RT_EXPORT int rt_device_count(int *count) {
+    if (!count) return fail(RT_ERR_INVALID, "count is NULL");
+    cudaError_t e = cudaGetDeviceCount(count);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    return RT_OK;
+}
+
+RT_EXPORT int rt_device_props(int device, int64_t *props6, size_t *total_mem) {
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    int khz = 0;
+    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    if (props6) {
+        props6[0] = p.multiProcessorCount; props6[1] = p.major; props6[2] = p.minor; props6[3] = khz;
+        props6[4] = p.l2CacheSize; props6[5] = (int64_t)p.sharedMemPerBlockOptin;
+    }
+    if (total_mem) *total_mem = p.totalGlobalMem;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_dev_alloc(int device, size_t bytes, void **out_dev) {
+    if (!out_dev) return fail(RT_ERR_INVALID, "out_dev is NULL");
+    CU(cudaSetDevice(device));
+    cudaError_t e = cudaMalloc(out_dev, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(RT_ERR_NOMEM, "cudaMalloc: out of device memory"); }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    return RT_OK;
+}
+RT_EXPORT int rt_dev_free(int device, void *ptr_dev) {
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr_dev));
+    return RT_OK;
+}
+RT_EXPORT int rt_host_alloc_pinned(size_t bytes, void **out_host) {
+    if (!out_host) return fail(RT_ERR_INVALID, "out_host is NULL");
+    CU(cudaHostAlloc(out_host, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RT_OK;
+}
+RT_EXPORT int rt_host_free_pinned(void *ptr_host) {
+    CU(cudaFreeHost(ptr_host));
+    return RT_OK;
+}
+RT_EXPORT int rt_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes, void *stream) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, S(stream)));
+    return RT_OK;
+}
+RT_EXPORT int rt_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, S(stream)));
+    return RT_OK;
+}
+RT_EXPORT int rt_memset_dev(int device, void *dst_dev, int value, size_t bytes, void *stream) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemsetAsync(dst_dev, value, bytes, S(stream)));
+    return RT_OK;
+}
+RT_EXPORT int rt_stream_sync(int device, void *stream) {
+    CU(cudaSetDevice(device));
+    CU(cudaStreamSynchronize(S(stream)));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_measure_fp32_peak(int device, int repeats, double *tflops_out, double *ms_out) {
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    float *sink = nullptr;
+    CU(cudaMalloc((void **)&sink, 4));
+    const int blocks = p.multiProcessorCount * 2, threads = 1024, iters = 1 << 14;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    CU(launch_fp32_peak(blocks, threads, 256, sink, nullptr));           // warm-up
+    CU(cudaDeviceSynchronize());
+    double best_ms = 1e30;
+    for (int r = 0; r < (repeats > 0 ? repeats : 1); ++r) {
+        CU(cudaEventRecord(a, nullptr));
+        CU(launch_fp32_peak(blocks, threads, iters, sink, nullptr));
+        CU(cudaEventRecord(b, nullptr));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        if (ms < best_ms) best_ms = ms;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(sink);
+    const double flop = 2.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+    if (tflops_out) *tflops_out = flop / (best_ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best_ms;
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ scene
+RT_EXPORT int rt_scene_create(int device, const rt_scene_desc *desc, rt_scene **out) {
+    if (!out) return fail(RT_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDeviceCount");
+    if (device < 0 || device >= count) return fail(RT_ERR_INVALID, "no such CUDA device");
+    rt_scene *sc = new (std::nothrow) rt_scene();
+    if (!sc) return fail(RT_ERR_NOMEM, "host allocation failed");
+    sc->device = device;
+    rc = upload_scene(sc, desc, nullptr);
+    if (rc) { rt_scene_destroy(sc); return rc; }
+    *out = sc;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_scene_update(rt_scene *scene, const rt_scene_desc *desc, void *stream) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    int rc = validate_desc(desc);
+    if (rc) return rc;
+    return upload_scene(scene, desc, S(stream));
+}
+
+RT_EXPORT int rt_scene_destroy(rt_scene *scene) {
+    if (!scene) return RT_OK;
+    cudaSetDevice(scene->device);
+    lbvh_drop(scene->bvh);
+    if (scene->f.blob) cudaFree(scene->f.blob);
+    if (scene->d.blob) cudaFree(scene->d.blob);
+    if (scene->small_dev) cudaFree(scene->small_dev);
+    if (scene->scratch) cudaFree(scene->scratch);
+    delete scene;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_scene_info(const rt_scene *scene, int32_t *n_spheres, int32_t *device, int32_t *has_lbvh) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (n_spheres) *n_spheres = scene->n;
+    if (device) *device = scene->device;
+    if (has_lbvh) *has_lbvh = scene->bvh.view.nodes > 0;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_lbvh_build(rt_scene *scene, double huge_radius, void *stream) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    CU(cudaSetDevice(scene->device));
+    cudaError_t e = lbvh_build(scene->bvh, scene->f.view.sph, scene->n, (float)huge_radius, S(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "lbvh_build");
+    scene->f.view.bvh = scene->bvh.view;
+    scene->d.view.bvh = scene->bvh.view;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_lbvh_drop(rt_scene *scene) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    CU(cudaSetDevice(scene->device));
+    lbvh_drop(scene->bvh);
+    std::memset(&scene->f.view.bvh, 0, sizeof(BvhView));
+    std::memset(&scene->d.view.bvh, 0, sizeof(BvhView));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ batched primitives
+RT_EXPORT int rt_sphere_discriminant(int device, int precision, int m, const double *rays_dev, const double *spheres_dev,
+                                     int point, double *out_dev, void *stream) {
+    if (m < 0 || (m > 0 && (!rays_dev || !spheres_dev || !out_dev))) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    if (precision == RT_F64) CU(launch_sphere_disc<double>(m, rays_dev, spheres_dev, point, out_dev, S(stream)));
+    else if (precision == RT_F32) CU(launch_sphere_disc<float>(m, rays_dev, spheres_dev, point, out_dev, S(stream)));
+    else return fail(RT_ERR_INVALID, "unknown precision");
+    return RT_OK;
+}
+
+RT_EXPORT int rt_trace_rays(rt_scene *scene, int precision, int m, const double *rays_dev, const int32_t *suppress_dev,
+                            const int32_t *bounces0_dev, const int32_t *through0_dev, int max_bounces,
+                            int shadow_max_bounces, const double miss[3], double *term_dev, double *rgb_dev,
+                            void *stream) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (m < 0 || (m > 0 && (!rays_dev || !term_dev))) return fail(RT_ERR_INVALID, "bad arguments");
+    const double zero[3] = {0, 0, 0};
+    if (!miss) miss = zero;
+    CU(cudaSetDevice(scene->device));
+    if (precision == RT_F64)
+        CU(launch_trace_rays<double>(scene->d.view, m, rays_dev, suppress_dev, bounces0_dev, through0_dev, max_bounces,
+                                     shadow_max_bounces, miss, term_dev, rgb_dev, S(stream)));
+    else if (precision == RT_F32)
+        CU(launch_trace_rays<float>(scene->f.view, m, rays_dev, suppress_dev, bounces0_dev, through0_dev, max_bounces,
+                                    shadow_max_bounces, miss, term_dev, rgb_dev, S(stream)));
+    else return fail(RT_ERR_INVALID, "unknown precision");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ Algorithm A frame
+template <typename T>
+static int render_whitted_t(rt_scene *sc, const SceneDev<T> &view, const rt_whitted_params *p, void *accum, int32_t *hit,
+                            uint64_t *stats, cudaStream_t st) {
+    const size_t nx = (size_t)p->W, ny = (size_t)p->H;
+    int rc = ensure_scratch(sc, (nx + ny) * sizeof(T));
+    if (rc) return rc;
+    std::vector<T> grid(nx + ny);
+    for (size_t i = 0; i < nx; ++i) grid[i] = (T)p->X[i];
+    for (size_t i = 0; i < ny; ++i) grid[nx + i] = (T)p->Y[i];
+    CU(cudaMemcpyAsync(sc->scratch, grid.data(), (nx + ny) * sizeof(T), cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));      // `grid` is pageable and dies at return
+    WhittedDev<T> wp;
+    wp.cam[0] = (T)p->cam[0]; wp.cam[1] = (T)p->cam[1]; wp.cam[2] = (T)p->cam[2];
+    wp.X = reinterpret_cast<const T *>(sc->scratch);
+    wp.Y = wp.X + nx;
+    wp.W = p->W; wp.H = p->H; wp.y0 = p->y0; wp.y1 = p->y1; wp.s0 = p->s0; wp.s1 = p->s1; wp.spp = p->spp;
+    wp.max_bounces = p->max_bounces; wp.shadow_max_bounces = p->shadow_max_bounces;
+    wp.miss[0] = (T)p->miss[0]; wp.miss[1] = (T)p->miss[1]; wp.miss[2] = (T)p->miss[2];
+    wp.pitch_x = (T)(p->W > 1 ? p->X[1] - p->X[0] : 0.0);
+    wp.pitch_y = (T)(p->H > 1 ? p->Y[0] - p->Y[1] : 0.0);
+    wp.k0 = (uint32_t)p->seed; wp.k1 = (uint32_t)(p->seed >> 32);
+    wp.prenorm = p->prenormalise; wp.accumulate = p->accumulate;
+    CU(launch_whitted<T>(view, wp, accum, hit, reinterpret_cast<unsigned long long *>(stats), st));
+    return RT_OK;
+}
+
+static int check_band(int W, int H, int y0, int y1, int s0, int s1) {
+    if (W <= 0 || H <= 0) return fail(RT_ERR_INVALID, "image size must be positive");
+    if (y0 < 0 || y1 > H || y0 > y1) return fail(RT_ERR_INVALID, "row band outside the image");
+    if (s0 < 0 || s0 > s1) return fail(RT_ERR_INVALID, "bad sample range");
+    if ((long long)W * H > 0x7fffffffLL) return fail(RT_ERR_INVALID, "image too large");
+    return RT_OK;
+}
+
+RT_EXPORT int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted_params *p, void *accum_dev,
+                                int32_t *hit_dev, uint64_t *stats_dev, void *stream) {
+    if (!scene || !p || !accum_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (!p->X || !p->Y) return fail(RT_ERR_INVALID, "direction grids missing");
+    int rc = check_band(p->W, p->H, p->y0, p->y1, p->s0, p->s1);
+    if (rc) return rc;
+    CU(cudaSetDevice(scene->device));
+    if (precision == RT_F64) return render_whitted_t<double>(scene, scene->d.view, p, accum_dev, hit_dev, stats_dev, S(stream));
+    if (precision == RT_F32) return render_whitted_t<float>(scene, scene->f.view, p, accum_dev, hit_dev, stats_dev, S(stream));
+    return fail(RT_ERR_INVALID, "unknown precision");
+}
+
+// ------------------------------------------------------------------ Algorithm B frame
+template <typename T>
+static int render_path_t(const SceneDev<T> &view, const rt_path_params *p, void *accum, uint64_t *stats, cudaStream_t st) {
+    PathDev<T> pp;
+    pp.cam[0] = (T)p->cam[0]; pp.cam[1] = (T)p->cam[1]; pp.cam[2] = (T)p->cam[2];
+    pp.W = p->W; pp.H = p->H; pp.y0 = p->y0; pp.y1 = p->y1; pp.s0 = p->s0; pp.s1 = p->s1; pp.max_bounces = p->max_bounces;
+    // chandelier.py:412-415: aspect = W/H; half_height = tan(radians(fov)/2); half_width = half_height*aspect
+    const double aspect = (double)p->W / (double)p->H;
+    const double half_h = std::tan((p->fov_deg * (M_PI / 180.0)) / 2), half_w = half_h * aspect;
+    pp.aspect = (T)aspect; pp.half_w = (T)half_w; pp.half_h = (T)half_h;
+    pp.mirror_threshold = (T)p->mirror_threshold;
+    pp.k0 = (uint32_t)p->seed; pp.k1 = (uint32_t)(p->seed >> 32);
+    pp.accumulate = p->accumulate;
+    CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_render_path(rt_scene *scene, int precision, const rt_path_params *p, void *accum_dev, uint64_t *stats_dev,
+                             void *stream) {
+    if (!scene || !p || !accum_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_band(p->W, p->H, p->y0, p->y1, p->s0, p->s1);
+    if (rc) return rc;
+    if (p->max_bounces > RT_PATH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "max_bounces above 32 is not supported by the path kernel");
+    CU(cudaSetDevice(scene->device));
+    if (precision == RT_F64) return render_path_t<double>(scene->d.view, p, accum_dev, stats_dev, S(stream));
+    if (precision == RT_F32) return render_path_t<float>(scene->f.view, p, accum_dev, stats_dev, S(stream));
+    return fail(RT_ERR_INVALID, "unknown precision");
+}
+
+RT_EXPORT int rt_resolve(int device, int precision, const void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1,
+                         int32_t spp, float *image_dev, void *stream) {
+    if (!accum_dev || !image_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (spp <= 0) return fail(RT_ERR_INVALID, "spp must be positive");
+    int rc = check_band(W, H, y0, y1, 0, spp);
+    if (rc) return rc;
+    CU(cudaSetDevice(device));
+    if (precision == RT_F64) CU(launch_resolve<double>(accum_dev, W, y0, y1, spp, image_dev, S(stream)));
+    else if (precision == RT_F32) CU(launch_resolve<float>(accum_dev, W, y0, y1, spp, image_dev, S(stream)));
+    else return fail(RT_ERR_INVALID, "unknown precision");
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ host-buffer convenience entries
+struct DevTmp {
+    void *p = nullptr;
+    ~DevTmp() { if (p) cudaFree(p); }
+};
+
+static int render_host_common(rt_scene *scene, int precision, bool whitted, const void *params, float *image_host,
+                              void *accum_host, int32_t *hit_host, uint64_t *stats_host) {
+    if (!scene || !params) return fail(RT_ERR_INVALID, "NULL argument");
+    if (precision != RT_F32 && precision != RT_F64) return fail(RT_ERR_INVALID, "unknown precision");
+    const rt_whitted_params *wp = whitted ? (const rt_whitted_params *)params : nullptr;
+    const rt_path_params *pp = whitted ? nullptr : (const rt_path_params *)params;
+    const int W = whitted ? wp->W : pp->W, H = whitted ? wp->H : pp->H;
+    const int y0 = whitted ? wp->y0 : pp->y0, y1 = whitted ? wp->y1 : pp->y1;
+    const int s0 = whitted ? wp->s0 : pp->s0, s1 = whitted ? wp->s1 : pp->s1;
+    int rc = check_band(W, H, y0, y1, s0, s1);
+    if (rc) return rc;
+    CU(cudaSetDevice(scene->device));
+    const size_t px = (size_t)W * H, el = precision == RT_F64 ? sizeof(double) : sizeof(float);
+    DevTmp accum, image, hit, stats;
+    CU(cudaMalloc(&accum.p, px * 4 * el));
+    CU(cudaMemsetAsync(accum.p, 0, px * 4 * el, nullptr));
+    CU(cudaMalloc(&stats.p, 8 * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(stats.p, 0, 8 * sizeof(uint64_t), nullptr));
+    if (whitted && hit_host) {
+        CU(cudaMalloc(&hit.p, px * sizeof(int32_t)));
+        CU(cudaMemsetAsync(hit.p, 0xff, px * sizeof(int32_t), nullptr));
+    }
+    if (whitted) rc = rt_render_whitted(scene, precision, wp, accum.p, (int32_t *)hit.p, (uint64_t *)stats.p, nullptr);
+    else rc = rt_render_path(scene, precision, pp, accum.p, (uint64_t *)stats.p, nullptr);
+    if (rc) return rc;
+    if (image_host) {
+        CU(cudaMalloc(&image.p, px * 3 * sizeof(float)));
+        CU(cudaMemsetAsync(image.p, 0, px * 3 * sizeof(float), nullptr));
+        const int spp = s1 - s0 > 0 ? s1 - s0 : 1;
+        rc = rt_resolve(scene->device, precision, accum.p, W, H, y0, y1, spp, (float *)image.p, nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(image_host, image.p, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+    }
+    if (accum_host) CU(cudaMemcpyAsync(accum_host, accum.p, px * 4 * el, cudaMemcpyDeviceToHost, nullptr));
+    if (hit_host && hit.p) CU(cudaMemcpyAsync(hit_host, hit.p, px * sizeof(int32_t), cudaMemcpyDeviceToHost, nullptr));
+    if (stats_host) CU(cudaMemcpyAsync(stats_host, stats.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_render_whitted_host(rt_scene *scene, int precision, const rt_whitted_params *p, float *image_host,
+                                     void *accum_host, int32_t *hit_host, uint64_t *stats_host) {
+    return render_host_common(scene, precision, true, p, image_host, accum_host, hit_host, stats_host);
+}
+
+RT_EXPORT int rt_render_path_host(rt_scene *scene, int precision, const rt_path_params *p, float *image_host,
+                                  void *accum_host, uint64_t *stats_host) {
+    return render_host_common(scene, precision, false, p, image_host, accum_host, nullptr, stats_host);
+}
+
+// ------------------------------------------------------------------ batched RayTracerEnv
+template <typename T> static void bind_env(EnvDev<T> &e, const rt_env_desc &d, void *blob) {
+    const size_t B = (size_t)d.B;
+    e.B = d.B; e.W = d.W; e.H = d.H; e.max_bounces = d.max_bounces; e.flavour = d.flavour; e.sun_id = d.sun_id;
+    for (int k = 0; k < 3; ++k) { e.cam[k] = (T)d.cam[k]; e.cam_angle[k] = (T)d.cam_angle[k]; }
+    const double fr = d.fov * M_PI / 180;             // RL/ray_tracer_env.py:127
+    e.tan_half = (T)std::tan(fr / 2);
+    unsigned char *p = reinterpret_cast<unsigned char *>(blob);
+    e.total = reinterpret_cast<double *>(p); p += B * sizeof(double);
+    e.p = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
+    e.n = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
+    e.d = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
+    e.acc = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
+    e.has_hit = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.idx = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.bounce = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.through = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.episode = reinterpret_cast<int *>(p); p += B * sizeof(int);
+}
+
+RT_EXPORT int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out) {
+    if (!scene || !desc || !out) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (precision != RT_F32 && precision != RT_F64) return fail(RT_ERR_INVALID, "unknown precision");
+    if (desc->B <= 0 || desc->W <= 0 || desc->H <= 0) return fail(RT_ERR_INVALID, "B, W, H must be positive");
+    if (desc->flavour != RT_ENV_RL && desc->flavour != RT_ENV_FB) return fail(RT_ERR_INVALID, "unknown env flavour");
+    CU(cudaSetDevice(scene->device));
+    rt_env *env = new (std::nothrow) rt_env();
+    if (!env) return fail(RT_ERR_NOMEM, "host allocation failed");
+    env->scene = scene; env->precision = precision; env->desc = *desc;
+    const size_t B = (size_t)desc->B, el = precision == RT_F64 ? sizeof(double) : sizeof(float);
+    const size_t bytes = B * sizeof(double) + 12 * B * el + 5 * B * sizeof(int);
+    cudaError_t e = cudaMalloc(&env->blob, bytes);
+    if (e != cudaSuccess) { delete env; cudaGetLastError(); return e == cudaErrorMemoryAllocation ? fail(RT_ERR_NOMEM, "out of device memory") : cuda_fail(e, "cudaMalloc"); }
+    e = cudaMemset(env->blob, 0, bytes);
+    if (e != cudaSuccess) { cudaFree(env->blob); delete env; return cuda_fail(e, "cudaMemset"); }
+    if (precision == RT_F64) bind_env<double>(env->d, *desc, env->blob);
+    else bind_env<float>(env->f, *desc, env->blob);
+    *out = env;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_env_destroy(rt_env *env) {
+    if (!env) return RT_OK;
+    cudaSetDevice(env->scene->device);
+    if (env->blob) cudaFree(env->blob);
+    delete env;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_env_reset(rt_env *env, const int32_t *pixels_dev, const uint8_t *mask_dev, uint64_t seed, float *obs_dev,
+                           int32_t *pixels_out_dev, void *stream) {
+    if (!env || !obs_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(env->scene->device));
+    if (env->precision == RT_F64)
+        CU(launch_env_reset<double>(env->scene->d.view, env->d, pixels_dev, mask_dev, seed, obs_dev, pixels_out_dev, nullptr, S(stream)));
+    else
+        CU(launch_env_reset<float>(env->scene->f.view, env->f, pixels_dev, mask_dev, seed, obs_dev, pixels_out_dev, nullptr, S(stream)));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev, double *reward_dev, uint8_t *terminated_dev,
+                          uint8_t *truncated_dev, int32_t *reason_dev, double *info_dev, uint64_t *stats_dev, void *stream) {
+    if (!env || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev || !reason_dev)
+        return fail(RT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(env->scene->device));
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (env->precision == RT_F64)
+        CU(launch_env_step<double>(env->scene->d.view, env->d, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev,
+                                   reason_dev, info_dev, st, S(stream)));
+    else
+        CU(launch_env_step<float>(env->scene->f.view, env->f, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev,
+                                  reason_dev, info_dev, st, S(stream)));
+    return RT_OK;
+}

@@ -8,11 +8,13 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include "rt_lbvh.cuh"
 
 namespace rt {
 
 #define RT_DEV __device__ __forceinline__
 #define RT_NO_ID_DEV INT32_MIN
+#define RT_PATH_MAX_DEPTH 32     /* deepest TraditionalRenderer recursion the path kernel unrolls */
 
 // ------------------------------------------------------------------ math traits
 template <typename T> struct M;
@@ -126,8 +128,8 @@ struct PathRng {
     uint32_t pixel, sample, k0, k1;
     uint32_t c2, c3;       // cached words 2,3
     uint32_t cached_pair;  // pair index the cache belongs to (0xffffffff = none)
-    RT_DEV void begin(uint32_t pix, uint32_t smp, uint64_t seed) {
-        pixel = pix; sample = smp; k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); cached_pair = 0xffffffffu;
+    RT_DEV void begin(uint32_t pix, uint32_t smp, uint32_t key0, uint32_t key1) {
+        pixel = pix; sample = smp; k0 = key0; k1 = key1; cached_pair = 0xffffffffu;
     }
     RT_DEV void pair(uint32_t slot, uint32_t &a, uint32_t &b) {
         uint32_t pr = slot >> 1;
@@ -153,12 +155,7 @@ template <typename T> struct SceneDev {
     const v4 *l_pos, *l_col; const int *l_index;
     const uint8_t *small;
     T bg[3];
-    // LBVH (optional): nodes in two arrays; see rt_lbvh.cuh
-    int bvh_nodes;            // 0 = no BVH
-    const float4 *bvh_lo;     // [nodes] aabb min xyz, w = left child (as int bits; <0 => leaf ~idx)
-    const float4 *bvh_hi;     // [nodes] aabb max xyz, w = right child
-    const int *bvh_prims;     // sorted primitive (sphere) indices
-    int n_huge; const int *huge;   // spheres kept out of the BVH
+    BvhView bvh;              // optional LBVH, see rt_lbvh.cuh
 };
 
 // sphere arrays as the tracing functions see them (shared-memory staged or global)

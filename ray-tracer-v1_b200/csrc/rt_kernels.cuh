@@ -1,0 +1,646 @@
+// rt_kernels.cuh -- the CUDA kernels of the hot path (templates; instantiated for float in rt_f32.cu and for
+// double, without FMA contraction, in rt_f64.cu) and their launchers.
+//
+//   whitted_kernel   Algorithm A frame: camera ray -> nearestSphereIntersect -> terminalRGB, spp accumulation
+//   path_kernel      Algorithm B frame: TraditionalRenderer.render, persistent per-pixel threads that regenerate
+//                    the next sample as soon as a path ends, so every loop trip of a warp is one nearest-hit query
+//   trace_rays_kernel / sphere_disc_kernel   batched Ray.nearestSphereIntersect / sphereDiscriminant
+//   env_reset_kernel / env_step_kernel       batched RayTracerEnv
+//   resolve_kernel   sums -> float32 image
+//
+// Thread mapping for frames: 256-thread blocks cover 32 x 8 pixels; each warp owns an 8 x 4 pixel tile so primary
+// rays of a warp are spatially coherent and the float4 accumulator rows it writes are full 128-byte segments.
+#pragma once
+#include "rt_trace.cuh"
+#include "rt_launch.h"
+
+namespace rt {
+
+// ------------------------------------------------------------------ scene staging
+template <typename T> struct Staged {
+    Geo<T> g;
+    LightsA<T> la;
+    LightsB<T> lb;
+};
+
+template <typename T> __host__ __device__ inline size_t align32(size_t x) { return (x + 31) & ~size_t(31); }
+
+// bytes of dynamic shared memory the staged scene needs (host + device agree on the layout)
+template <typename T> __host__ __device__ inline size_t scene_smem_bytes(int n, int nG, int nP, int nL) {
+    const size_t v = sizeof(typename M<T>::v4);
+    size_t b = 0;
+    b += 3 * (size_t)n * v;                 // sph, mat, col
+    b += 2 * (size_t)nG * v + 2 * (size_t)nP * v + 2 * (size_t)nL * v;
+    b = align32<T>(b);
+    b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
+    return align32<T>(b);
+}
+
+template <typename T> RT_DEV void coop_copy(T *dst, const T *src, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
+}
+
+template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &sc, unsigned char *smem, Staged<T> &S) {
+    using v4 = typename M<T>::v4;
+    S.g.sv.n = sc.n;
+    S.g.bvh = sc.bvh;
+    S.la.nG = sc.nG; S.la.nP = sc.nP; S.lb.nL = sc.nL;
+    S.la.bg[0] = sc.bg[0]; S.la.bg[1] = sc.bg[1]; S.la.bg[2] = sc.bg[2];
+    if constexpr (kShared) {
+        v4 *p = reinterpret_cast<v4 *>(smem);
+        v4 *sph = p; p += sc.n;
+        v4 *mat = p; p += sc.n;
+        v4 *col = p; p += sc.n;
+        v4 *g_vec = p; p += sc.nG;
+        v4 *g_col = p; p += sc.nG;
+        v4 *p_pos = p; p += sc.nP;
+        v4 *p_col = p; p += sc.nP;
+        v4 *l_pos = p; p += sc.nL;
+        v4 *l_col = p; p += sc.nL;
+        size_t off = align32<T>((size_t)(reinterpret_cast<unsigned char *>(p) - smem));
+        int *q = reinterpret_cast<int *>(smem + off);
+        int *ids = q; q += sc.n;
+        int *g_func = q; q += sc.nG;
+        int *p_id = q; q += sc.nP;
+        int *p_func = q; q += sc.nP;
+        int *l_index = q; q += sc.nL;
+        coop_copy(sph, sc.sph, sc.n); coop_copy(mat, sc.mat, sc.n); coop_copy(col, sc.col, sc.n);
+        coop_copy(ids, sc.ids, sc.n);
+        coop_copy(g_vec, sc.g_vec, sc.nG); coop_copy(g_col, sc.g_col, sc.nG); coop_copy(g_func, sc.g_func, sc.nG);
+        coop_copy(p_pos, sc.p_pos, sc.nP); coop_copy(p_col, sc.p_col, sc.nP);
+        coop_copy(p_id, sc.p_id, sc.nP); coop_copy(p_func, sc.p_func, sc.nP);
+        coop_copy(l_pos, sc.l_pos, sc.nL); coop_copy(l_col, sc.l_col, sc.nL); coop_copy(l_index, sc.l_index, sc.nL);
+        __syncthreads();
+        S.g.sv.sph = sph; S.g.sv.mat = mat; S.g.sv.col = col; S.g.sv.ids = ids;
+        S.la.g_vec = g_vec; S.la.g_col = g_col; S.la.g_func = g_func;
+        S.la.p_pos = p_pos; S.la.p_col = p_col; S.la.p_id = p_id; S.la.p_func = p_func;
+        S.lb.l_pos = l_pos; S.lb.l_col = l_col; S.lb.l_index = l_index;
+    } else {
+        S.g.sv.sph = sc.sph; S.g.sv.mat = sc.mat; S.g.sv.col = sc.col; S.g.sv.ids = sc.ids;
+        S.la.g_vec = sc.g_vec; S.la.g_col = sc.g_col; S.la.g_func = sc.g_func;
+        S.la.p_pos = sc.p_pos; S.la.p_col = sc.p_col; S.la.p_id = sc.p_id; S.la.p_func = sc.p_func;
+        S.lb.l_pos = sc.l_pos; S.lb.l_col = sc.l_col; S.lb.l_index = sc.l_index;
+    }
+}
+
+// pixel of this thread inside the launch's row band: 32x8 block tile, 8x4 warp tile
+RT_DEV void tile_pixel(int &x, int &y_rel) {
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    x = blockIdx.x * 32 + (w & 3) * 8 + (lane & 7);
+    y_rel = blockIdx.y * 8 + (w >> 2) * 4 + (lane >> 3);
+}
+
+RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long v) {
+    v = warp_sum(v);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + slot, v);
+}
+
+// ------------------------------------------------------------------ Algorithm A frame
+template <typename T, bool kShared>
+__global__ void __launch_bounds__(256) whitted_kernel(SceneDev<T> sc, WhittedDev<T> wp, typename M<T>::v4 *accum,
+                                                      int *hit_out, unsigned long long *stats) {
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    int x, yr;
+    tile_pixel(x, yr);
+    const int y = wp.y0 + yr;
+    Counters ct = {0u, 0u, 0u};
+    unsigned primaries = 0;
+    if (x < wp.W && y < wp.y1) {
+        const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
+        const T X0 = wp.X[x], Y0 = wp.Y[y];
+        const uint32_t pixel = (uint32_t)(y * wp.W + x);
+        T a0 = T(0), a1 = T(0), a2 = T(0);
+        int last = -1;
+        for (int s = wp.s0; s < wp.s1; ++s) {
+            T Xj = X0, Yj = Y0;
+            if (wp.spp > 1) {                                            // output5.py:1463-1470
+                Philox4 o = philox4x32_10(pixel, (uint32_t)s, 0u, RT_PHILOX_TAG, wp.k0, wp.k1);
+                Xj = X0 + (u01<T>(o.w[0]) - T(0.5)) * wp.pitch_x;
+                Yj = Y0 + (u01<T>(o.w[1]) - T(0.5)) * wp.pitch_y;
+            }
+            V3<T> d = mk<T>(Xj, Yj, T(-1));
+            if constexpr (M<T>::exact) { if (wp.prenorm) d = normalise(d); }
+            d = normalise(d);                                            // Ray.__init__, ray.py:69-71
+            Hit<T> h = trace_terminal<T>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct);
+            primaries++;
+            T c[3];
+            if (h.idx >= 0) { terminal_rgb<T>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); last = h.idx; }
+            else { c[0] = wp.miss[0]; c[1] = wp.miss[1]; c[2] = wp.miss[2]; last = -1; }
+            a0 += c[0]; a1 += c[1]; a2 += c[2];
+        }
+        const size_t o = (size_t)y * wp.W + x;
+        typename M<T>::v4 out = M<T>::make4(a0, a1, a2, T(wp.s1 - wp.s0));
+        if (wp.accumulate) {
+            const typename M<T>::v4 old = accum[o];
+            out.x += old.x; out.y += old.y; out.z += old.z; out.w += old.w;
+        }
+        accum[o] = out;
+        if (hit_out) hit_out[o] = last;
+    }
+    if (stats) {
+        flush_stats(stats, STAT_QUERIES, ct.queries);
+        flush_stats(stats, STAT_RAYS, primaries);
+        flush_stats(stats, STAT_SPHERE_TESTS, ct.tests);
+        flush_stats(stats, STAT_AABB_TESTS, ct.boxes);
+    }
+}
+
+// ------------------------------------------------------------------ Algorithm B frame
+// TraditionalRenderer.generate_camera_ray (chandelier.py:417-429): aspect is applied twice on x.
+template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, int y, T u0, T u1) {
+    T sx = T(0.5) + (u0 - T(0.5)), sy = T(0.5) + (u1 - T(0.5));         // 0.5 + jitter, chandelier.py:534-536
+    T ndc_x = (T(x) + sx) / T(pp.W), ndc_y = (T(y) + sy) / T(pp.H);
+    T scx = T(2) * ndc_x - T(1), scy = T(1) - T(2) * ndc_y;
+    scx *= pp.aspect; scx *= pp.half_w; scy *= pp.half_h;
+    V3<T> d = normalise(mk<T>(scx, scy, T(-1)));
+    if constexpr (M<T>::exact) d = normalise(d);                         // Ray() normalises again
+    return d;
+}
+
+template <typename T, bool kShared>
+__global__ void __launch_bounds__(256) path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum,
+                                                   unsigned long long *stats) {
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    int x, yr;
+    tile_pixel(x, yr);
+    const int y = pp.y0 + yr;
+    unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
+    if (x < pp.W && y < pp.y1 && pp.s0 < pp.s1) {
+        const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
+        const uint32_t pixel = (uint32_t)(y * pp.W + x);
+        PathStack st;
+        PathRng rng;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;           // integer-valued sums: exact in double for any spp
+        if (pp.max_bounces <= 0) {                     // degenerate: every call returns at the depth check
+            const int ns = pp.s1 - pp.s0;
+            n_rays = (unsigned)ns; a0 = 2.0 * ns; a1 = 2.0 * ns; a2 = 5.0 * ns;
+        } else {
+        int s = pp.s0, depth = 0;
+        V3<T> O = cam, D;
+        {
+            rng.begin(pixel, (uint32_t)s, pp.k0, pp.k1);
+            uint32_t wa, wb;
+            rng.pair(0u, wa, wb);
+            D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
+        }
+        n_rays = 1;                                    // trace_ray_traditional call count, chandelier.py:432
+        for (;;) {
+            // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
+            T t;
+            n_query++;
+            const int i = nearest<T, true>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes);
+            double leaf[3];
+            bool ended;
+            if (i < 0) { leaf[0] = 2.0; leaf[1] = 2.0; leaf[2] = 5.0; ended = true; }          // miss: Colour(2,2,5)
+            else {
+                n_inter++;
+                const typename M<T>::v4 m = S.g.sv.mat[i];
+                if (m.z != T(0)) {                                                              // emissive: its colour
+                    n_light++;
+                    if (sc.small && sc.small[i]) n_small++;
+                    const typename M<T>::v4 col = S.g.sv.col[i];
+                    leaf[0] = (double)col.x; leaf[1] = (double)col.y; leaf[2] = (double)col.z;
+                    ended = true;
+                } else {
+                    Hit<T> h;
+                    finish_hit<T>(S.g, O, D, i, t, h);
+                    st.idx[depth] = (uint32_t)i;
+                    st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
+                    const bool mirror = m.x > pp.mirror_threshold;
+                    T r1 = T(0), r2 = T(0);
+                    if (!mirror) {
+                        uint32_t wa, wb;
+                        rng.pair((uint32_t)depth + 1u, wa, wb);
+                        r1 = u01<T>(wa); r2 = u01<T>(wb);
+                    }
+                    D = bounce_direction<T>(D, h.n, mirror, r1, r2);
+                    O = h.p + h.n * T(0.001);
+                    depth++;
+                    n_rays++;                                                                   // the recursive call
+                    ended = depth >= pp.max_bounces;                                            // ... returns (2,2,5)
+                    if (ended) { leaf[0] = 2.0; leaf[1] = 2.0; leaf[2] = 5.0; }
+                }
+            }
+            if (!ended) continue;
+            fold_path<T>(S.g, st, depth, leaf);
+            a0 += leaf[0]; a1 += leaf[1]; a2 += leaf[2];
+            if (++s >= pp.s1) break;
+            // ---- regenerate: next sample of this pixel
+            depth = 0; O = cam;
+            rng.begin(pixel, (uint32_t)s, pp.k0, pp.k1);
+            uint32_t wa, wb;
+            rng.pair(0u, wa, wb);
+            D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
+            n_rays++;
+        }
+        }
+        const size_t o = (size_t)y * pp.W + x;
+        typename M<T>::v4 out = M<T>::make4(T(a0), T(a1), T(a2), T(pp.s1 - pp.s0));
+        if (pp.accumulate) {
+            const typename M<T>::v4 old = accum[o];
+            out.x += old.x; out.y += old.y; out.z += old.z; out.w += old.w;
+        }
+        accum[o] = out;
+    }
+    if (stats) {
+        flush_stats(stats, STAT_RAYS, n_rays);
+        flush_stats(stats, STAT_INTER, n_inter);
+        flush_stats(stats, STAT_LIGHT, n_light);
+        flush_stats(stats, STAT_SMALL, n_small);
+        flush_stats(stats, STAT_QUERIES, n_query);
+        flush_stats(stats, STAT_SPHERE_TESTS, n_tests);
+        flush_stats(stats, STAT_AABB_TESTS, n_boxes);
+    }
+}
+
+// ------------------------------------------------------------------ resolve
+// pixel // spp then min(1, /255) (chandelier.py:540-549; output5.py:1500-1512)
+template <typename T>
+__global__ void resolve_kernel(const typename M<T>::v4 *accum, int W, int y0, int y1, int spp, float *image) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t n = (size_t)(y1 - y0) * W;
+    if (i >= n) return;
+    const size_t o = (size_t)y0 * W + i;
+    const typename M<T>::v4 a = accum[o];
+    const double s = (double)spp;
+    double r = floor((double)a.x / s) / 255.0, g = floor((double)a.y / s) / 255.0, b = floor((double)a.z / s) / 255.0;
+    image[3 * o + 0] = (float)(r < 1.0 ? r : 1.0);
+    image[3 * o + 1] = (float)(g < 1.0 ? g : 1.0);
+    image[3 * o + 2] = (float)(b < 1.0 ? b : 1.0);
+}
+
+// ------------------------------------------------------------------ batched primitives
+template <typename T>
+__global__ void sphere_disc_kernel(int m, const double *rays, const double *spheres, int point, double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double *r = rays + 6 * (size_t)i, *s = spheres + 4 * (size_t)i;
+    V3<T> O = mk<T>(T(r[0]), T(r[1]), T(r[2]));
+    V3<T> D = normalise(mk<T>(T(r[3]), T(r[4]), T(r[5])));
+    typename M<T>::v4 sp = M<T>::make4(T(s[0]), T(s[1]), T(s[2]), T(s[3]));
+    T t;
+    double *o = out + 8 * (size_t)i;
+    if (!sphere_test<T>(O, D, sp, point, t)) { for (int k = 0; k < 8; ++k) o[k] = 0.0; return; }
+    V3<T> p = O + D * t, n = normalise(p - centre_of<T>(sp));
+    o[0] = 1.0; o[1] = (double)t; o[2] = (double)p.x; o[3] = (double)p.y; o[4] = (double)p.z;
+    o[5] = (double)n.x; o[6] = (double)n.y; o[7] = (double)n.z;
+}
+
+template <typename T, bool kShared>
+__global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, const double *rays, const int *suppress,
+                                                         const int *bounces0, const int *through0, int max_bounces,
+                                                         int shadow_max_bounces, double miss0, double miss1,
+                                                         double miss2, double *term, double *rgb) {
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double *r = rays + 6 * (size_t)i;
+    V3<T> O = mk<T>(T(r[0]), T(r[1]), T(r[2]));
+    V3<T> D = normalise(mk<T>(T(r[3]), T(r[4]), T(r[5])));
+    Counters ct = {0u, 0u, 0u};
+    Hit<T> h = trace_terminal<T>(S.g, O, D, suppress ? suppress[i] : RT_NO_ID_DEV, bounces0 ? bounces0[i] : 0,
+                                 max_bounces, through0 ? through0[i] : 0, ct);
+    double *t = term + 10 * (size_t)i;
+    t[0] = h.idx >= 0 ? 1.0 : 0.0; t[1] = (double)h.idx; t[2] = (double)h.bounces; t[3] = (double)h.through;
+    t[4] = (double)h.p.x; t[5] = (double)h.p.y; t[6] = (double)h.p.z;
+    t[7] = (double)h.n.x; t[8] = (double)h.n.y; t[9] = (double)h.n.z;
+    if (rgb) {
+        double *c = rgb + 3 * (size_t)i;
+        if (h.idx >= 0) {
+            T o[3];
+            terminal_rgb<T>(S.g, S.la, h, shadow_max_bounces, o, ct);
+            c[0] = (double)o[0]; c[1] = (double)o[1]; c[2] = (double)o[2];
+        } else { c[0] = miss0; c[1] = miss1; c[2] = miss2; }
+    }
+}
+
+// ------------------------------------------------------------------ batched RayTracerEnv
+template <typename T> RT_DEV void env_load_hit(const EnvDev<T> &e, int b, Hit<T> &h) {
+    const size_t B = (size_t)e.B;
+    h.idx = e.has_hit[b] ? e.idx[b] : -1;
+    h.p = mk<T>(e.p[b], e.p[B + b], e.p[2 * B + b]);
+    h.n = mk<T>(e.n[b], e.n[B + b], e.n[2 * B + b]);
+    h.t = T(0); h.bounces = 0; h.through = 0;
+}
+
+template <typename T> RT_DEV void env_store_hit(const EnvDev<T> &e, int b, const Hit<T> &h, V3<T> D) {
+    const size_t B = (size_t)e.B;
+    e.has_hit[b] = h.idx >= 0; e.idx[b] = h.idx;
+    e.p[b] = h.p.x; e.p[B + b] = h.p.y; e.p[2 * B + b] = h.p.z;
+    e.n[b] = h.n.x; e.n[B + b] = h.n.y; e.n[2 * B + b] = h.n.z;
+    e.d[b] = D.x; e.d[B + b] = D.y; e.d[2 * B + b] = D.z;
+}
+
+// _get_observation (RL/ray_tracer_env.py:184-222): 18 x float32
+template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, int b, float *obs) {
+    const size_t B = (size_t)e.B;
+    float *o = obs + 18 * (size_t)b;
+    if (!e.has_hit[b]) {
+#pragma unroll
+        for (int k = 0; k < 18; ++k) o[k] = 0.f;
+        return;
+    }
+    const typename M<T>::v4 m = g.sv.mat[e.idx[b]];
+    o[0] = (float)e.p[b]; o[1] = (float)e.p[B + b]; o[2] = (float)e.p[2 * B + b];
+    o[3] = (float)e.d[b]; o[4] = (float)e.d[B + b]; o[5] = (float)e.d[2 * B + b];
+    o[6] = (float)e.n[b]; o[7] = (float)e.n[B + b]; o[8] = (float)e.n[2 * B + b];
+    o[9] = (float)m.x; o[10] = (float)m.y; o[11] = (float)m.z; o[12] = (float)m.w;
+    o[13] = (float)(e.acc[b] / T(255)); o[14] = (float)(e.acc[B + b] / T(255)); o[15] = (float)(e.acc[2 * B + b] / T(255));
+    o[16] = (float)e.bounce[b]; o[17] = (float)e.through[b];
+}
+
+// RL _calculate_reward (RL/ray_tracer_env.py:224-252); FB _calculate_reward (FB/ray_tracer_env.py:241-278)
+template <typename T>
+RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, const Hit<T> &h, int bounce_count,
+                         Counters &ct) {
+    if (h.idx < 0) return -0.1;
+    if (e.flavour == 1 && g.sv.ids[h.idx] == e.sun_id) return 10.0;
+    T c[3];
+    terminal_rgb<T>(g, la, h, 0, c, ct);
+    if constexpr (M<T>::exact) {
+        double brightness = (c[0] + c[1] + c[2]) / (3 * 255);
+        double pen = -0.01 * bounce_count;
+        return brightness + pen;
+    } else {
+        return (double)((c[0] + c[1] + c[2]) * (1.f / 765.f) - 0.01f * (float)bounce_count);
+    }
+}
+
+// FB _calculate_lighting_reward (FB/ray_tracer_env.py:280-336)
+template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const EnvDev<T> &e, const Hit<T> &h) {
+    if (h.idx < 0) return 0.0;
+    if (g.sv.mat[h.idx].z != T(0)) return 0.0;
+    int sun = -1;
+    for (int i = 0; i < g.sv.n; ++i) if (g.sv.ids[i] == e.sun_id) { sun = i; break; }
+    if (sun < 0) return 0.1;
+    const V3<T> sc = centre_of<T>(g.sv.sph[sun]);
+    V3<T> to_sun = normalise(sc - h.p);
+    T ca = dot(h.n, to_sun);
+    if (!(ca > T(0))) ca = T(0);
+    const V3<T> so = h.p + h.n * T(0.001);
+    const V3<T> sd = M<T>::exact ? normalise(to_sun) : to_sun;
+    const T sun_dist = mag(sc - h.p);
+    bool shadow = false;
+    for (int i = 0; i < g.sv.n && !shadow; ++i) {
+        if (i == h.idx || g.sv.ids[i] == e.sun_id) continue;
+        T t;
+        if (!sphere_test<T>(so, sd, g.sv.sph[i], 0, t)) continue;
+        const V3<T> ip = so + sd * t;
+        if (mag(ip - h.p) < sun_dist) shadow = true;
+    }
+    return shadow ? 0.3 : 0.3 + 0.7 * (double)ca;
+}
+
+// reset (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142).  pixels == NULL: draw with Philox(seed) keyed by
+// the env index.  mask != NULL: only envs with mask[b] != 0 are reset.
+template <typename T, bool kShared>
+__global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T> e, const int *pixels,
+                                                        const uint8_t *mask, uint32_t k0, uint32_t k1, float *obs,
+                                                        int *pixels_out, unsigned long long *stats) {
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ct = {0u, 0u, 0u};
+    if (b < e.B && (!mask || mask[b])) {
+        const size_t B = (size_t)e.B;
+        int px, py;
+        if (pixels) { px = pixels[2 * b]; py = pixels[2 * b + 1]; }
+        else {
+            Philox4 o = philox4x32_10((uint32_t)b, e.episode ? (uint32_t)e.episode[b] : 0u, 0u, 0x52544556u /* "RTEV" */, k0, k1);
+            px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
+            py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
+        }
+        if (e.episode) e.episode[b] += 1;
+        if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
+        const T aspect = T(e.W) / T(e.H);
+        const T x = (T(2) * (T(px) + T(0.5)) / T(e.W) - T(1)) * aspect * e.tan_half;
+        const T y = (T(1) - T(2) * (T(py) + T(0.5)) / T(e.H)) * e.tan_half;
+        V3<T> d = normalise(mk<T>(x, y, T(-1)));
+        if (e.cam_angle[0] != T(0) || e.cam_angle[1] != T(0) || e.cam_angle[2] != T(0))
+            d = rotate<T>(d, mk<T>(e.cam_angle[0], e.cam_angle[1], e.cam_angle[2]));
+        d = normalise(d);
+        Hit<T> h = trace_terminal<T>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
+        env_store_hit<T>(e, b, h, d);
+        e.bounce[b] = 0; e.through[b] = 0;
+        e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
+        e.total[b] = 0.0;
+        env_obs<T>(S.g, e, b, obs);
+    }
+    if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
+}
+
+// step (RL/ray_tracer_env.py:295-401, FB/ray_tracer_env.py:378-514)
+template <typename T, bool kShared>
+__global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
+                                                       double *reward, uint8_t *terminated, uint8_t *truncated,
+                                                       int *reason, double *info, unsigned long long *stats) {
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ct = {0u, 0u, 0u};
+    if (b < e.B) {
+        const size_t B = (size_t)e.B;
+        Hit<T> cur;
+        env_load_hit<T>(e, b, cur);
+        int bc = e.bounce[b];
+        const int through = e.through[b];
+        int rsn = 0, term = 0, trunc = 0;
+        double rw = 0.0, info_total, info_sun = -1.0;
+        int info_bounce = bc;
+        if (cur.idx < 0) {                                                   // ray already missed, :313-323
+            rsn = 1; rw = -1.0; term = 1; info_total = e.total[b];
+        } else if (bc >= e.max_bounces) {                                    // :325-337
+            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T>(S.g, S.la, e, cur, bc, ct);
+            e.total[b] += rw; info_total = e.total[b];
+            rsn = 3; term = 1; trunc = 1;
+        } else if (e.flavour == 1 && S.g.sv.ids[cur.idx] == e.sun_id) {      // FB :417-431 (total_reward not updated)
+            rsn = 5; rw = 10.0; term = 1; info_total = e.total[b] + rw; info_sun = 1.0;
+        } else {
+            // _action_to_direction: RL :144-182, FB :157-198
+            T theta, phi;
+            if (e.flavour == 1) {
+                theta = (T(actions[2 * b]) + T(1)) * T(3.14159265358979323846) / T(4);
+                phi = T(actions[2 * b + 1]) * T(3.14159265358979323846);
+            } else { theta = T(actions[2 * b]); phi = T(actions[2 * b + 1]); }
+            T st_, ct_, sp_, cp_;
+            M<T>::sincos(theta, &st_, &ct_); M<T>::sincos(phi, &sp_, &cp_);
+            const T lx = st_ * cp_, ly = st_ * sp_, lz = ct_;
+            const V3<T> n = cur.n;
+            V3<T> tg = M<T>::fabs(n.z) < T(0.9) ? cross(mk<T>(0, 0, 1), n) : cross(mk<T>(1, 0, 0), n);
+            tg = normalise(tg);
+            const V3<T> bt = normalise(cross(n, tg));
+            V3<T> D = normalise(mk<T>(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y,
+                                      lx * tg.z + ly * bt.z + lz * n.z));
+            if constexpr (M<T>::exact) D = normalise(D);                      // Ray() normalises again
+            bc += 1;
+            Hit<T> nx = trace_terminal<T>(S.g, cur.p, D, S.g.sv.ids[cur.idx], bc, e.max_bounces, through, ct);
+            if (e.flavour == 0) rw = env_reward<T>(S.g, S.la, e, cur, bc, ct);    // reward at the PRE-update hit, :362
+            else if (nx.idx >= 0) {
+                if (S.g.sv.ids[nx.idx] == e.sun_id) { rw = 10.0; rsn = 4; term = 1; info_sun = 1.0; }
+                else { rw = env_lighting_reward<T>(S.g, e, nx); info_sun = 0.0; }
+            } else { rw = -0.1; rsn = 1; term = 1; }
+            e.total[b] += rw; info_total = e.total[b];
+            env_store_hit<T>(e, b, nx, D);
+            e.bounce[b] = bc; info_bounce = bc;
+            if (nx.idx >= 0) {                                               // :373-381
+                T c[3];
+                terminal_rgb<T>(S.g, S.la, nx, 0, c, ct);
+                e.acc[b] = e.acc[b] + c[0]; e.acc[B + b] = e.acc[B + b] + c[1]; e.acc[2 * B + b] = e.acc[2 * B + b] + c[2];
+            }
+            if (e.flavour == 0) {
+                if (nx.idx < 0) { term = 1; rsn = 2; }
+                else if (bc >= e.max_bounces) { term = 1; trunc = 1; rsn = 3; }
+            } else if (!term && bc >= e.max_bounces) { term = 1; trunc = 1; rsn = 3; }
+        }
+        reward[b] = rw; terminated[b] = (uint8_t)term; truncated[b] = (uint8_t)trunc; reason[b] = rsn;
+        if (info) {
+            double *q = info + 4 * (size_t)b;
+            q[0] = (double)info_bounce; q[1] = (double)through; q[2] = info_total; q[3] = info_sun;
+        }
+        env_obs<T>(S.g, e, b, obs);
+    }
+    if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
+}
+
+// ------------------------------------------------------------------ launchers
+template <typename T> static inline size_t smem_for(const SceneDev<T> &sc) {
+    return scene_smem_bytes<T>(sc.n, sc.nG, sc.nP, sc.nL);
+}
+
+#define RT_SMEM_LIMIT (96 * 1024)
+
+template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return cudaSuccess;
+}
+
+template <typename T>
+cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
+                           unsigned long long *stats, cudaStream_t st) {
+    const int rows = wp.y1 - wp.y0;
+    if (rows <= 0 || wp.W <= 0) return cudaSuccess;
+    dim3 grid((wp.W + 31) / 32, (rows + 7) / 8), block(256);
+    const size_t sm = smem_for(sc);
+    using v4 = typename M<T>::v4;
+    if (sm <= RT_SMEM_LIMIT) {
+        cudaError_t e = allow_smem(whitted_kernel<T, true>, sm);
+        if (e != cudaSuccess) return e;
+        whitted_kernel<T, true><<<grid, block, sm, st>>>(sc, wp, (v4 *)accum, hit, stats);
+    } else {
+        whitted_kernel<T, false><<<grid, block, 0, st>>>(sc, wp, (v4 *)accum, hit, stats);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
+                        cudaStream_t st) {
+    const int rows = pp.y1 - pp.y0;
+    if (rows <= 0 || pp.W <= 0) return cudaSuccess;
+    dim3 grid((pp.W + 31) / 32, (rows + 7) / 8), block(256);
+    const size_t sm = smem_for(sc);
+    using v4 = typename M<T>::v4;
+    if (sm <= RT_SMEM_LIMIT) {
+        cudaError_t e = allow_smem(path_kernel<T, true>, sm);
+        if (e != cudaSuccess) return e;
+        path_kernel<T, true><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats);
+    } else {
+        path_kernel<T, false><<<grid, block, 0, st>>>(sc, pp, (v4 *)accum, stats);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_resolve(const void *accum, int W, int y0, int y1, int spp, float *image, cudaStream_t st) {
+    const size_t n = (size_t)(y1 - y0) * W;
+    if (n == 0) return cudaSuccess;
+    resolve_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const typename M<T>::v4 *)accum, W, y0, y1, spp, image);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_sphere_disc(int m, const double *rays, const double *spheres, int point, double *out, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+    sphere_disc_kernel<T><<<(m + 127) / 128, 128, 0, st>>>(m, rays, spheres, point, out);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_trace_rays(const SceneDev<T> &sc, int m, const double *rays, const int *suppress, const int *bounces0,
+                              const int *through0, int max_bounces, int shadow_max_bounces, const double miss[3],
+                              double *term, double *rgb, cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+    const size_t sm = smem_for(sc);
+    const int block = 256, grid = (m + block - 1) / block;
+    if (sm <= RT_SMEM_LIMIT) {
+        cudaError_t e = allow_smem(trace_rays_kernel<T, true>, sm);
+        if (e != cudaSuccess) return e;
+        trace_rays_kernel<T, true><<<grid, block, sm, st>>>(sc, m, rays, suppress, bounces0, through0, max_bounces,
+                                                            shadow_max_bounces, miss[0], miss[1], miss[2], term, rgb);
+    } else {
+        trace_rays_kernel<T, false><<<grid, block, 0, st>>>(sc, m, rays, suppress, bounces0, through0, max_bounces,
+                                                            shadow_max_bounces, miss[0], miss[1], miss[2], term, rgb);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
+                             uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st) {
+    if (e.B <= 0) return cudaSuccess;
+    const size_t sm = smem_for(sc);
+    const int block = 128, grid = (e.B + block - 1) / block;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (sm <= RT_SMEM_LIMIT) {
+        cudaError_t err = allow_smem(env_reset_kernel<T, true>, sm);
+        if (err != cudaSuccess) return err;
+        env_reset_kernel<T, true><<<grid, block, sm, st>>>(sc, e, pixels, mask, k0, k1, obs, pixels_out, stats);
+    } else {
+        env_reset_kernel<T, false><<<grid, block, 0, st>>>(sc, e, pixels, mask, k0, k1, obs, pixels_out, stats);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, double *reward,
+                            uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
+                            unsigned long long *stats, cudaStream_t st) {
+    if (e.B <= 0) return cudaSuccess;
+    const size_t sm = smem_for(sc);
+    const int block = 128, grid = (e.B + block - 1) / block;
+    if (sm <= RT_SMEM_LIMIT) {
+        cudaError_t err = allow_smem(env_step_kernel<T, true>, sm);
+        if (err != cudaSuccess) return err;
+        env_step_kernel<T, true><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason,
+                                                          info, stats);
+    } else {
+        env_step_kernel<T, false><<<grid, block, 0, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason,
+                                                          info, stats);
+    }
+    return cudaGetLastError();
+}
+
+#define RT_INSTANTIATE_LAUNCHERS(T)                                                                                     \
+    template cudaError_t launch_whitted<T>(const SceneDev<T> &, const WhittedDev<T> &, void *, int *,                   \
+                                           unsigned long long *, cudaStream_t);                                         \
+    template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
+                                        cudaStream_t);                                                                  \
+    template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \
+    template cudaError_t launch_sphere_disc<T>(int, const double *, const double *, int, double *, cudaStream_t);       \
+    template cudaError_t launch_trace_rays<T>(const SceneDev<T> &, int, const double *, const int *, const int *,       \
+                                              const int *, int, int, const double[3], double *, double *,              \
+                                              cudaStream_t);                                                            \
+    template cudaError_t launch_env_reset<T>(const SceneDev<T> &, const EnvDev<T> &, const int *, const uint8_t *,      \
+                                             uint64_t, float *, int *, unsigned long long *, cudaStream_t);             \
+    template cudaError_t launch_env_step<T>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, double *,   \
+                                            uint8_t *, uint8_t *, int *, double *, unsigned long long *, cudaStream_t);
+
+}  // namespace rt

@@ -1,0 +1,63 @@
+// rt_launch.h -- kernel parameter blocks and launcher declarations shared by the two kernel translation units
+// (rt_f32.cu: float, FMA-contracted; rt_f64.cu: double, -fmad=false) and the C-ABI layer (rt_api.cu).
+#pragma once
+#include "rt_common.cuh"
+
+namespace rt {
+
+// Algorithm A frame (rt_whitted_params, include/rt_b200.h)
+template <typename T> struct WhittedDev {
+    T cam[3];
+    const T *X, *Y;              // device copies of the direction grids
+    int W, H, y0, y1, s0, s1, spp, max_bounces, shadow_max_bounces;
+    T miss[3];
+    T pitch_x, pitch_y;          // X[1]-X[0], Y[0]-Y[1] (output5.py:1465-1466)
+    uint32_t k0, k1;             // Philox key
+    int prenorm, accumulate;
+};
+
+// Algorithm B frame (rt_path_params)
+template <typename T> struct PathDev {
+    T cam[3];
+    int W, H, y0, y1, s0, s1, max_bounces;
+    T aspect, half_w, half_h;    // W/H, tan(fov/2)*aspect, tan(fov/2)   (chandelier.py:412-415)
+    T mirror_threshold;
+    uint32_t k0, k1;
+    int accumulate;
+};
+
+// batched RayTracerEnv state (SoA, [3][B] for vectors)
+template <typename T> struct EnvDev {
+    int B, W, H, max_bounces, flavour, sun_id;
+    T cam[3], cam_angle[3], tan_half;
+    int *has_hit, *idx, *bounce, *through, *episode;
+    T *p, *n, *d, *acc;
+    double *total;
+};
+
+template <typename T>
+cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
+                           unsigned long long *stats, cudaStream_t st);
+template <typename T>
+cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
+                        cudaStream_t st);
+template <typename T>
+cudaError_t launch_resolve(const void *accum, int W, int y0, int y1, int spp, float *image, cudaStream_t st);
+template <typename T>
+cudaError_t launch_sphere_disc(int m, const double *rays, const double *spheres, int point, double *out, cudaStream_t st);
+template <typename T>
+cudaError_t launch_trace_rays(const SceneDev<T> &sc, int m, const double *rays, const int *suppress, const int *bounces0,
+                              const int *through0, int max_bounces, int shadow_max_bounces, const double miss[3],
+                              double *term, double *rgb, cudaStream_t st);
+template <typename T>
+cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
+                             uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st);
+template <typename T>
+cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, double *reward,
+                            uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
+                            unsigned long long *stats, cudaStream_t st);
+
+// FFMA issue-rate micro-benchmark (rt_f32.cu): `iters` trips of 16 independent FFMA per thread
+cudaError_t launch_fp32_peak(int blocks, int threads, int iters, float *sink, cudaStream_t st);
+
+}  // namespace rt

@@ -1,0 +1,353 @@
+// rt_trace.cuh -- the tracing and shading functions of the hot path, as device templates.
+//
+//   T = float  : product path.  Robust f-vector discriminant, rsqrt normalisation, winner-only hit point.
+//   T = double : parity build.  Written in the reference's operation order (compiled with -fmad=false), so it
+//                tracks the IEEE-double Python arithmetic to libm precision.
+//
+// Reference functions restated here (path:line relative to the reference root):
+//   Ray.sphereDiscriminant          RL/ray.py:73-107
+//   Intersection.nearestIntersection RL/ray.py:10-20
+//   Ray.sphereExitRay               RL/ray.py:109-157
+//   Ray.nearestSphereIntersect      RL/ray.py:160-231
+//   Intersection.terminalRGB        RL/ray.py:37-65   (+ colour.py:21-29, light.py:3-37)
+//   TraditionalRenderer.trace_ray_traditional  FB/fb_vs_traditional_chandelier.py:431-521 (= complex.py:299-389)
+#pragma once
+#include "rt_common.cuh"
+#include "rt_lbvh.cuh"
+
+namespace rt {
+
+// ------------------------------------------------------------------ geometry view
+template <typename T> struct Geo {
+    SphereView<T> sv;     // spheres (shared-memory staged or global)
+    BvhView bvh;          // nodes == 0 -> brute force over sv
+};
+
+template <typename T> struct Hit {
+    int idx;              // scene index, -1 = none
+    T t;                  // Intersection.distance (signed)
+    V3<T> p, n;
+    int bounces, through;
+};
+
+template <typename T> RT_DEV V3<T> centre_of(typename M<T>::v4 s) { return mk<T>(s.x, s.y, s.z); }
+
+// One ray/sphere test (ray.py:73-107), near root (point = 0) or far root (point = 1).  D is a unit vector.
+template <typename T> RT_DEV bool sphere_test(V3<T> O, V3<T> D, typename M<T>::v4 s, int point, T &t) {
+    V3<T> L = centre_of<T>(s) - O;
+    T tca = dot(L, D);
+    if constexpr (M<T>::exact) {
+        if (tca < T(0)) return false;                     // ray.py:81-82
+        T q = dot(L, L) - tca * tca;
+        T d = q < T(0) ? T(0) : ::sqrt(q);                // ray.py:85-88 (math.sqrt raising -> d = 0)
+        if (d > s.w) return false;                        // ray.py:89-90
+        T thc = ::sqrt(s.w * s.w - d * d);
+        t = point ? tca + thc : tca - thc;                // ray.py:93-96 (may be negative)
+        return true;
+    } else {
+        // |L - tca D|^2 instead of L.L - tca^2: no catastrophic cancellation for the r = 99..1000 wall spheres
+        V3<T> f = L - D * tca;
+        T disc = fmaf(s.w, s.w, -dot(f, f));
+        if (!(tca >= 0.f) || !(disc >= 0.f)) return false;
+        T thc = M<T>::sqrt(disc);
+        t = point ? tca + thc : tca - thc;
+        return true;
+    }
+}
+
+// Nearest hit over the scene.  kAbs = false: Algorithm A, smallest SIGNED distance wins (ray.py:10-20);
+// kAbs = true: Algorithm B, smallest |hit - origin| wins (chandelier.py:438-444).  First in list wins ties.
+// `suppress` is a Sphere.id (ray.py:165) or RT_NO_ID_DEV.  Returns the scene index or -1; t = signed distance.
+template <typename T, bool kAbs> RT_DEV void consider(const Geo<T> &g, int i, V3<T> O, V3<T> D, int suppress, T &best,
+                                                      T &bt, int &bi, unsigned &tests) {
+    if (suppress != RT_NO_ID_DEV && g.sv.ids[i] == suppress) return;
+    tests++;
+    T t;
+    if (!sphere_test<T>(O, D, g.sv.sph[i], 0, t)) return;
+    T key;
+    if constexpr (!kAbs) key = t;
+    else if constexpr (M<T>::exact) { V3<T> p = O + D * t, d = p - O; key = ::sqrt(d.x * d.x + d.y * d.y + d.z * d.z); }
+    else key = fabsf(t);
+    if (key < best || (g.bvh.nodes != 0 && key == best && i < bi)) { best = key; bt = t; bi = i; }
+}
+
+template <typename T, bool kAbs>
+RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests) {
+    T best = M<T>::inf(), bt = T(0);
+    int bi = -1;
+    if (g.bvh.nodes == 0) {
+        const int n = g.sv.n;
+        if (suppress == RT_NO_ID_DEV) {
+#pragma unroll 4
+            for (int i = 0; i < n; ++i) {
+                T t;
+                if (sphere_test<T>(O, D, g.sv.sph[i], 0, t)) {
+                    T key;
+                    if constexpr (!kAbs) key = t;
+                    else if constexpr (M<T>::exact) {
+                        V3<T> p = O + D * t, d = p - O;
+                        key = ::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
+                    } else key = fabsf(t);
+                    if (key < best) { best = key; bt = t; bi = i; }
+                }
+            }
+            tests += n;
+        } else {
+#pragma unroll 2
+            for (int i = 0; i < n; ++i) consider<T, kAbs>(g, i, O, D, suppress, best, bt, bi, tests);
+        }
+    } else {
+        for (int k = 0; k < g.bvh.n_huge; ++k) consider<T, kAbs>(g, g.bvh.huge[k], O, D, suppress, best, bt, bi, tests);
+        // float boxes (conservatively grown at build time) cull for both precisions
+        float ox = (float)O.x, oy = (float)O.y, oz = (float)O.z;
+        float idx_ = 1.f / (float)D.x, idy = 1.f / (float)D.y, idz = 1.f / (float)D.z;
+        int stack[RT_BVH_STACK];
+        int sp = 0;
+        int node = g.bvh.root;            // >= 0 internal, < 0 leaf ~prim
+        for (;;) {
+            if (node < 0) {
+                consider<T, kAbs>(g, g.bvh.prims[~node], O, D, suppress, best, bt, bi, tests);
+            } else {
+                const float4 a = g.bvh.node4[4 * node + 0], b = g.bvh.node4[4 * node + 1],
+                             c = g.bvh.node4[4 * node + 2], ch = g.bvh.node4[4 * node + 3];
+                box_tests += 2;
+                float bound = (float)best * 1.00001f + 1e-6f;
+                // left child
+                float t0x = (a.x - ox) * idx_, t1x = (a.y - ox) * idx_, t0y = (a.z - oy) * idy, t1y = (a.w - oy) * idy;
+                float t0z = (c.x - oz) * idz, t1z = (c.y - oz) * idz;
+                float ln = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+                float lf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                bool hl = ln <= lf && lf >= 0.f && ln <= bound;
+                t0x = (b.x - ox) * idx_; t1x = (b.y - ox) * idx_; t0y = (b.z - oy) * idy; t1y = (b.w - oy) * idy;
+                t0z = (c.z - oz) * idz; t1z = (c.w - oz) * idz;
+                float rn = fmaxf(fmaxf(fminf(t0x, t1x), fminf(t0y, t1y)), fminf(t0z, t1z));
+                float rf = fminf(fminf(fmaxf(t0x, t1x), fmaxf(t0y, t1y)), fmaxf(t0z, t1z));
+                bool hr = rn <= rf && rf >= 0.f && rn <= bound;
+                int cl = __float_as_int(ch.x), cr = __float_as_int(ch.y);
+                if (hl && hr) {
+                    bool left_first = ln <= rn;
+                    int nearc = left_first ? cl : cr, farc = left_first ? cr : cl;
+                    if (sp < RT_BVH_STACK) stack[sp++] = farc;
+                    node = nearc;
+                    continue;
+                }
+                if (hl) { node = cl; continue; }
+                if (hr) { node = cr; continue; }
+            }
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+    t_out = bt;
+    return bi;
+}
+
+template <typename T> RT_DEV void finish_hit(const Geo<T> &g, V3<T> O, V3<T> D, int i, T t, Hit<T> &h) {
+    h.idx = i; h.t = t;
+    h.p = O + D * t;                                          // ray.py:99
+    h.n = normalise(h.p - centre_of<T>(g.sv.sph[i]));         // ray.py:100
+}
+
+// Ray.sphereExitRay (ray.py:109-157).  false = trapped (reference prints + returns None) or the reference would
+// raise (entry TIR for ior < 1, degenerate chord): callers treat both as None.
+template <typename T>
+RT_DEV bool sphere_exit_ray(V3<T> D, typename M<T>::v4 sph, T ior, const Hit<T> &in, V3<T> &eo, V3<T> &ed) {
+    V3<T> refr;
+    if (!refract<T>(D, in.n, T(1), ior, refr)) return false;
+    V3<T> C = centre_of<T>(sph);
+    V3<T> xo = in.p, xd = M<T>::exact ? normalise(refr) : refr;
+    T t;
+    if (!sphere_test<T>(xo, xd, sph, 1, t)) return false;
+    V3<T> xp = xo + xd * t, xn = normalise(xp - C);
+    V3<T> exit_d;
+    bool done = false;
+    for (int k = 0; k < 10 && !done; ++k) {
+        if (refract<T>(refr, -xn, ior, T(1), exit_d)) done = true;
+        else {
+            refr = reflect<T>(refr, xn);                      // total internal reflection, ray.py:137
+            xd = M<T>::exact ? normalise(refr) : refr;
+            if (!sphere_test<T>(xp, xd, sph, 1, t)) return false;
+            xp = xp + xd * t;
+            xn = normalise(xp - C);
+        }
+    }
+    if (!done) return false;
+    eo = xp;
+    ed = M<T>::exact ? normalise(exit_d) : exit_d;
+    return true;
+}
+
+struct Counters { unsigned queries, tests, boxes; };
+
+// Ray.nearestSphereIntersect (ray.py:160-231) with the recursion unrolled: a mirror that finds nothing returns
+// ITSELF (ray.py:198-201), glass that finds nothing returns None (ray.py:226-229), so a dead-ended chain yields the
+// most recent mirror hit, else None.  D is a unit vector.
+template <typename T>
+RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, int bounces, int max_bounces, int through,
+                             Counters &ct) {
+    Hit<T> fallback;
+    fallback.idx = -1; fallback.t = T(0); fallback.bounces = 0; fallback.through = 0;
+    fallback.p = mk<T>(0, 0, 0); fallback.n = mk<T>(0, 0, 0);
+    for (;;) {
+        ct.queries++;
+        T t;
+        int i = nearest<T, false>(g, O, D, suppress, t, ct.tests, ct.boxes);
+        if (i < 0) return fallback;                           // ray.py:170-171
+        if (bounces > max_bounces) return fallback;           // ray.py:173-174
+        Hit<T> h;
+        finish_hit<T>(g, O, D, i, t, h);
+        h.bounces = bounces; h.through = through;
+        const typename M<T>::v4 m = g.sv.mat[i];
+        if (m.x == T(1)) {                                    // material.reflective == True, ray.py:180
+            fallback = h;
+            V3<T> r = reflect<T>(D, h.n);
+            D = M<T>::exact ? normalise(r) : r;               // Ray() normalises again
+            O = h.p;
+            bounces += 1; suppress = g.sv.ids[i];
+            continue;
+        }
+        if (m.y == T(1)) {                                    // material.transparent == True, ray.py:204
+            V3<T> eo, ed;
+            if (!sphere_exit_ray<T>(D, g.sv.sph[i], m.w, h, eo, ed)) return fallback;
+            O = eo; D = ed;
+            bounces += 1; through += 1; suppress = g.sv.ids[i];
+            continue;
+        }
+        return h;
+    }
+}
+
+template <typename T> RT_DEV T incidence(T angle, T max_angle) {        // light.py:3-9
+    if (angle > max_angle) return T(0);
+    if (angle == T(0)) return T(1);
+    return (max_angle - angle) / max_angle;
+}
+
+// lights of Algorithm A as the shading function sees them
+template <typename T> struct LightsA {
+    using v4 = typename M<T>::v4;
+    int nG, nP;
+    const v4 *g_vec, *g_col; const int *g_func;     // g_vec.w = max_angle, g_col.w = strength
+    const v4 *p_pos, *p_col; const int *p_id, *p_func;
+    T bg[3];
+};
+
+// Intersection.terminalRGB (ray.py:37-65) + Colour.illuminate (colour.py:21-29, round half to even, not clamped)
+template <typename T>
+RT_DEV void terminal_rgb(const Geo<T> &g, const LightsA<T> &lt, const Hit<T> &h, int shadow_max_bounces, T out[3],
+                         Counters &ct) {
+    const typename M<T>::v4 m = g.sv.mat[h.idx], col = g.sv.col[h.idx];
+    T il0 = col.x * m.z, il1 = col.y * m.z, il2 = col.z * m.z;            // ray.py:41
+    for (int k = 0; k < lt.nG; ++k) {                                      // ray.py:43-45
+        if (lt.g_func[k] != 0) continue;
+        const typename M<T>::v4 gv = lt.g_vec[k], gc = lt.g_col[k];
+        T ang = angle_between<T>(h.n, mk<T>(gv.x, gv.y, gv.z));
+        T sc = incidence<T>(ang, gv.w) * gc.w;
+        il0 = il0 + gc.x * sc; il1 = il1 + gc.y * sc; il2 = il2 + gc.z * sc;
+    }
+    const int own = g.sv.ids[h.idx];
+    for (int k = 0; k < lt.nP; ++k) {                                      // ray.py:47-62
+        const int pid = lt.p_id[k];
+        if (own == pid) continue;
+        const typename M<T>::v4 pp = lt.p_pos[k], pc = lt.p_col[k];
+        V3<T> vl = mk<T>(pp.x, pp.y, pp.z) - h.p;
+        Hit<T> s = trace_terminal<T>(g, h.p, normalise(vl), own, 0, shadow_max_bounces, 0, ct);
+        if (s.idx < 0 || g.sv.ids[s.idx] != pid) continue;
+        T ang = angle_between<T>(h.n, vl);
+        const int fn = lt.p_func[k];
+        T sc;
+        if (fn == -1) sc = incidence<T>(ang, pp.w) * pc.w;
+        else if (fn == 0) sc = incidence<T>(ang, pp.w) * pc.w / mag(vl);
+        else continue;
+        il0 = il0 + pc.x * sc; il1 = il1 + pc.y * sc; il2 = il2 + pc.z * sc;
+    }
+    out[0] = lt.bg[0] + M<T>::rint(col.x * (il0 / T(255)));
+    out[1] = lt.bg[1] + M<T>::rint(col.y * (il1 / T(255)));
+    out[2] = lt.bg[2] + M<T>::rint(col.z * (il2 / T(255)));
+}
+
+// ------------------------------------------------------------------ Algorithm B
+// light spheres of TraditionalRenderer.light_sources: l_pos.w = scene index (int bits via __T_as_int surrogate: stored
+// as a separate int array), l_col = colour.
+template <typename T> struct LightsB {
+    using v4 = typename M<T>::v4;
+    int nL;
+    const v4 *l_pos, *l_col;
+    const int *l_index;
+};
+
+// Per-level record of the unrolled recursion: the hit sphere (albedo) and the direct light collected there,
+// clamped to 255 per channel.  Clamping early is exact: direct is a sum of int()s and the indirect term is >= 0,
+// so min(255, direct + ind) == min(255, min(255, direct) + ind).
+struct PathStack {
+    uint32_t idx[RT_PATH_MAX_DEPTH];
+    uint32_t direct[RT_PATH_MAX_DEPTH];     // r | g << 8 | b << 16
+};
+
+// final = int(albedo * (min(255, direct + indirect) / 255.0)) per channel, folded from the leaf back to the camera
+// (chandelier.py:509-521).  Always evaluated in double: the truncation must see the reference's rounding.
+template <typename T>
+RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[3]) {
+    for (int k = depth - 1; k >= 0; --k) {
+        const typename M<T>::v4 col = g.sv.col[st.idx[k]];
+        const uint32_t d = st.direct[k];
+        double t0 = (double)(d & 255u) + c[0], t1 = (double)((d >> 8) & 255u) + c[1], t2 = (double)((d >> 16) & 255u) + c[2];
+        t0 = t0 < 255.0 ? t0 : 255.0; t1 = t1 < 255.0 ? t1 : 255.0; t2 = t2 < 255.0 ? t2 : 255.0;
+        c[0] = ::trunc(__dmul_rn((double)col.x, __ddiv_rn(t0, 255.0)));
+        c[1] = ::trunc(__dmul_rn((double)col.y, __ddiv_rn(t1, 255.0)));
+        c[2] = ::trunc(__dmul_rn((double)col.z, __ddiv_rn(t2, 255.0)));
+    }
+}
+
+// direct light at a non-emissive hit: every light sphere, NO occlusion test (chandelier.py:463-477)
+template <typename T>
+RT_DEV uint32_t direct_light(const LightsB<T> &lb, int hit_idx, V3<T> p, V3<T> n) {
+    T d0 = T(0), d1 = T(0), d2 = T(0);
+    for (int l = 0; l < lb.nL; ++l) {
+        if (lb.l_index[l] == hit_idx) continue;
+        const typename M<T>::v4 lp = lb.l_pos[l], lc = lb.l_col[l];
+        V3<T> tl = mk<T>(lp.x, lp.y, lp.z) - p;
+        if constexpr (M<T>::exact) {
+            V3<T> tln = normalise(tl);
+            T ca = dot(n, tln);
+            if (!(ca > T(0))) continue;
+            T dist = ::sqrt(dot(tl, tl)), att = 1.0 / (dist * dist);
+            d0 += ::trunc(lc.x * ca * att * 0.3); d1 += ::trunc(lc.y * ca * att * 0.3); d2 += ::trunc(lc.z * ca * att * 0.3);
+        } else {
+            T q = dot(tl, tl), inv = rsqrtf(q);
+            T ca = dot(n, tl) * inv;
+            if (!(ca > 0.f)) continue;
+            T s = ca * (inv * inv) * 0.3f;
+            d0 += truncf(lc.x * s); d1 += truncf(lc.y * s); d2 += truncf(lc.z * s);
+        }
+    }
+    d0 = d0 < T(255) ? d0 : T(255); d1 = d1 < T(255) ? d1 : T(255); d2 = d2 < T(255) ? d2 : T(255);
+    return (uint32_t)d0 | ((uint32_t)d1 << 8) | ((uint32_t)d2 << 16);
+}
+
+// next ray of a path after a non-emissive hit (chandelier.py:479-507): mirror if reflective > threshold, else a
+// cosine-weighted direction around the normal from two uniforms.
+template <typename T>
+RT_DEV V3<T> bounce_direction(V3<T> D, V3<T> n, bool mirror, T r1, T r2) {
+    if (mirror) {
+        V3<T> r = reflect<T>(D, n);
+        return M<T>::exact ? normalise(r) : r;
+    }
+    T st, ct, sp, cp;
+    if constexpr (M<T>::exact) {
+        T theta = ::acos(::sqrt(r1)), phi = 2 * 3.14159265358979323846 * r2;
+        st = ::sin(theta); ct = ::cos(theta); sp = ::sin(phi); cp = ::cos(phi);
+    } else {
+        ct = sqrtf(r1); st = sqrtf(1.f - r1);                 // cos/sin(acos(sqrt r1))
+        sincospif(2.f * r2, &sp, &cp);
+    }
+    V3<T> tg = M<T>::fabs(n.z) > T(0.9) ? mk<T>(1, 0, 0) : cross(mk<T>(0, 0, 1), n);
+    tg = normalise(tg);
+    V3<T> bt = normalise(cross(n, tg));
+    T lx = st * cp, ly = st * sp, lz = ct;
+    V3<T> bd = normalise(mk<T>(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y,
+                               lx * tg.z + ly * bt.z + lz * n.z));
+    return M<T>::exact ? normalise(bd) : bd;
+}
+
+}  // namespace rt
