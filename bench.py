@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: Mrays/s and ms/frame of the traditional path tracer (Algorithm B, TraditionalRenderer.render)
+on the complex scene, 1920x1080, 64 spp (BASELINE.json configs[2]) at N = 1/2/4/8 B200, tile-sharded.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # own arm (CUDA)
+    python bench.py --impl reference [...]                         # the CPU port of the reference (oracle/, OpenMP)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # N > 1, one rank per GPU over NCCL
+
+A step = one frame.  A ray = one nearest-hit query; `rays_ref_compatible` counts like the reference's
+own `total_rays` (every trace_ray_traditional call, including the ones that return at the depth check).
+`value` is device-timed with inputs resident in HBM; `e2e` goes through the reference-facing API with host buffers
+(scene flattening + upload in, float32 image out, every step).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+W, H, SPP, DEPTH, THRESHOLD, FOV = 1920, 1080, 64, 5, 0.9, 60.0
+METRIC, UNIT = "Mrays/s (complex scene, 1920x1080, 64 spp)", "Mrays/s"
+WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer), tile-sharded"
+
+
+def complex_scene():
+    import ray_tracer_v1_b200 as rtb
+    from ray_tracer_v1_b200 import scenes
+    spec = scenes.build_complex()
+    fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
+    return spec, fs
+
+
+def flop_per_query(n_spheres, n_lights):
+    """20 FLOP per ray-sphere test x N, + hit point/normal 15 + 25 per light + bounce/TBN/fold 70."""
+    return 20 * n_spheres + 15 + 25 * n_lights + 70
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20}
+    NOTE = {"sw_power_cap": 0x4}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in {**self.BAD, **self.NOTE}.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        return {"sm_mhz": (statistics.median(self.samples) if self.samples else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_port_run(fs, spec, width, height, spp, seed, threads):
+    """The oracle's C restatement of TraditionalRenderer.render on the host cores (OpenMP).  -> (queries, rays, seconds)"""
+    from oracle import oracle as orc
+    t0 = time.perf_counter()
+    _, st = orc.render_path(fs, spec.camera, width, height, spp, DEPTH, THRESHOLD, seed=seed, fov=FOV, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return st["queries"], st["total_rays"], dt
+
+
+def host_threads():
+    from oracle import oracle as orc
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    return max(1, min(avail, orc.max_threads() if orc.max_threads() > 1 else avail))
+
+
+def cpu_baseline(fs, spec):
+    """Bounded sample of the SAME workload (same scene, depth, camera; 480x270, 8 spp ~ 6 M rays ~ 10 s of CPU work)."""
+    threads = host_threads()
+    cpu_port_run(fs, spec, 96, 54, 2, 1, threads)        # warm the library / thread pool
+    q, r, dt = cpu_port_run(fs, spec, 480, 270, 8, 0, threads)
+    return {"value": q / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"480x270 x 8 spp of the same scene/depth/camera ({q} queries, {r} reference-counted rays, {dt:.2f} s); "
+                      "oracle/rt_oracle.c (C, FP64, OpenMP) -- the reference itself is single-threaded Python "
+                      "(3.3-7.4 krays/s published, BASELINE.md)",
+            "rays_ref_compatible_per_s": r / dt / 1e6}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU port of the reference's path on all host threads, same metric/config; each step a
+    bounded sample (480x270 x 8 spp) of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    spec, fs = complex_scene()
+    threads = host_threads()
+    sw, sh, sspp = 480, 270, 8
+    for i in range(args.warmup):
+        cpu_port_run(fs, spec, 96, 54, 2, 100 + i, threads)
+    q_tot = r_tot = 0
+    t_tot = 0.0
+    for i in range(args.steps):
+        q, r, dt = cpu_port_run(fs, spec, sw, sh, sspp, i, threads)
+        q_tot += q; r_tot += r; t_tot += dt
+    value = q_tot / t_tot / 1e6
+    sample = f"{sw}x{sh} x {sspp} spp of the same scene/depth/camera per step"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "rays_ref_compatible_per_s": r_tot / t_tot / 1e6, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ own arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="tiles", choices=["tiles", "samples"])
+    ap.add_argument("--spp", type=int, default=SPP)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from ray_tracer_v1_b200 import _native as nat
+    from ray_tracer_v1_b200.distributed import ShardedPathRenderer, row_bands, sample_ranges
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    nat.lib()      # fail loudly if the CUDA extension is missing
+
+    spec, fs = complex_scene()
+    spp = args.spp
+    r = ShardedPathRenderer(device=local)
+    r.set_scene(fs)
+    cam = spec.camera
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        return r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode)
+
+    fp32_peak, _ = nat.measure_fp32_peak(local, 5)
+    for i in range(args.warmup):
+        step(1000 + i)
+    barrier()
+
+    # ---- device-timed steps (inputs resident in HBM); L2 flushed, untimed, between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    counters = torch.zeros(8, dtype=torch.int64, device="cuda")
+    launches = 0
+    barrier()
+    for i in range(args.steps):
+        flush.zero_()
+        barrier()
+        ev[i][0].record()
+        # the step, with the dominant kernel bracketed separately for the roofline
+        r._ensure(W, H)
+        rows = row_bands(H, world)[rank] if args.mode == "tiles" else (0, H)
+        smp = sample_ranges(spp, world)[rank] if args.mode == "samples" else (0, spp)
+        r.stats.zero_()
+        p = r.scene.path_params(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, rows=rows, samples=smp)
+        kev[i][0].record()
+        r.scene.render_path(p, r.accum, nat.F32, stats=r.stats)
+        kev[i][1].record()
+        if args.mode == "tiles":
+            r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32, rows=rows)
+            launches += 2
+            if world > 1:
+                from ray_tracer_v1_b200.distributed import gather_row_bands
+                gather_row_bands(r.image, row_bands(H, world))
+        else:
+            from ray_tracer_v1_b200.distributed import reduce_sample_sums
+            reduce_sample_sums(r.accum)
+            launches += 1
+            if rank == 0:
+                r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32)
+                launches += 1
+        ev[i][1].record()
+        counters += r.stats
+    barrier()
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    kern_ms = [a.elapsed_time(b) for a, b in kev]
+    t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)
+    total_ms, kernel_ms = float(t[0]), float(t[1])
+    c = counters.cpu().numpy()
+    rays_ref, queries, tests = int(c[0]), int(c[4]), int(c[5])
+    value = queries / (total_ms * 1e-3) / 1e6
+
+    # ---- end to end through the reference-facing API: host scene in, host image out, every step
+    barrier()
+    e2e_q = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for i in range(2):
+        r.set_scene(fs)
+        r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=2000 + i, fov=FOV, mode=args.mode, to_host=True)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        spec_i, fs_i = (spec, fs)
+        r.set_scene(fs_i)                                     # H2D: the flattened scene, re-uploaded every frame
+        img, st = r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, to_host=True)   # D2H: image
+        e2e_q += st[4:5]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_q, op=dist.ReduceOp.SUM)
+    e2e_value = int(e2e_q[0]) / float(te[0]) / 1e6
+
+    if rank == 0:
+        n_sph, n_l = int(fs.radius.shape[0]), int(fs.l_index.shape[0])
+        fpq = flop_per_query(n_sph, n_l)
+        # roofline of the dominant kernel (path_kernel<float>): algorithmic FLOP per launch / its mean duration,
+        # per GPU (this rank's launches; all ranks run the same kernel on equal bands)
+        q_rank0 = queries / world
+        achieved = q_rank0 * fpq / (kernel_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": spp, "max_bounces": DEPTH,
+                       "sharding": args.mode, "l2": "flushed between steps (256 MiB memset, untimed); inputs are a 3 KB scene",
+                       "ray_definition": "one nearest-hit query over the scene (SURVEY 8d)"},
+            "rays_ref_compatible_per_s": rays_ref / (total_ms * 1e-3) / 1e6,
+            "rays_per_pixel_sample": rays_ref / (args.steps * W * H * spp),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(r.h2d_bytes),
+                    "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": 1e3 * float(te[0]) / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32", "kernel": "path_kernel<float,true>", "achieved": achieved, "peak": fp32_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                         "peak_source": "rt_measure_fp32_peak (FFMA issue-rate micro-benchmark, measured in this run; "
+                                        "MEASURED_PEAKS.json has no FP32 figure)",
+                         "flop_per_query": fpq, "queries_per_launch": q_rank0 / args.steps,
+                         "kernel_ms": kernel_ms / args.steps, "traffic": None,
+                         "hbm_algorithmic_bytes_per_launch": W * H * 16 // world},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(fs, spec)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -133,7 +133,8 @@ typedef struct rt_whitted_params {
 } rt_whitted_params;
 /* accum_dev: [H,W,4] float (RT_F32) or double (RT_F64): sum r,g,b over the sample range + sample count.
  * hit_dev (optional) [H,W] int32 terminal scene index of the last sample (-1 miss).
- * stats_dev (optional) uint64[8]: [0] nearest-hit/occlusion queries, [1] primary rays. */
+ * stats_dev (optional) uint64[8]: [0] primary rays, [4] nearest-hit/occlusion queries, [5] sphere tests,
+ * [6] AABB tests (LBVH only). */
 int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted_params *p, void *accum_dev, int32_t *hit_dev,
                       uint64_t *stats_dev, void *stream);
 
@@ -149,6 +150,7 @@ typedef struct rt_path_params {
     double mirror_threshold;/* material.reflective > threshold mirrors: 0.9 complex (:349), 0 chandelier (:481) */
     uint64_t seed;
     int32_t accumulate;
+    int32_t schedule;       /* 0 = lock-step warps (default), 1 = per-lane path regeneration; same image either way */
 } rt_path_params;
 /* accum_dev as above.  stats_dev (optional) uint64[8]: [0] total_rays (trace calls, reference-compatible),
  * [1] total_intersections, [2] light_hits, [3] small_light_hits, [4] nearest-hit queries,

@@ -197,11 +197,11 @@ def render_path(fs, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=6
     y0, y1 = rows if rows is not None else (0, H)
     s0, s1 = samples if samples is not None else (0, spp)
     out = np.zeros((H, W, 3))
-    st = (C.c_uint64 * 4)()
+    st = (C.c_uint64 * 5)()
     lib().orc_render_path(sc.ref, _p(_d(cam), c_dp), int(W), int(H), float(fov), int(y0), int(y1), int(s0), int(s1),
                           int(max_bounces), float(mirror_threshold), int(seed), _p(out, c_dp), st, int(nthreads))
     stats = {"total_rays": int(st[0]), "total_intersections": int(st[1]), "light_hits": int(st[2]),
-             "small_light_hits": int(st[3])}
+             "small_light_hits": int(st[3]), "queries": int(st[4])}
     return out, stats
 
 

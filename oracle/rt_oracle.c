@@ -355,7 +355,7 @@ ORC_API void orc_render_whitted(const orc_scene *s, const double *cam, const dou
 }
 
 /* --------------------------------- Algorithm B frame (TraditionalRenderer) */
-typedef struct { uint64_t rays, inter, light, small; } bstats;
+typedef struct { uint64_t rays, inter, light, small, queries; } bstats;
 typedef struct {
     const orc_scene *s; int max_bounces; double thr; uint64_t seed; uint32_t pixel, sample; bstats *st;
 } bctx;
@@ -367,6 +367,7 @@ static void trace_path(const bctx *c, v3 O, v3 D, int bounce, double out[3]) {
     const orc_scene *s = c->s;
     c->st->rays++;
     if (bounce >= c->max_bounces) { out[0] = 2; out[1] = 2; out[2] = 5; return; }
+    c->st->queries++;                                  /* calls that actually loop over the spheres */
     isect best; memset(&best, 0, sizeof best); best.idx = -1; double nd = INFINITY;
     for (int i = 0; i < s->n; ++i) {
         isect it = sphere_discriminant(O, D, ld3(s->centre, i), s->radius[i], 0);
@@ -417,17 +418,17 @@ static void trace_path(const bctx *c, v3 O, v3 D, int bounce, double out[3]) {
    sum over samples [s0,s1) of the per-sample colour for rows [y0,y1).       */
 ORC_API void orc_render_path(const orc_scene *s, const double *cam, int W, int H, double fov_deg, int y0, int y1,
                              int s0, int s1, int max_bounces, double mirror_threshold, uint64_t seed,
-                             double *sum_out, uint64_t *stats4, int nthreads) {
+                             double *sum_out, uint64_t *stats5, int nthreads) {
     v3 O = V(cam[0], cam[1], cam[2]);
     double aspect = (double)W / (double)H;
     double half_h = tan((fov_deg * (M_PI / 180.0)) / 2), half_w = half_h * aspect;
-    uint64_t R = 0, I = 0, Lh = 0, Sh = 0;
+    uint64_t R = 0, I = 0, Lh = 0, Sh = 0, Q = 0;
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : R, I, Lh, Sh)
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : R, I, Lh, Sh, Q)
 #endif
     for (int y = y0; y < y1; ++y) {
-        bstats st = {0, 0, 0, 0};
+        bstats st = {0, 0, 0, 0, 0};
         for (int x = 0; x < W; ++x) {
             double acc[3] = {0, 0, 0};
             for (int sm = s0; sm < s1; ++sm) {
@@ -446,9 +447,9 @@ ORC_API void orc_render_path(const orc_scene *s, const double *cam, int W, int H
             double *o = sum_out + 3 * ((size_t)y * W + x);
             o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
         }
-        R += st.rays; I += st.inter; Lh += st.light; Sh += st.small;
+        R += st.rays; I += st.inter; Lh += st.light; Sh += st.small; Q += st.queries;
     }
-    if (stats4) { stats4[0] = R; stats4[1] = I; stats4[2] = Lh; stats4[3] = Sh; }
+    if (stats5) { stats5[0] = R; stats5[1] = I; stats5[2] = Lh; stats5[3] = Sh; stats5[4] = Q; }
 }
 
 /* -------------------------------------------------- RayTracerEnv (batched) */

@@ -15,7 +15,7 @@ import threading
 
 import numpy as np
 
-__all__ = ["NativeLibraryError", "lib", "build", "DeviceBuffer", "DeviceScene", "device_count", "device_props",
+__all__ = ["NativeLibraryError", "lib", "build", "DeviceBuffer", "PinnedArray", "DeviceScene", "device_count", "device_props",
            "measure_fp32_peak", "F32", "F64", "NO_ID", "REASONS", "LIB_PATH"]
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -58,7 +58,8 @@ class WhittedParams(C.Structure):
 class PathParams(C.Structure):
     _fields_ = [("cam", C.c_double * 3), ("W", C.c_int32), ("H", C.c_int32), ("fov_deg", C.c_double),
                 ("y0", C.c_int32), ("y1", C.c_int32), ("s0", C.c_int32), ("s1", C.c_int32), ("max_bounces", C.c_int32),
-                ("mirror_threshold", C.c_double), ("seed", C.c_uint64), ("accumulate", C.c_int32)]
+                ("mirror_threshold", C.c_double), ("seed", C.c_uint64), ("accumulate", C.c_int32),
+                ("schedule", C.c_int32)]
 
 
 class EnvDesc(C.Structure):
@@ -242,6 +243,34 @@ class DeviceBuffer:
             pass
 
 
+class PinnedArray:
+    """Page-locked host memory (rt_host_alloc_pinned) viewed as a numpy array: the staging end of D2H / H2D copies."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in (shape if isinstance(shape, (tuple, list)) else (shape,)))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = vp()
+        check(lib().rt_host_alloc_pinned(max(self.nbytes, 1), C.byref(p)))
+        self.ptr = p.value
+        raw = (C.c_byte * max(self.nbytes, 1)).from_address(self.ptr)
+        self.array = np.frombuffer(raw, dtype=self.dtype, count=int(np.prod(self.shape, dtype=np.int64))).reshape(self.shape)
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            self.array = None
+            try:
+                load_symbols().rt_host_free_pinned(self.ptr)
+            finally:
+                self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
 def _d(a, shape=None):
     a = np.ascontiguousarray(a, np.float64)
     return a if shape is None else a.reshape(shape)
@@ -322,7 +351,7 @@ class DeviceScene:
         return p
 
     def path_params(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, rows=None, samples=None,
-                    accumulate=False):
+                    accumulate=False, schedule=0):
         p = PathParams()
         p.cam[:] = [float(c) for c in cam]
         p.W, p.H, p.fov_deg = int(W), int(H), float(fov)
@@ -330,6 +359,7 @@ class DeviceScene:
         p.s0, p.s1 = (0, int(spp)) if samples is None else (int(samples[0]), int(samples[1]))
         p.max_bounces, p.mirror_threshold, p.seed = int(max_bounces), float(mirror_threshold), int(seed)
         p.accumulate = int(bool(accumulate))
+        p.schedule = int(schedule)
         return p
 
     def render_whitted(self, params, accum, precision=F32, hit=None, stats=None, stream=None):

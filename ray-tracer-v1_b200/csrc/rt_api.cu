@@ -46,6 +46,7 @@ struct rt_scene {
     void *scratch = nullptr;      // X/Y grids of whitted frames
     size_t scratch_bytes = 0;
     LbvhStorage bvh;              // rt_lbvh_build.h
+    bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
 };
 
 struct rt_env {
@@ -173,6 +174,11 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
         CU(cudaMalloc((void **)&sc->small_dev, (size_t)(s->n > 0 ? s->n : 1)));
     }
     sc->n = s->n; sc->nG = s->nG; sc->nP = s->nP; sc->nL = s->nL;
+    sc->int_colours = true;
+    for (int i = 0; i < 3 * s->n && sc->int_colours; ++i) {
+        const double c = s->colour[i];
+        if (!(c >= 0.0 && c <= 65535.0 && c == std::floor(c))) sc->int_colours = false;
+    }
     std::vector<unsigned char> hf, hd;
     pack_scene<float>(s, hf, sc->f.bytes);
     pack_scene<double>(s, hd, sc->d.bytes);
@@ -440,7 +446,8 @@ RT_EXPORT int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted
 
 // ------------------------------------------------------------------ Algorithm B frame
 template <typename T>
-static int render_path_t(const SceneDev<T> &view, const rt_path_params *p, void *accum, uint64_t *stats, cudaStream_t st) {
+static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_path_params *p, void *accum, uint64_t *stats,
+                         cudaStream_t st) {
     PathDev<T> pp;
     pp.cam[0] = (T)p->cam[0]; pp.cam[1] = (T)p->cam[1]; pp.cam[2] = (T)p->cam[2];
     pp.W = p->W; pp.H = p->H; pp.y0 = p->y0; pp.y1 = p->y1; pp.s0 = p->s0; pp.s1 = p->s1; pp.max_bounces = p->max_bounces;
@@ -451,6 +458,8 @@ static int render_path_t(const SceneDev<T> &view, const rt_path_params *p, void 
     pp.mirror_threshold = (T)p->mirror_threshold;
     pp.k0 = (uint32_t)p->seed; pp.k1 = (uint32_t)(p->seed >> 32);
     pp.accumulate = p->accumulate;
+    pp.int_fold = sc->int_colours && (p->s1 - p->s0) <= 65536;
+    pp.regenerate = p->schedule == 1;
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st));
     return RT_OK;
 }
@@ -462,8 +471,8 @@ RT_EXPORT int rt_render_path(rt_scene *scene, int precision, const rt_path_param
     if (rc) return rc;
     if (p->max_bounces > RT_PATH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "max_bounces above 32 is not supported by the path kernel");
     CU(cudaSetDevice(scene->device));
-    if (precision == RT_F64) return render_path_t<double>(scene->d.view, p, accum_dev, stats_dev, S(stream));
-    if (precision == RT_F32) return render_path_t<float>(scene->f.view, p, accum_dev, stats_dev, S(stream));
+    if (precision == RT_F64) return render_path_t<double>(scene, scene->d.view, p, accum_dev, stats_dev, S(stream));
+    if (precision == RT_F32) return render_path_t<float>(scene, scene->f.view, p, accum_dev, stats_dev, S(stream));
     return fail(RT_ERR_INVALID, "unknown precision");
 }
 

@@ -21,8 +21,9 @@ template <typename T> struct M;
 template <> struct M<float> {
     static constexpr bool exact = false;
     using v4 = float4;
-    static RT_DEV float sqrt(float x) { return x * rsqrtf(fmaxf(x, 1e-30f)); }   // MUFU.RSQ + FMUL, 0 -> 0
-    static RT_DEV float rsqrt(float x) { return rsqrtf(x); }
+    // single MUFU each, denormals flushed (no range-fixup code around the MUFU)
+    static RT_DEV float sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+    static RT_DEV float rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
     static RT_DEV float acos(float x) { return acosf(fminf(1.f, fmaxf(-1.f, x))); }
     static RT_DEV float fabs(float x) { return fabsf(x); }
     static RT_DEV float rint(float x) { return rintf(x); }
@@ -62,12 +63,12 @@ template <typename T> RT_DEV T mag(V3<T> a) { return M<T>::sqrt(dot(a, a)); }
 // Vector.normalise (vector.py:110-112): exact = three divisions by the magnitude; fast = one rsqrt
 template <typename T> RT_DEV V3<T> normalise(V3<T> a) {
     if constexpr (M<T>::exact) { T m = ::sqrt(dot(a, a)); return mk<T>(a.x / m, a.y / m, a.z / m); }
-    else { T i = rsqrtf(dot(a, a)); return a * i; }
+    else { T i = M<T>::rsqrt(dot(a, a)); return a * i; }
 }
 // Vector.angleBetween (vector.py:61-62).  fast: clamps the cosine (the reference would produce NaN -> raise)
 template <typename T> RT_DEV T angle_between(V3<T> a, V3<T> b) {
     if constexpr (M<T>::exact) return ::acos(dot(a, b) / (::sqrt(dot(a, a)) * ::sqrt(dot(b, b))));
-    else return M<T>::acos(dot(a, b) * rsqrtf(dot(a, a) * dot(b, b)));
+    else return M<T>::acos(dot(a, b) * M<T>::rsqrt(dot(a, a) * dot(b, b)));
 }
 // Vector.reflectInVector (vector.py:64-67).  `self` and `n` are unit vectors on every call site of the hot path;
 // exact re-normalises like the reference, fast normalises the result only.

@@ -13,6 +13,7 @@
 #pragma once
 #include "rt_trace.cuh"
 #include "rt_launch.h"
+#include <type_traits>
 
 namespace rt {
 
@@ -95,10 +96,15 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + slot, v);
 }
 
+// Kernel variants: kMode 0 = scene staged in shared memory, brute force (no hierarchy code in the kernel at all);
+//                  kMode 1 = staged in shared memory + LBVH traversal; kMode 2 = scene read from global + LBVH.
+#define RT_MODE_DECL constexpr bool kShared = kMode < 2; constexpr bool kBvh = kMode > 0
+
 // ------------------------------------------------------------------ Algorithm A frame
-template <typename T, bool kShared>
+template <typename T, int kMode>
 __global__ void __launch_bounds__(256) whitted_kernel(SceneDev<T> sc, WhittedDev<T> wp, typename M<T>::v4 *accum,
                                                       int *hit_out, unsigned long long *stats) {
+    RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
@@ -123,10 +129,10 @@ __global__ void __launch_bounds__(256) whitted_kernel(SceneDev<T> sc, WhittedDev
             V3<T> d = mk<T>(Xj, Yj, T(-1));
             if constexpr (M<T>::exact) { if (wp.prenorm) d = normalise(d); }
             d = normalise(d);                                            // Ray.__init__, ray.py:69-71
-            Hit<T> h = trace_terminal<T>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct);
+            Hit<T> h = trace_terminal<T, kBvh>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct);
             primaries++;
             T c[3];
-            if (h.idx >= 0) { terminal_rgb<T>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); last = h.idx; }
+            if (h.idx >= 0) { terminal_rgb<T, kBvh>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); last = h.idx; }
             else { c[0] = wp.miss[0]; c[1] = wp.miss[1]; c[2] = wp.miss[2]; last = -1; }
             a0 += c[0]; a1 += c[1]; a2 += c[2];
         }
@@ -159,87 +165,121 @@ template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, 
     return d;
 }
 
-template <typename T, bool kShared>
-__global__ void __launch_bounds__(256) path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum,
-                                                   unsigned long long *stats) {
+// One thread per pixel, looping over its samples; 8x4-pixel warps.  Two schedules:
+//   kRegen = false  lock-step: the warp traces sample s of all its 32 pixels together, one nearest-hit query per
+//                   trip, until every lane's path has ended, then folds and starts sample s+1 together.  Everything
+//                   outside the sphere loop (camera ray, Philox, fold) runs once per sample at full lane occupancy.
+//   kRegen = true   path regeneration: a lane starts its next sample the trip after its path ends.  No idle lanes in
+//                   the sphere loop, but lanes drift out of phase, so the per-sample code runs on a few lanes every
+//                   trip.  Pays off only when early termination is common and the per-sample code is short.
+// kIntFold: integer fold through the div255 table (all leaf colours integer-valued), else the double-division fold.
+template <typename T, int kMode, bool kIntFold, bool kRegen>
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 4 : 1))
+path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned long long *stats) {
+    RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
+    double *div255 = reinterpret_cast<double *>(smem);                 // [256] k / 255.0, correctly rounded
+    for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
     Staged<T> S;
-    stage_scene<T, kShared>(sc, smem, S);
+    stage_scene<T, kShared>(sc, smem + 256 * sizeof(double), S);        // ends with __syncthreads() when staging
+    if constexpr (!kShared) __syncthreads();
     int x, yr;
     tile_pixel(x, yr);
     const int y = pp.y0 + yr;
+    const bool has_pixel = x < pp.W && y < pp.y1;
     unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
-    if (x < pp.W && y < pp.y1 && pp.s0 < pp.s1) {
-        const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
-        const uint32_t pixel = (uint32_t)(y * pp.W + x);
-        PathStack st;
-        PathRng rng;
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0;           // integer-valued sums: exact in double for any spp
-        if (pp.max_bounces <= 0) {                     // degenerate: every call returns at the depth check
-            const int ns = pp.s1 - pp.s0;
-            n_rays = (unsigned)ns; a0 = 2.0 * ns; a1 = 2.0 * ns; a2 = 5.0 * ns;
-        } else {
+    const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
+    const uint32_t pixel = (uint32_t)(y * pp.W + x);
+    PathStack st;
+    PathRng rng;
+    // integer-valued sums: exact in uint32 (int fold: colours <= 65535, samples per launch <= 65536) / in double
+    typename std::conditional<kIntFold, unsigned, double>::type a0 = 0, a1 = 0, a2 = 0;
+    const int ns = pp.s1 - pp.s0;
+
+    if (pp.max_bounces <= 0) {                        // degenerate: every call returns (2,2,5) at the depth check
+        n_rays = has_pixel ? (unsigned)ns : 0u;
+        a0 = 2 * ns; a1 = 2 * ns; a2 = 5 * ns;
+    } else {
         int s = pp.s0, depth = 0;
-        V3<T> O = cam, D;
-        {
-            rng.begin(pixel, (uint32_t)s, pp.k0, pp.k1);
+        bool alive = has_pixel && ns > 0;             // lane has a path in flight
+        bool more = alive;                            // lane still has samples to do (regen schedule)
+        V3<T> O = cam, D = mk<T>(T(0), T(0), T(-1));
+        auto start_sample = [&](int smp) {
+            depth = 0; O = cam;
+            rng.begin(pixel, (uint32_t)smp, pp.k0, pp.k1);
             uint32_t wa, wb;
             rng.pair(0u, wa, wb);
             D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
-        }
-        n_rays = 1;                                    // trace_ray_traditional call count, chandelier.py:432
+            n_rays++;                                 // trace_ray_traditional call count, chandelier.py:432
+        };
+        if (alive) start_sample(s);
         for (;;) {
-            // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
-            T t;
-            n_query++;
-            const int i = nearest<T, true>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes);
-            double leaf[3];
-            bool ended;
-            if (i < 0) { leaf[0] = 2.0; leaf[1] = 2.0; leaf[2] = 5.0; ended = true; }          // miss: Colour(2,2,5)
-            else {
-                n_inter++;
-                const typename M<T>::v4 m = S.g.sv.mat[i];
-                if (m.z != T(0)) {                                                              // emissive: its colour
-                    n_light++;
-                    if (sc.small && sc.small[i]) n_small++;
-                    const typename M<T>::v4 col = S.g.sv.col[i];
-                    leaf[0] = (double)col.x; leaf[1] = (double)col.y; leaf[2] = (double)col.z;
-                    ended = true;
-                } else {
-                    Hit<T> h;
-                    finish_hit<T>(S.g, O, D, i, t, h);
-                    st.idx[depth] = (uint32_t)i;
-                    st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
-                    const bool mirror = m.x > pp.mirror_threshold;
-                    T r1 = T(0), r2 = T(0);
-                    if (!mirror) {
-                        uint32_t wa, wb;
-                        rng.pair((uint32_t)depth + 1u, wa, wb);
-                        r1 = u01<T>(wa); r2 = u01<T>(wb);
+            bool ended = false;
+            int leaf0 = 2, leaf1 = 2, leaf2 = 5;      // miss / depth limit: Colour(2,2,5)
+            double lf0 = 2.0, lf1 = 2.0, lf2 = 5.0;
+            if (alive) {
+                // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
+                T t;
+                n_query++;
+                const int i = nearest<T, true, kBvh>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes);
+                if (i < 0) ended = true;
+                else {
+                    n_inter++;
+                    const typename M<T>::v4 m = S.g.sv.mat[i];
+                    if (m.z != T(0)) {                                               // emissive: its own colour
+                        n_light++;
+                        if (sc.small && sc.small[i]) n_small++;
+                        const typename M<T>::v4 col = S.g.sv.col[i];
+                        if constexpr (kIntFold) { leaf0 = (int)col.x; leaf1 = (int)col.y; leaf2 = (int)col.z; }
+                        else { lf0 = (double)col.x; lf1 = (double)col.y; lf2 = (double)col.z; }
+                        ended = true;
+                    } else {
+                        Hit<T> h;
+                        finish_hit<T>(S.g, O, D, i, t, h);
+                        st.idx[depth] = (uint32_t)i;
+                        st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
+                        const bool mirror = m.x > pp.mirror_threshold;
+                        T r1 = T(0), r2 = T(0);
+                        if (!mirror) {
+                            uint32_t wa, wb;
+                            rng.pair((uint32_t)depth + 1u, wa, wb);
+                            r1 = u01<T>(wa); r2 = u01<T>(wb);
+                        }
+                        D = bounce_direction<T>(D, h.n, mirror, r1, r2);
+                        O = h.p + h.n * T(0.001);
+                        depth++;
+                        n_rays++;                                                    // the recursive call ...
+                        ended = depth >= pp.max_bounces;                             // ... returns (2,2,5) at once
                     }
-                    D = bounce_direction<T>(D, h.n, mirror, r1, r2);
-                    O = h.p + h.n * T(0.001);
-                    depth++;
-                    n_rays++;                                                                   // the recursive call
-                    ended = depth >= pp.max_bounces;                                            // ... returns (2,2,5)
-                    if (ended) { leaf[0] = 2.0; leaf[1] = 2.0; leaf[2] = 5.0; }
                 }
             }
-            if (!ended) continue;
-            fold_path<T>(S.g, st, depth, leaf);
-            a0 += leaf[0]; a1 += leaf[1]; a2 += leaf[2];
-            if (++s >= pp.s1) break;
-            // ---- regenerate: next sample of this pixel
-            depth = 0; O = cam;
-            rng.begin(pixel, (uint32_t)s, pp.k0, pp.k1);
-            uint32_t wa, wb;
-            rng.pair(0u, wa, wb);
-            D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
-            n_rays++;
+            if (alive && ended) {
+                alive = false;
+                if constexpr (kIntFold) {
+                    int c[3] = {leaf0, leaf1, leaf2};
+                    fold_path_int<T>(S.g, st, depth, div255, c);
+                    a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
+                } else {
+                    double c[3] = {lf0, lf1, lf2};
+                    fold_path<T>(S.g, st, depth, c);
+                    a0 += c[0]; a1 += c[1]; a2 += c[2];
+                }
+                if constexpr (kRegen) {
+                    if (++s < pp.s1) { alive = true; start_sample(s); } else more = false;
+                }
+            }
+            if constexpr (kRegen) {
+                if (!more) break;
+            } else {
+                if (__any_sync(0xffffffffu, alive)) continue;      // wait for the warp's longest path
+                if (++s >= pp.s1) break;                           // s is warp-uniform in this schedule
+                if (has_pixel) { alive = true; start_sample(s); }
+            }
         }
-        }
+    }
+    if (has_pixel && ns > 0) {
         const size_t o = (size_t)y * pp.W + x;
-        typename M<T>::v4 out = M<T>::make4(T(a0), T(a1), T(a2), T(pp.s1 - pp.s0));
+        typename M<T>::v4 out = M<T>::make4(T(a0), T(a1), T(a2), T(ns));
         if (pp.accumulate) {
             const typename M<T>::v4 old = accum[o];
             out.x += old.x; out.y += old.y; out.z += old.z; out.w += old.w;
@@ -290,11 +330,12 @@ __global__ void sphere_disc_kernel(int m, const double *rays, const double *sphe
     o[5] = (double)n.x; o[6] = (double)n.y; o[7] = (double)n.z;
 }
 
-template <typename T, bool kShared>
+template <typename T, int kMode>
 __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, const double *rays, const int *suppress,
                                                          const int *bounces0, const int *through0, int max_bounces,
                                                          int shadow_max_bounces, double miss0, double miss1,
                                                          double miss2, double *term, double *rgb) {
+    RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
@@ -304,7 +345,7 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, 
     V3<T> O = mk<T>(T(r[0]), T(r[1]), T(r[2]));
     V3<T> D = normalise(mk<T>(T(r[3]), T(r[4]), T(r[5])));
     Counters ct = {0u, 0u, 0u};
-    Hit<T> h = trace_terminal<T>(S.g, O, D, suppress ? suppress[i] : RT_NO_ID_DEV, bounces0 ? bounces0[i] : 0,
+    Hit<T> h = trace_terminal<T, kBvh>(S.g, O, D, suppress ? suppress[i] : RT_NO_ID_DEV, bounces0 ? bounces0[i] : 0,
                                  max_bounces, through0 ? through0[i] : 0, ct);
     double *t = term + 10 * (size_t)i;
     t[0] = h.idx >= 0 ? 1.0 : 0.0; t[1] = (double)h.idx; t[2] = (double)h.bounces; t[3] = (double)h.through;
@@ -314,7 +355,7 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, 
         double *c = rgb + 3 * (size_t)i;
         if (h.idx >= 0) {
             T o[3];
-            terminal_rgb<T>(S.g, S.la, h, shadow_max_bounces, o, ct);
+            terminal_rgb<T, kBvh>(S.g, S.la, h, shadow_max_bounces, o, ct);
             c[0] = (double)o[0]; c[1] = (double)o[1]; c[2] = (double)o[2];
         } else { c[0] = miss0; c[1] = miss1; c[2] = miss2; }
     }
@@ -356,13 +397,13 @@ template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, i
 }
 
 // RL _calculate_reward (RL/ray_tracer_env.py:224-252); FB _calculate_reward (FB/ray_tracer_env.py:241-278)
-template <typename T>
+template <typename T, bool kBvh>
 RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, const Hit<T> &h, int bounce_count,
                          Counters &ct) {
     if (h.idx < 0) return -0.1;
     if (e.flavour == 1 && g.sv.ids[h.idx] == e.sun_id) return 10.0;
     T c[3];
-    terminal_rgb<T>(g, la, h, 0, c, ct);
+    terminal_rgb<T, kBvh>(g, la, h, 0, c, ct);
     if constexpr (M<T>::exact) {
         double brightness = (c[0] + c[1] + c[2]) / (3 * 255);
         double pen = -0.01 * bounce_count;
@@ -399,10 +440,11 @@ template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const E
 
 // reset (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142).  pixels == NULL: draw with Philox(seed) keyed by
 // the env index.  mask != NULL: only envs with mask[b] != 0 are reset.
-template <typename T, bool kShared>
+template <typename T, int kMode>
 __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T> e, const int *pixels,
                                                         const uint8_t *mask, uint32_t k0, uint32_t k1, float *obs,
                                                         int *pixels_out, unsigned long long *stats) {
+    RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
@@ -426,7 +468,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         if (e.cam_angle[0] != T(0) || e.cam_angle[1] != T(0) || e.cam_angle[2] != T(0))
             d = rotate<T>(d, mk<T>(e.cam_angle[0], e.cam_angle[1], e.cam_angle[2]));
         d = normalise(d);
-        Hit<T> h = trace_terminal<T>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
+        Hit<T> h = trace_terminal<T, kBvh>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
         env_store_hit<T>(e, b, h, d);
         e.bounce[b] = 0; e.through[b] = 0;
         e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
@@ -437,10 +479,11 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
 }
 
 // step (RL/ray_tracer_env.py:295-401, FB/ray_tracer_env.py:378-514)
-template <typename T, bool kShared>
+template <typename T, int kMode>
 __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
                                                        double *reward, uint8_t *terminated, uint8_t *truncated,
                                                        int *reason, double *info, unsigned long long *stats) {
+    RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
@@ -458,7 +501,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
         if (cur.idx < 0) {                                                   // ray already missed, :313-323
             rsn = 1; rw = -1.0; term = 1; info_total = e.total[b];
         } else if (bc >= e.max_bounces) {                                    // :325-337
-            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T>(S.g, S.la, e, cur, bc, ct);
+            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T, kBvh>(S.g, S.la, e, cur, bc, ct);
             e.total[b] += rw; info_total = e.total[b];
             rsn = 3; term = 1; trunc = 1;
         } else if (e.flavour == 1 && S.g.sv.ids[cur.idx] == e.sun_id) {      // FB :417-431 (total_reward not updated)
@@ -481,8 +524,8 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
                                       lx * tg.z + ly * bt.z + lz * n.z));
             if constexpr (M<T>::exact) D = normalise(D);                      // Ray() normalises again
             bc += 1;
-            Hit<T> nx = trace_terminal<T>(S.g, cur.p, D, S.g.sv.ids[cur.idx], bc, e.max_bounces, through, ct);
-            if (e.flavour == 0) rw = env_reward<T>(S.g, S.la, e, cur, bc, ct);    // reward at the PRE-update hit, :362
+            Hit<T> nx = trace_terminal<T, kBvh>(S.g, cur.p, D, S.g.sv.ids[cur.idx], bc, e.max_bounces, through, ct);
+            if (e.flavour == 0) rw = env_reward<T, kBvh>(S.g, S.la, e, cur, bc, ct);    // reward at the PRE-update hit, :362
             else if (nx.idx >= 0) {
                 if (S.g.sv.ids[nx.idx] == e.sun_id) { rw = 10.0; rsn = 4; term = 1; info_sun = 1.0; }
                 else { rw = env_lighting_reward<T>(S.g, e, nx); info_sun = 0.0; }
@@ -492,7 +535,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
             e.bounce[b] = bc; info_bounce = bc;
             if (nx.idx >= 0) {                                               // :373-381
                 T c[3];
-                terminal_rgb<T>(S.g, S.la, nx, 0, c, ct);
+                terminal_rgb<T, kBvh>(S.g, S.la, nx, 0, c, ct);
                 e.acc[b] = e.acc[b] + c[0]; e.acc[B + b] = e.acc[B + b] + c[1]; e.acc[2 * B + b] = e.acc[2 * B + b] + c[2];
             }
             if (e.flavour == 0) {
@@ -522,21 +565,34 @@ template <typename K> static cudaError_t allow_smem(K kernel, size_t bytes) {
     return cudaSuccess;
 }
 
+// kMode for a scene: shared-memory staging when it fits, hierarchy code only when a hierarchy exists
+template <typename T> static inline int mode_for(const SceneDev<T> &sc, size_t extra_smem = 0) {
+    const bool shared = smem_for(sc) + extra_smem <= RT_SMEM_LIMIT;
+    if (!shared) return 2;
+    return sc.bvh.nodes > 0 ? 1 : 0;
+}
+
+#define RT_DISPATCH_MODE(mode, KERNEL, grid, block, smem_bytes, st, ...)                                       \
+    do {                                                                                                        \
+        cudaError_t e__ = cudaSuccess;                                                                          \
+        switch (mode) {                                                                                         \
+            case 0: e__ = allow_smem(KERNEL<T, 0>, smem_bytes); if (e__ != cudaSuccess) return e__;             \
+                    KERNEL<T, 0><<<grid, block, smem_bytes, st>>>(__VA_ARGS__); break;                          \
+            case 1: e__ = allow_smem(KERNEL<T, 1>, smem_bytes); if (e__ != cudaSuccess) return e__;             \
+                    KERNEL<T, 1><<<grid, block, smem_bytes, st>>>(__VA_ARGS__); break;                          \
+            default: KERNEL<T, 2><<<grid, block, 0, st>>>(__VA_ARGS__); break;                                  \
+        }                                                                                                       \
+    } while (0)
+
 template <typename T>
 cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
                            unsigned long long *stats, cudaStream_t st) {
     const int rows = wp.y1 - wp.y0;
     if (rows <= 0 || wp.W <= 0) return cudaSuccess;
     dim3 grid((wp.W + 31) / 32, (rows + 7) / 8), block(256);
-    const size_t sm = smem_for(sc);
     using v4 = typename M<T>::v4;
-    if (sm <= RT_SMEM_LIMIT) {
-        cudaError_t e = allow_smem(whitted_kernel<T, true>, sm);
-        if (e != cudaSuccess) return e;
-        whitted_kernel<T, true><<<grid, block, sm, st>>>(sc, wp, (v4 *)accum, hit, stats);
-    } else {
-        whitted_kernel<T, false><<<grid, block, 0, st>>>(sc, wp, (v4 *)accum, hit, stats);
-    }
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, whitted_kernel, grid, block, smem_for(sc), st, sc, wp, (v4 *)accum, hit, stats);
     return cudaGetLastError();
 }
 
@@ -546,15 +602,24 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     const int rows = pp.y1 - pp.y0;
     if (rows <= 0 || pp.W <= 0) return cudaSuccess;
     dim3 grid((pp.W + 31) / 32, (rows + 7) / 8), block(256);
-    const size_t sm = smem_for(sc);
     using v4 = typename M<T>::v4;
-    if (sm <= RT_SMEM_LIMIT) {
-        cudaError_t e = allow_smem(path_kernel<T, true>, sm);
-        if (e != cudaSuccess) return e;
-        path_kernel<T, true><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats);
-    } else {
-        path_kernel<T, false><<<grid, block, 0, st>>>(sc, pp, (v4 *)accum, stats);
+    const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold
+    const int mode = mode_for(sc, extra);
+    const size_t sm = (mode < 2 ? smem_for(sc) : 0) + extra;
+    cudaError_t e = cudaSuccess;
+#define RT_PATH_CASE(M_, F_, R_)                                                                                   \
+    { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \
+      path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats); }
+    const int variant = mode * 4 + (pp.int_fold ? 2 : 0) + (pp.regenerate ? 1 : 0);
+    switch (variant) {
+        case 0: RT_PATH_CASE(0, false, false) break;   case 1: RT_PATH_CASE(0, false, true) break;
+        case 2: RT_PATH_CASE(0, true, false) break;    case 3: RT_PATH_CASE(0, true, true) break;
+        case 4: RT_PATH_CASE(1, false, false) break;   case 5: RT_PATH_CASE(1, false, true) break;
+        case 6: RT_PATH_CASE(1, true, false) break;    case 7: RT_PATH_CASE(1, true, true) break;
+        case 8: RT_PATH_CASE(2, false, false) break;   case 9: RT_PATH_CASE(2, false, true) break;
+        case 10: RT_PATH_CASE(2, true, false) break;   default: RT_PATH_CASE(2, true, true) break;
     }
+#undef RT_PATH_CASE
     return cudaGetLastError();
 }
 
@@ -578,17 +643,10 @@ cudaError_t launch_trace_rays(const SceneDev<T> &sc, int m, const double *rays, 
                               const int *through0, int max_bounces, int shadow_max_bounces, const double miss[3],
                               double *term, double *rgb, cudaStream_t st) {
     if (m <= 0) return cudaSuccess;
-    const size_t sm = smem_for(sc);
     const int block = 256, grid = (m + block - 1) / block;
-    if (sm <= RT_SMEM_LIMIT) {
-        cudaError_t e = allow_smem(trace_rays_kernel<T, true>, sm);
-        if (e != cudaSuccess) return e;
-        trace_rays_kernel<T, true><<<grid, block, sm, st>>>(sc, m, rays, suppress, bounces0, through0, max_bounces,
-                                                            shadow_max_bounces, miss[0], miss[1], miss[2], term, rgb);
-    } else {
-        trace_rays_kernel<T, false><<<grid, block, 0, st>>>(sc, m, rays, suppress, bounces0, through0, max_bounces,
-                                                            shadow_max_bounces, miss[0], miss[1], miss[2], term, rgb);
-    }
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, trace_rays_kernel, grid, block, smem_for(sc), st, sc, m, rays, suppress, bounces0, through0,
+                     max_bounces, shadow_max_bounces, miss[0], miss[1], miss[2], term, rgb);
     return cudaGetLastError();
 }
 
@@ -596,16 +654,11 @@ template <typename T>
 cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
                              uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st) {
     if (e.B <= 0) return cudaSuccess;
-    const size_t sm = smem_for(sc);
     const int block = 128, grid = (e.B + block - 1) / block;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    if (sm <= RT_SMEM_LIMIT) {
-        cudaError_t err = allow_smem(env_reset_kernel<T, true>, sm);
-        if (err != cudaSuccess) return err;
-        env_reset_kernel<T, true><<<grid, block, sm, st>>>(sc, e, pixels, mask, k0, k1, obs, pixels_out, stats);
-    } else {
-        env_reset_kernel<T, false><<<grid, block, 0, st>>>(sc, e, pixels, mask, k0, k1, obs, pixels_out, stats);
-    }
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, env_reset_kernel, grid, block, smem_for(sc), st, sc, e, pixels, mask, k0, k1, obs, pixels_out,
+                     stats);
     return cudaGetLastError();
 }
 
@@ -614,17 +667,10 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
                             uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
                             unsigned long long *stats, cudaStream_t st) {
     if (e.B <= 0) return cudaSuccess;
-    const size_t sm = smem_for(sc);
     const int block = 128, grid = (e.B + block - 1) / block;
-    if (sm <= RT_SMEM_LIMIT) {
-        cudaError_t err = allow_smem(env_step_kernel<T, true>, sm);
-        if (err != cudaSuccess) return err;
-        env_step_kernel<T, true><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason,
-                                                          info, stats);
-    } else {
-        env_step_kernel<T, false><<<grid, block, 0, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason,
-                                                          info, stats);
-    }
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, env_step_kernel, grid, block, smem_for(sc), st, sc, e, actions, obs, reward, terminated,
+                     truncated, reason, info, stats);
     return cudaGetLastError();
 }
 

@@ -24,6 +24,8 @@ template <typename T> struct PathDev {
     T mirror_threshold;
     uint32_t k0, k1;
     int accumulate;
+    int int_fold;                // every leaf colour is an integer in [0, 65535]: integer fold + uint32 accumulators
+    int regenerate;              // 1: path-regeneration schedule, 0: lock-step schedule (rt_kernels.cuh)
 };
 
 // batched RayTracerEnv state (SoA, [3][B] for vectors)

@@ -55,6 +55,13 @@ template <typename T> RT_DEV bool sphere_test(V3<T> O, V3<T> D, typename M<T>::v
     }
 }
 
+// key a candidate hit is ranked by
+template <typename T, bool kAbs> RT_DEV T hit_key(V3<T> O, V3<T> D, T t) {
+    if constexpr (!kAbs) return t;
+    else if constexpr (M<T>::exact) { V3<T> p = O + D * t, d = p - O; return ::sqrt(d.x * d.x + d.y * d.y + d.z * d.z); }
+    else return fabsf(t);
+}
+
 // Nearest hit over the scene.  kAbs = false: Algorithm A, smallest SIGNED distance wins (ray.py:10-20);
 // kAbs = true: Algorithm B, smallest |hit - origin| wins (chandelier.py:438-444).  First in list wins ties.
 // `suppress` is a Sphere.id (ray.py:165) or RT_NO_ID_DEV.  Returns the scene index or -1; t = signed distance.
@@ -64,31 +71,67 @@ template <typename T, bool kAbs> RT_DEV void consider(const Geo<T> &g, int i, V3
     tests++;
     T t;
     if (!sphere_test<T>(O, D, g.sv.sph[i], 0, t)) return;
-    T key;
-    if constexpr (!kAbs) key = t;
-    else if constexpr (M<T>::exact) { V3<T> p = O + D * t, d = p - O; key = ::sqrt(d.x * d.x + d.y * d.y + d.z * d.z); }
-    else key = fabsf(t);
-    if (key < best || (g.bvh.nodes != 0 && key == best && i < bi)) { best = key; bt = t; bi = i; }
+    const T key = hit_key<T, kAbs>(O, D, t);
+    if (key < best || (key == best && i < bi)) { best = key; bt = t; bi = i; }
 }
 
-template <typename T, bool kAbs>
+// FP32 brute force, four spheres per trip: 13 FP32 ops per sphere (L, tca, f = L - tca D, |f|^2, r^2 - |f|^2), the
+// eight sign bits of (tca, disc) folded with LOP3 so the common "all four miss" case costs one branch.
+template <bool kAbs>
+RT_DEV void brute4(const float4 *sph, int n, V3<float> O, V3<float> D, float &best, float &bt, int &bi) {
+    int i = 0;
+#pragma unroll 2
+    for (; i + 4 <= n; i += 4) {
+        float tca[4], disc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4 s = sph[i + k];
+            const V3<float> L = mk<float>(s.x - O.x, s.y - O.y, s.z - O.z);
+            tca[k] = dot(L, D);
+            const V3<float> f = L - D * tca[k];
+            disc[k] = fmaf(s.w, s.w, -dot(f, f));
+        }
+        // sign bit clear in BOTH tca and disc <=> candidate; any candidate <=> AND over k of (tca|disc) has it clear
+        const int any = (__float_as_int(tca[0]) | __float_as_int(disc[0])) & (__float_as_int(tca[1]) | __float_as_int(disc[1])) &
+                        (__float_as_int(tca[2]) | __float_as_int(disc[2])) & (__float_as_int(tca[3]) | __float_as_int(disc[3]));
+        if (any >= 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (tca[k] >= 0.f && disc[k] >= 0.f) {
+                    const float t = tca[k] - M<float>::sqrt(disc[k]);
+                    const float key = kAbs ? fabsf(t) : t;
+                    if (key < best) { best = key; bt = t; bi = i + k; }
+                }
+            }
+        }
+    }
+    for (; i < n; ++i) {
+        float t;
+        if (sphere_test<float>(O, D, sph[i], 0, t)) {
+            const float key = kAbs ? fabsf(t) : t;
+            if (key < best) { best = key; bt = t; bi = i; }
+        }
+    }
+}
+
+template <typename T, bool kAbs, bool kBvh>
 RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests) {
     T best = M<T>::inf(), bt = T(0);
     int bi = -1;
-    if (g.bvh.nodes == 0) {
+    bool brute = true;
+    if constexpr (kBvh) brute = g.bvh.nodes == 0;
+    if (brute) {
         const int n = g.sv.n;
         if (suppress == RT_NO_ID_DEV) {
-#pragma unroll 4
-            for (int i = 0; i < n; ++i) {
-                T t;
-                if (sphere_test<T>(O, D, g.sv.sph[i], 0, t)) {
-                    T key;
-                    if constexpr (!kAbs) key = t;
-                    else if constexpr (M<T>::exact) {
-                        V3<T> p = O + D * t, d = p - O;
-                        key = ::sqrt(d.x * d.x + d.y * d.y + d.z * d.z);
-                    } else key = fabsf(t);
-                    if (key < best) { best = key; bt = t; bi = i; }
+            if constexpr (!M<T>::exact) brute4<kAbs>(g.sv.sph, n, O, D, best, bt, bi);
+            else {
+#pragma unroll 2
+                for (int i = 0; i < n; ++i) {
+                    T t;
+                    if (sphere_test<T>(O, D, g.sv.sph[i], 0, t)) {
+                        const T key = hit_key<T, kAbs>(O, D, t);
+                        if (key < best) { best = key; bt = t; bi = i; }
+                    }
                 }
             }
             tests += n;
@@ -96,7 +139,7 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
 #pragma unroll 2
             for (int i = 0; i < n; ++i) consider<T, kAbs>(g, i, O, D, suppress, best, bt, bi, tests);
         }
-    } else {
+    } else if constexpr (kBvh) {
         for (int k = 0; k < g.bvh.n_huge; ++k) consider<T, kAbs>(g, g.bvh.huge[k], O, D, suppress, best, bt, bi, tests);
         // float boxes (conservatively grown at build time) cull for both precisions
         float ox = (float)O.x, oy = (float)O.y, oz = (float)O.z;
@@ -182,7 +225,7 @@ struct Counters { unsigned queries, tests, boxes; };
 // Ray.nearestSphereIntersect (ray.py:160-231) with the recursion unrolled: a mirror that finds nothing returns
 // ITSELF (ray.py:198-201), glass that finds nothing returns None (ray.py:226-229), so a dead-ended chain yields the
 // most recent mirror hit, else None.  D is a unit vector.
-template <typename T>
+template <typename T, bool kBvh>
 RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, int bounces, int max_bounces, int through,
                              Counters &ct) {
     Hit<T> fallback;
@@ -191,7 +234,7 @@ RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, in
     for (;;) {
         ct.queries++;
         T t;
-        int i = nearest<T, false>(g, O, D, suppress, t, ct.tests, ct.boxes);
+        int i = nearest<T, false, kBvh>(g, O, D, suppress, t, ct.tests, ct.boxes);
         if (i < 0) return fallback;                           // ray.py:170-171
         if (bounces > max_bounces) return fallback;           // ray.py:173-174
         Hit<T> h;
@@ -233,7 +276,7 @@ template <typename T> struct LightsA {
 };
 
 // Intersection.terminalRGB (ray.py:37-65) + Colour.illuminate (colour.py:21-29, round half to even, not clamped)
-template <typename T>
+template <typename T, bool kBvh>
 RT_DEV void terminal_rgb(const Geo<T> &g, const LightsA<T> &lt, const Hit<T> &h, int shadow_max_bounces, T out[3],
                          Counters &ct) {
     const typename M<T>::v4 m = g.sv.mat[h.idx], col = g.sv.col[h.idx];
@@ -251,7 +294,7 @@ RT_DEV void terminal_rgb(const Geo<T> &g, const LightsA<T> &lt, const Hit<T> &h,
         if (own == pid) continue;
         const typename M<T>::v4 pp = lt.p_pos[k], pc = lt.p_col[k];
         V3<T> vl = mk<T>(pp.x, pp.y, pp.z) - h.p;
-        Hit<T> s = trace_terminal<T>(g, h.p, normalise(vl), own, 0, shadow_max_bounces, 0, ct);
+        Hit<T> s = trace_terminal<T, kBvh>(g, h.p, normalise(vl), own, 0, shadow_max_bounces, 0, ct);
         if (s.idx < 0 || g.sv.ids[s.idx] != pid) continue;
         T ang = angle_between<T>(h.n, vl);
         const int fn = lt.p_func[k];
@@ -299,6 +342,22 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
     }
 }
 
+// Same fold for integer-valued leaves (every scene of the reference: colours are 0-255 ints): tot is then an integer
+// in [0,255] at every level, so tot/255.0 comes from a 256-entry table of correctly rounded doubles (identical to
+// the division) and the running colour stays an int.  Still a double multiply: the truncation sees the same product.
+template <typename T>
+RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3]) {
+    for (int k = depth - 1; k >= 0; --k) {
+        const typename M<T>::v4 col = g.sv.col[st.idx[k]];
+        const uint32_t d = st.direct[k];
+        const int t0 = min(255, (int)(d & 255u) + c[0]), t1 = min(255, (int)((d >> 8) & 255u) + c[1]),
+                  t2 = min(255, (int)((d >> 16) & 255u) + c[2]);
+        c[0] = __double2int_rz(__dmul_rn((double)col.x, div255[t0]));
+        c[1] = __double2int_rz(__dmul_rn((double)col.y, div255[t1]));
+        c[2] = __double2int_rz(__dmul_rn((double)col.z, div255[t2]));
+    }
+}
+
 // direct light at a non-emissive hit: every light sphere, NO occlusion test (chandelier.py:463-477)
 template <typename T>
 RT_DEV uint32_t direct_light(const LightsB<T> &lb, int hit_idx, V3<T> p, V3<T> n) {
@@ -314,7 +373,7 @@ RT_DEV uint32_t direct_light(const LightsB<T> &lb, int hit_idx, V3<T> p, V3<T> n
             T dist = ::sqrt(dot(tl, tl)), att = 1.0 / (dist * dist);
             d0 += ::trunc(lc.x * ca * att * 0.3); d1 += ::trunc(lc.y * ca * att * 0.3); d2 += ::trunc(lc.z * ca * att * 0.3);
         } else {
-            T q = dot(tl, tl), inv = rsqrtf(q);
+            T q = dot(tl, tl), inv = M<T>::rsqrt(q);
             T ca = dot(n, tl) * inv;
             if (!(ca > 0.f)) continue;
             T s = ca * (inv * inv) * 0.3f;
@@ -338,7 +397,7 @@ RT_DEV V3<T> bounce_direction(V3<T> D, V3<T> n, bool mirror, T r1, T r2) {
         T theta = ::acos(::sqrt(r1)), phi = 2 * 3.14159265358979323846 * r2;
         st = ::sin(theta); ct = ::cos(theta); sp = ::sin(phi); cp = ::cos(phi);
     } else {
-        ct = sqrtf(r1); st = sqrtf(1.f - r1);                 // cos/sin(acos(sqrt r1))
+        ct = M<T>::sqrt(r1); st = M<T>::sqrt(1.f - r1);                 // cos/sin(acos(sqrt r1))
         sincospif(2.f * r2, &sp, &cp);
     }
     V3<T> tg = M<T>::fabs(n.z) > T(0.9) ? mk<T>(1, 0, 0) : cross(mk<T>(0, 0, 1), n);

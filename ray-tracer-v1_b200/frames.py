@@ -1,0 +1,115 @@
+"""Persistent frame state on one GPU: scene handle, accumulation / image buffers in HBM and a pinned host image.
+
+``FrameContext`` is what the render entry points and the multi-GPU sharding layer (distributed.py) share.  A frame is
+rendered in three stream-ordered launches -- path/whitted kernel -> resolve kernel -> one D2H copy of the float32
+image into page-locked memory -- and nothing else crosses PCIe except the few KB of flattened scene.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+__all__ = ["FrameContext"]
+
+
+class FrameContext:
+    def __init__(self, device=0):
+        self.device = device
+        self.scene = None
+        self._key = None
+        self.accum = self.image = self.stats = self.hit = None
+        self.host_image = self.host_stats = None
+        self.h2d_bytes = 0          # bytes of the last scene upload
+        self.d2h_bytes = 0          # bytes of the last read-back
+
+    # ---- scene -----------------------------------------------------------------------------------------------
+    def set_scene(self, fs, lbvh=None):
+        """(Re)upload the flattened scene; allocations are reused when the census is unchanged."""
+        if self.scene is None:
+            self.scene = nat.DeviceScene(fs, self.device)
+        else:
+            self.scene.update(fs)
+        n, nG, nP, nL = fs.radius.shape[0], fs.g_strength.shape[0], fs.p_strength.shape[0], fs.l_index.shape[0]
+        self.h2d_bytes = (16 + 32) * (3 * n + 2 * (nG + nP + nL)) + 2 * 4 * (n + nG + 2 * nP + nL) + n
+        if lbvh or (lbvh is None and self.scene.n > 256):
+            self.scene.build_lbvh()
+        return self.scene
+
+    # ---- buffers ---------------------------------------------------------------------------------------------
+    def ensure(self, W, H, precision=nat.F32, want_hit=False):
+        key = (int(W), int(H), precision)
+        if self._key != key:
+            for b in (self.accum, self.image, self.stats, self.hit, self.host_image, self.host_stats):
+                if b is not None:
+                    b.free()
+            ft = np.float64 if precision == nat.F64 else np.float32
+            self.accum = nat.DeviceBuffer((H, W, 4), ft, self.device)
+            self.image = nat.DeviceBuffer((H, W, 3), np.float32, self.device)
+            self.stats = nat.DeviceBuffer(8, np.uint64, self.device)
+            self.host_image = nat.PinnedArray((H, W, 3), np.float32)
+            self.host_stats = nat.PinnedArray(8, np.uint64)
+            self.hit = None
+            self._key = key
+        if want_hit and self.hit is None:
+            self.hit = nat.DeviceBuffer((H, W), np.int32, self.device)
+
+    # ---- frames ----------------------------------------------------------------------------------------------
+    def render_path(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, precision=nat.F32, rows=None,
+                    samples=None, resolve=True, read_back=True, stream=None):
+        """Algorithm B over rows x samples of this rank.  Returns (host image view or None, stats u64[8] or None)."""
+        self.ensure(W, H, precision)
+        L = nat.lib()
+        p = self.scene.path_params(cam, W, H, spp, max_bounces, mirror_threshold, seed=seed, fov=fov, rows=rows,
+                                   samples=samples)
+        self.stats.fill(0, stream)
+        self.scene.render_path(p, self.accum, precision, stats=self.stats, stream=stream)
+        self.launches = 1
+        if resolve:
+            self.scene.resolve(self.accum, W, H, p.s1 - p.s0, self.image, precision, rows=(p.y0, p.y1), stream=stream)
+            self.launches += 1
+        if not read_back:
+            return None, None
+        return self.read_back(W, H, (p.y0, p.y1), stream)
+
+    def render_whitted(self, cam, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0, miss=None, seed=0, prenorm=False,
+                       precision=nat.F32, rows=None, samples=None, read_back=True, stream=None):
+        W, H = len(X), len(Y)
+        self.ensure(W, H, precision)
+        p = self.scene.whitted_params(cam, X, Y, spp=spp, max_bounces=max_bounces, shadow_max_bounces=shadow_max_bounces,
+                                      miss=miss, seed=seed, prenorm=prenorm, rows=rows, samples=samples)
+        self.stats.fill(0, stream)
+        self.scene.render_whitted(p, self.accum, precision, stats=self.stats, stream=stream)
+        self.scene.resolve(self.accum, W, H, p.s1 - p.s0, self.image, precision, rows=(p.y0, p.y1), stream=stream)
+        self.launches = 2
+        if not read_back:
+            return None, None
+        return self.read_back(W, H, (p.y0, p.y1), stream)
+
+    def read_back(self, W, H, rows, stream=None):
+        """D2H of the resolved rows (float32) + the stats block into pinned memory; synchronises the stream."""
+        L = nat.lib()
+        y0, y1 = rows
+        off, nbytes = y0 * W * 3 * 4, (y1 - y0) * W * 3 * 4
+        if nbytes:
+            nat.check(L.rt_memcpy_d2h(self.device, self.host_image.ptr + off, self.image.ptr + off, nbytes, stream))
+        nat.check(L.rt_memcpy_d2h(self.device, self.host_stats.ptr, self.stats.ptr, 64, stream))
+        nat.check(L.rt_stream_sync(self.device, stream))
+        self.d2h_bytes = nbytes + 64
+        return self.host_image.array, self.host_stats.array
+
+    def close(self):
+        for b in (self.accum, self.image, self.stats, self.hit, self.host_image, self.host_stats):
+            if b is not None:
+                b.free()
+        self.accum = self.image = self.stats = self.hit = self.host_image = self.host_stats = None
+        self._key = None
+        if self.scene is not None:
+            self.scene.close()
+            self.scene = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,206 @@
+"""Render entry points of the reference, backed by the CUDA kernels.
+
+* ``TraditionalRenderer``        FB/fb_vs_traditional_chandelier.py:393-554 (Algorithm B; ``mirror_threshold`` 0, the
+                                 chandelier flavour) and ``ComplexTraditionalRenderer`` FB/fb_vs_traditional_complex.py:262-422
+                                 (threshold 0.9).  Same attribute-injection style (``.scene .light_sources .small_lights
+                                 .camera_position``), same ``render(width, height, samples_per_pixel, max_bounces)`` and
+                                 ``stats`` keys.
+* ``CustomSceneExperiment``      RL/output5.py:264 -- ``render_true_original(scene, path)`` (:416-533) and
+                                 ``render_custom_scene(scene, 'traditional', path)`` (:1420-1525) (Algorithm A).
+* ``render_whitted`` / ``render_path``  the plain functions underneath (flat scene in, numpy image out).
+
+Every call re-flattens the scene (the reference's scenes are mutable lists) and uploads it; frames are rendered and
+resolved on the GPU and only the float32 image (plus, on request, the raw sums) comes back to the host.
+"""
+import time
+from pathlib import Path
+
+import numpy as np
+
+from . import _native as nat
+from .frames import FrameContext
+from .colour import Colour
+from .light import GlobalLight, PointLight
+from .material import Material
+from .object import Sphere
+from .scene import flatten_scene
+from .scenes import custom_scene_grid, notebook_grid
+from .vector import Vector
+
+__all__ = ["render_whitted", "render_path", "TraditionalRenderer", "ComplexTraditionalRenderer",
+           "CustomSceneExperiment", "save_png"]
+
+_PREC = {"f32": nat.F32, "fp32": nat.F32, "float32": nat.F32, nat.F32: nat.F32,
+         "f64": nat.F64, "fp64": nat.F64, "float64": nat.F64, "double": nat.F64}
+
+
+def _precision(p):
+    try:
+        return _PREC[p]
+    except KeyError:
+        raise ValueError(f"unknown precision {p!r}") from None
+
+
+def _xyz(v):
+    return (float(v.x), float(v.y), float(v.z)) if hasattr(v, "x") else tuple(float(c) for c in v)
+
+
+def save_png(image, path):
+    """Raw framebuffer -> 8-bit PNG (the reference saves a matplotlib figure; this writes the pixels themselves)."""
+    from PIL import Image
+    Image.fromarray((np.clip(image, 0, 1) * 255.0 + 0.5).astype(np.uint8)).save(str(path))
+
+
+def render_whitted(fs, camera, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0, miss=None, seed=0, prenorm=False,
+                   precision="f32", device=0, return_raw=False):
+    """Algorithm A frame over the direction grid (X[i], Y[j], -1) -> float32 image [H,W,3] (``int(sum/spp)/255``).
+
+    return_raw=True also returns (sums [H,W,4], hit [H,W] int32, stats dict)."""
+    sc = nat.DeviceScene(fs, device)
+    try:
+        p = sc.whitted_params(_xyz(camera), X, Y, spp=spp, max_bounces=max_bounces, shadow_max_bounces=shadow_max_bounces,
+                              miss=miss, seed=seed, prenorm=prenorm)
+        image, sums, hit, st = sc.render_whitted_host(p, _precision(precision), want_accum=return_raw, want_hit=return_raw)
+    finally:
+        sc.close()
+    if return_raw:
+        return image, sums, hit, {"primary_rays": int(st[0]), "queries": int(st[4]), "sphere_tests": int(st[5])}
+    return image
+
+
+def render_path(fs, camera, width, height, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, precision="f32",
+                device=0, lbvh=None, return_raw=False):
+    """Algorithm B frame -> float32 image [H,W,3] (``sum // spp / 255``).  lbvh: None = build the on-device LBVH when
+    the scene has more than 256 spheres, True/False to force."""
+    sc = nat.DeviceScene(fs, device)
+    try:
+        if lbvh or (lbvh is None and sc.n > 256):
+            sc.build_lbvh()
+        p = sc.path_params(_xyz(camera), width, height, spp, max_bounces, mirror_threshold, seed=seed, fov=fov)
+        image, sums, st = sc.render_path_host(p, _precision(precision), want_accum=return_raw)
+    finally:
+        sc.close()
+    stats = {"total_rays": int(st[0]), "total_intersections": int(st[1]), "light_hits": int(st[2]),
+             "small_light_hits": int(st[3]), "queries": int(st[4]), "sphere_tests": int(st[5]), "aabb_tests": int(st[6])}
+    if return_raw:
+        return image, sums, stats
+    return image, stats
+
+
+class TraditionalRenderer:
+    """Drop-in for the reference's ``TraditionalRenderer`` (chandelier flavour: a sphere mirrors when
+    ``material.reflective > 0``, FB/fb_vs_traditional_chandelier.py:481).
+
+    The reference draws jitter and bounce directions from the global ``np.random`` stream; here they come from
+    Philox4x32-10 keyed (pixel, sample, bounce) with ``self.seed`` (``None`` = a fresh seed per render), so a render is
+    reproducible and independent of how it is sharded."""
+
+    mirror_threshold = 0.0
+
+    def __init__(self, device=0, precision="f32", seed=None):
+        self.scene = []
+        self.camera_position = Vector(0, 2, 0)
+        self.camera_angle = None  # unused, as in the reference
+        self.global_lights = []
+        self.point_lights = []
+        self.light_sources = []
+        self.small_lights = []
+        self.stats = {'total_rays': 0, 'total_intersections': 0, 'light_hits': 0, 'small_light_hits': 0,
+                      'render_time': 0, 'rays_per_second': 0}
+        self.device, self.precision, self.seed = device, precision, seed
+        self._renders = 0
+        self._ctx = None            # persistent FrameContext (HBM buffers + pinned host image), created on first render
+
+    def set_render_settings(self, width=200, height=150, max_bounces=3, samples_per_pixel=16):
+        self.image_width = width
+        self.image_height = height
+        self.max_bounces = max_bounces
+        self.samples_per_pixel = samples_per_pixel
+        self.aspect_ratio = width / height
+        self.fov = 60
+
+    def flat_scene(self):
+        return flatten_scene(self.scene, background_colour=Colour(2, 2, 5), light_sources=self.light_sources,
+                             small_lights=self.small_lights)
+
+    def render(self, width=200, height=150, samples_per_pixel=4, max_bounces=3):
+        self.set_render_settings(width, height, max_bounces, samples_per_pixel)
+        self.stats = {k: 0 for k in self.stats}
+        start = time.time()
+        seed = self.seed if self.seed is not None else (time.time_ns() ^ (self._renders * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
+        self._renders += 1
+        if self._ctx is None:
+            self._ctx = FrameContext(self.device)
+        self._ctx.set_scene(self.flat_scene())          # re-flattened every render: the scene list is mutable
+        view, st = self._ctx.render_path(_xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
+                                         self.mirror_threshold, seed=seed, fov=self.fov,
+                                         precision=_precision(self.precision))
+        image = view.copy()                             # a fresh array per render, like the reference
+        for i, k in enumerate(('total_rays', 'total_intersections', 'light_hits', 'small_light_hits')):
+            self.stats[k] = int(st[i])
+        render_time = time.time() - start
+        self.stats['render_time'] = render_time
+        if render_time > 0:
+            self.stats['rays_per_second'] = self.stats['total_rays'] / render_time
+        return image
+
+
+class ComplexTraditionalRenderer(TraditionalRenderer):
+    """The complex-scene flavour (FB/fb_vs_traditional_complex.py:262-422): mirrors only when ``reflective > 0.9`` (:349)."""
+    mirror_threshold = 0.9
+
+    def __init__(self, device=0, precision="f32", seed=None):
+        super().__init__(device, precision, seed)
+        self.camera_position = Vector(0, 0, 12)
+
+
+class CustomSceneExperiment:
+    """The traditional-method render entries of RL/output5.py's ``CustomSceneExperiment``."""
+
+    def __init__(self, output_dir="./custom_scene_results", device=0, precision="f32", seed=0):
+        self.output_dir = Path(output_dir)
+        self.output_dir.mkdir(parents=True, exist_ok=True)
+        self.config = {'max_bounces': 6, 'image_width': 200, 'image_height': 200, 'samples_per_pixel': 16}
+        self.timing_data = {'traditional': []}
+        self.rendered_images = {}
+        self.device, self.precision, self.seed = device, precision, seed
+
+    @staticmethod
+    def _as_rendered(scene_spheres):
+        """RL/output5.py:447-486 / :543-578: sun id 7 replaced by an id-0 sun appended last, fixed light set."""
+        sun = Sphere(id=0, centre=Vector(-0.6, 0.2, 6), radius=0.1, material=Material(emitive=True),
+                     colour=Colour(255, 255, 204))
+        spheres = [s for s in scene_spheres if not (hasattr(s, 'id') and s.id == 7)]
+        spheres.append(sun)
+        gl = [GlobalLight(vector=Vector(3, 1, -0.75), colour=Colour(20, 20, 255), strength=1,
+                          max_angle=np.radians(90), func=0)]
+        pl = [PointLight(id=sun.id, position=sun.centre, colour=sun.colour, strength=1, max_angle=np.radians(90), func=-1)]
+        return flatten_scene(spheres, gl, pl, Colour(2, 2, 5))
+
+    def render_true_original(self, scene_spheres, save_path=None):
+        """601x601 notebook grid, depth 5, direction NOT pre-normalised (RL/output5.py:416-533) -> image."""
+        X, Y = notebook_grid(300, 0.01 / 3)
+        fs = self._as_rendered(scene_spheres)
+        image = render_whitted(fs, (0, 0, 1), X, Y, spp=1, max_bounces=5, miss=(2, 2, 5), prenorm=False,
+                               precision=self.precision, device=self.device)
+        if save_path is not None:
+            save_png(image, save_path)
+        return image
+
+    def render_custom_scene(self, scene_spheres, method, save_path=None):
+        """``render_custom_scene(scene, 'traditional', path)`` (RL/output5.py:1420-1525) -> (render_time, image)."""
+        if method != 'traditional':
+            raise NotImplementedError("only the traditional method is part of the hot path (SURVEY.md section 2, rows 12-13)")
+        width, height = self.config['image_width'], self.config['image_height']
+        spp = self.config['samples_per_pixel']
+        start = time.time()
+        X, Y = custom_scene_grid(width, height)
+        fs = self._as_rendered(scene_spheres)
+        image = render_whitted(fs, (0, 0, 1), X, Y, spp=spp, max_bounces=self.config['max_bounces'], miss=(2, 2, 5),
+                               seed=self.seed, prenorm=True, precision=self.precision, device=self.device)
+        render_time = time.time() - start
+        self.timing_data['traditional'].append(render_time)
+        self.rendered_images[method] = image
+        if save_path is not None:
+            save_png(image, save_path)
+        return render_time, image

@@ -163,6 +163,34 @@ def test_path_shards_compose(nat, precision):
     sc.close()
 
 
+def test_path_schedules_agree(nat):
+    """Lock-step and path-regeneration schedules are two orders of the same arithmetic: identical sums and counters."""
+    for name in ("path_chandelier_48x27", "path_complex_48x27"):
+        z, fs = load_golden(name)
+        sc = nat.DeviceScene(fs)
+        out = []
+        for schedule in (0, 1):
+            p = sc.path_params(z["cam"], 200, 120, 5, int(z["max_bounces"]), float(z["mirror_threshold"]), seed=77,
+                               schedule=schedule)
+            _, sums, stats = sc.render_path_host(p, nat.F32)
+            out.append((sums, stats))
+        assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+        sc.close()
+
+
+def test_path_non_integer_colours_use_the_double_fold(nat, orc):
+    """A scene whose colours are not integers takes the double-division fold; FP64 still equals the oracle exactly."""
+    z, fs = load_golden("path_complex_48x27")
+    fs.colour = fs.colour + 0.37
+    fs.l_colour = fs.l_colour + 0.37
+    W, H, spp = 64, 36, 3
+    sums_o, st_o = orc.render_path(fs, z["cam"], W, H, spp, 5, 0.9, seed=4)
+    sc = nat.DeviceScene(fs)
+    _, sums, stats = sc.render_path_host(sc.path_params(z["cam"], W, H, spp, 5, 0.9, seed=4), nat.F64)
+    assert np.array_equal(sums[..., :3], sums_o) and int(stats[0]) == st_o["total_rays"]
+    sc.close()
+
+
 def test_path_matches_oracle_larger(nat, orc):
     """Seeded 160x90 x 8 spp frames of both Algorithm-B scenes: FP64 CUDA == oracle exactly."""
     for name in ("path_chandelier_48x27", "path_complex_48x27"):

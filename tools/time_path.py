@@ -1,0 +1,50 @@
+#!/usr/bin/env python
+"""Device-time the path kernel alone (CUDA events) for schedule / scene / spp variants.  Development aid."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import ray_tracer_v1_b200 as rtb
+from ray_tracer_v1_b200 import _native as nat, scenes
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scene", default="complex")
+    ap.add_argument("--spp", type=int, default=16)
+    ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--w", type=int, default=1920)
+    ap.add_argument("--h", type=int, default=1080)
+    args = ap.parse_args()
+    spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
+    fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H = args.w, args.h
+    accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    ref = None
+    for schedule in (0, 1):
+        p = sc.path_params(spec.camera, W, H, args.spp, spec.max_bounces, spec.mirror_threshold, seed=1, schedule=schedule)
+        sc.render_path(p, accum, nat.F32, stats=stats)
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(args.reps):
+            stats.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); sc.render_path(p, accum, nat.F32, stats=stats); b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        st = stats.cpu().numpy()
+        img = accum.cpu().numpy()
+        same = None if ref is None else bool(np.array_equal(ref, img))
+        ref = img if ref is None else ref
+        print(f"{args.scene} {W}x{H} spp {args.spp} schedule {schedule}: {best:.3f} ms  {st[4] / best / 1e6:.2f} Gqueries/s "
+              f"rays/sample {st[0] / (W * H * args.spp):.3f}  same_image={same}", flush=True)
+
+
+if __name__ == "__main__":
+    main()
