@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <new>
 #include <string>
 #include <vector>
@@ -60,7 +61,7 @@ struct rt_env {
 
 template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
-    size_t b = v * (3 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
+    size_t b = v * ((size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
     return (b + 255) & ~size_t(255);
 }
@@ -71,7 +72,9 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
     host.assign(bytes, 0);
     v4 *p = reinterpret_cast<v4 *>(host.data());
     const int n = s->n, nG = s->nG, nP = s->nP, nL = s->nL;
-    v4 *sph = p; p += n;
+    const int n_pad = (n + 7) & ~7;          // brute_select reads whole groups of 8: pad with never-hit spheres
+    v4 *sph = p; p += n_pad;
+    for (int i = n; i < n_pad; ++i) { sph[i].x = sph[i].y = sph[i].z = (T)0; sph[i].w = std::numeric_limits<T>::quiet_NaN(); }
     v4 *mat = p; p += n;
     v4 *col = p; p += n;
     v4 *g_vec = p; p += nG;
@@ -124,7 +127,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     const int n = s->n, nG = s->nG, nP = s->nP, nL = s->nL;
     v.n = n; v.nG = nG; v.nP = nP; v.nL = nL;
     v4 *p = reinterpret_cast<v4 *>(b.blob);
-    v.sph = p; p += n;
+    v.sph = p; p += (n + 7) & ~7;
     v.mat = p; p += n;
     v.col = p; p += n;
     v.g_vec = p; p += nG;

@@ -163,6 +163,7 @@ template <typename T> struct SceneDev {
 template <typename T> struct SphereView {
     using v4 = typename M<T>::v4;
     int n;
+    int n_padded;            // sph[] readable up to here: n rounded up to 8 with NaN-radius spheres (never hit)
     const v4 *sph, *mat, *col;
     const int *ids;
 };

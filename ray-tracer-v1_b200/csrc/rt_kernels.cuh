@@ -30,7 +30,7 @@ template <typename T> __host__ __device__ inline size_t align32(size_t x) { retu
 template <typename T> __host__ __device__ inline size_t scene_smem_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
     size_t b = 0;
-    b += 3 * (size_t)n * v;                 // sph, mat, col
+    b += ((size_t)((n + 7) & ~7) + 2 * (size_t)n) * v;      // sph (padded to 8), mat, col
     b += 2 * (size_t)nG * v + 2 * (size_t)nP * v + 2 * (size_t)nL * v;
     b = align32<T>(b);
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
@@ -44,12 +44,13 @@ template <typename T> RT_DEV void coop_copy(T *dst, const T *src, int count) {
 template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &sc, unsigned char *smem, Staged<T> &S) {
     using v4 = typename M<T>::v4;
     S.g.sv.n = sc.n;
+    S.g.sv.n_padded = (sc.n + 7) & ~7;      // both the staged copy and the HBM blob are padded
     S.g.bvh = sc.bvh;
     S.la.nG = sc.nG; S.la.nP = sc.nP; S.lb.nL = sc.nL;
     S.la.bg[0] = sc.bg[0]; S.la.bg[1] = sc.bg[1]; S.la.bg[2] = sc.bg[2];
     if constexpr (kShared) {
         v4 *p = reinterpret_cast<v4 *>(smem);
-        v4 *sph = p; p += sc.n;
+        v4 *sph = p; p += (sc.n + 7) & ~7;
         v4 *mat = p; p += sc.n;
         v4 *col = p; p += sc.n;
         v4 *g_vec = p; p += sc.nG;
@@ -65,7 +66,7 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
         int *p_id = q; q += sc.nP;
         int *p_func = q; q += sc.nP;
         int *l_index = q; q += sc.nL;
-        coop_copy(sph, sc.sph, sc.n); coop_copy(mat, sc.mat, sc.n); coop_copy(col, sc.col, sc.n);
+        coop_copy(sph, sc.sph, (sc.n + 7) & ~7); coop_copy(mat, sc.mat, sc.n); coop_copy(col, sc.col, sc.n);
         coop_copy(ids, sc.ids, sc.n);
         coop_copy(g_vec, sc.g_vec, sc.nG); coop_copy(g_col, sc.g_col, sc.nG); coop_copy(g_func, sc.g_func, sc.nG);
         coop_copy(p_pos, sc.p_pos, sc.nP); coop_copy(p_col, sc.p_col, sc.nP);

@@ -75,42 +75,25 @@ template <typename T, bool kAbs> RT_DEV void consider(const Geo<T> &g, int i, V3
     if (key < best || (key == best && i < bi)) { best = key; bt = t; bi = i; }
 }
 
-// FP32 brute force, four spheres per trip: 13 FP32 ops per sphere (L, tca, f = L - tca D, |f|^2, r^2 - |f|^2), the
-// eight sign bits of (tca, disc) folded with LOP3 so the common "all four miss" case costs one branch.
+// FP32 brute force over a sphere array padded to a multiple of 8 (padding spheres have a NaN radius), branch-free:
+// warps are incoherent after the first bounce, so a "does any lane hit" branch is almost always taken and only adds
+// reconvergence overhead.  Per sphere: 11 FP32 ops for (tca, disc), one LOP3 that copies tca's sign into disc so that
+// a single MUFU.SQRT turns every non-candidate (tca < 0 or disc < 0, ray.py:80-90) into NaN, one FADD, one compare
+// (NaN compares false) and two predicated moves.  Selection uses the short L.L - tca^2 form; the winner's distance is
+// then recomputed once with the cancellation-free form (sphere_test) by the caller.
 template <bool kAbs>
-RT_DEV void brute4(const float4 *sph, int n, V3<float> O, V3<float> D, float &best, float &bt, int &bi) {
-    int i = 0;
-#pragma unroll 2
-    for (; i + 4 <= n; i += 4) {
-        float tca[4], disc[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float4 s = sph[i + k];
-            const V3<float> L = mk<float>(s.x - O.x, s.y - O.y, s.z - O.z);
-            tca[k] = dot(L, D);
-            const V3<float> f = L - D * tca[k];
-            disc[k] = fmaf(s.w, s.w, -dot(f, f));
-        }
-        // sign bit clear in BOTH tca and disc <=> candidate; any candidate <=> AND over k of (tca|disc) has it clear
-        const int any = (__float_as_int(tca[0]) | __float_as_int(disc[0])) & (__float_as_int(tca[1]) | __float_as_int(disc[1])) &
-                        (__float_as_int(tca[2]) | __float_as_int(disc[2])) & (__float_as_int(tca[3]) | __float_as_int(disc[3]));
-        if (any >= 0) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (tca[k] >= 0.f && disc[k] >= 0.f) {
-                    const float t = tca[k] - M<float>::sqrt(disc[k]);
-                    const float key = kAbs ? fabsf(t) : t;
-                    if (key < best) { best = key; bt = t; bi = i + k; }
-                }
-            }
-        }
-    }
-    for (; i < n; ++i) {
-        float t;
-        if (sphere_test<float>(O, D, sph[i], 0, t)) {
-            const float key = kAbs ? fabsf(t) : t;
-            if (key < best) { best = key; bt = t; bi = i; }
-        }
+RT_DEV void brute_select(const float4 *sph, int n_padded, V3<float> O, V3<float> D, float &best, int &bi) {
+#pragma unroll 8
+    for (int i = 0; i < n_padded; ++i) {
+        const float4 s = sph[i];
+        const float lx = s.x - O.x, ly = s.y - O.y, lz = s.z - O.z;
+        const float tca = fmaf(lz, D.z, fmaf(ly, D.y, lx * D.x));
+        const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+        const float disc = fmaf(tca, tca, fmaf(s.w, s.w, -ll));
+        const float dm = __int_as_float(__float_as_int(disc) | (__float_as_int(tca) & (int)0x80000000));
+        const float t = tca - M<float>::sqrt(dm);
+        const float key = kAbs ? fabsf(t) : t;
+        if (key < best) { best = key; bi = i; }
     }
 }
 
@@ -123,8 +106,19 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
     if (brute) {
         const int n = g.sv.n;
         if (suppress == RT_NO_ID_DEV) {
-            if constexpr (!M<T>::exact) brute4<kAbs>(g.sv.sph, n, O, D, best, bt, bi);
-            else {
+            if constexpr (!M<T>::exact) {
+                brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
+                if (bi >= 0) {
+                    // winner's distance, cancellation-free; a silhouette-grazing winner the robust form rejects keeps
+                    // the selection's own distance
+                    if (!sphere_test<T>(O, D, g.sv.sph[bi], 0, bt)) {
+                        const typename M<T>::v4 w = g.sv.sph[bi];
+                        const V3<T> L = centre_of<T>(w) - O;
+                        const T tca = dot(L, D);
+                        bt = tca - M<T>::sqrt(fmaxf(fmaf(tca, tca, fmaf(w.w, w.w, -dot(L, L))), 0.f));
+                    }
+                }
+            } else {
 #pragma unroll 2
                 for (int i = 0; i < n; ++i) {
                     T t;

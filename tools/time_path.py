@@ -19,10 +19,13 @@ def main():
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--w", type=int, default=1920)
     ap.add_argument("--h", type=int, default=1080)
+    ap.add_argument("--lbvh", action="store_true")
     args = ap.parse_args()
     spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
     fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
     sc = nat.DeviceScene(fs)
+    if args.lbvh:
+        sc.build_lbvh(50.0)
     W, H = args.w, args.h
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stats = torch.zeros(8, dtype=torch.int64, device="cuda")
@@ -43,7 +46,7 @@ def main():
         same = None if ref is None else bool(np.array_equal(ref, img))
         ref = img if ref is None else ref
         print(f"{args.scene} {W}x{H} spp {args.spp} schedule {schedule}: {best:.3f} ms  {st[4] / best / 1e6:.2f} Gqueries/s "
-              f"rays/sample {st[0] / (W * H * args.spp):.3f}  same_image={same}", flush=True)
+              f"rays/sample {st[0] / (W * H * args.spp):.3f}  tests/query {st[5] / st[4]:.1f} boxes/query {st[6] / st[4]:.1f} same_image={same}", flush=True)
 
 
 if __name__ == "__main__":
