@@ -26,6 +26,8 @@ if ROOT not in sys.path:
 import numpy as np  # noqa: E402
 
 W, H, SPP, DEPTH, THRESHOLD, FOV = 1920, 1080, 64, 5, 0.9, 60.0
+NCU_DRAM_BYTES_PER_LAUNCH = 52736 + 1675776    # profiles/ncu_path_kernel_r1c.txt (one ncu --set full capture)
+CPU_W, CPU_H, CPU_SPP = 960, 540, 16          # bounded CPU sample: 1/16 of the frame's pixel-samples
 METRIC, UNIT = "Mrays/s (complex scene, 1920x1080, 64 spp)", "Mrays/s"
 WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer), tile-sharded"
 
@@ -108,12 +110,13 @@ def host_threads():
 
 
 def cpu_baseline(fs, spec):
-    """Bounded sample of the SAME workload (same scene, depth, camera; 480x270, 8 spp ~ 6 M rays ~ 10 s of CPU work)."""
+    """Bounded sample of the SAME workload (same scene, depth, camera): 960x540 x 16 spp = 1/16 of the frame's
+    pixel-samples, ~40 M queries, ~30 core-seconds of CPU work."""
     threads = host_threads()
     cpu_port_run(fs, spec, 96, 54, 2, 1, threads)        # warm the library / thread pool
-    q, r, dt = cpu_port_run(fs, spec, 480, 270, 8, 0, threads)
+    q, r, dt = cpu_port_run(fs, spec, CPU_W, CPU_H, CPU_SPP, 0, threads)
     return {"value": q / dt / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"480x270 x 8 spp of the same scene/depth/camera ({q} queries, {r} reference-counted rays, {dt:.2f} s); "
+            "sample": f"{CPU_W}x{CPU_H} x {CPU_SPP} spp of the same scene/depth/camera ({q} queries, {r} reference-counted rays, {dt:.2f} s); "
                       "oracle/rt_oracle.c (C, FP64, OpenMP) -- the reference itself is single-threaded Python "
                       "(3.3-7.4 krays/s published, BASELINE.md)",
             "rays_ref_compatible_per_s": r / dt / 1e6}
@@ -121,13 +124,13 @@ def cpu_baseline(fs, spec):
 
 def run_reference_arm(args):
     """--impl reference: the CPU port of the reference's path on all host threads, same metric/config; each step a
-    bounded sample (480x270 x 8 spp) of the workload."""
+    bounded sample (960x540 x 16 spp, 1/16 of the frame) of the workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     spec, fs = complex_scene()
     threads = host_threads()
-    sw, sh, sspp = 480, 270, 8
+    sw, sh, sspp = CPU_W, CPU_H, CPU_SPP
     for i in range(args.warmup):
         cpu_port_run(fs, spec, 96, 54, 2, 100 + i, threads)
     q_tot = r_tot = 0
@@ -286,12 +289,15 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(r.h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": 1e3 * float(te[0]) / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32", "kernel": "path_kernel<float,true>", "achieved": achieved, "peak": fp32_peak,
+            "roofline": {"bound": "fp32", "kernel": "path_kernel<float, 0, true, false> (brute force, integer fold, lock-step)", "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "rt_measure_fp32_peak (FFMA issue-rate micro-benchmark, measured in this run; "
                                         "MEASURED_PEAKS.json has no FP32 figure)",
                          "flop_per_query": fpq, "queries_per_launch": q_rank0 / args.steps,
-                         "kernel_ms": kernel_ms / args.steps, "traffic": None,
+                         "kernel_ms": kernel_ms / args.steps,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ncu_path_kernel_r1c.txt:
+                         # the 33 MB framebuffer write mostly stays in the 126 MB L2 past the end of the kernel
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "hbm_algorithmic_bytes_per_launch": W * H * 16 // world},
             "clocks": clocks,
         }

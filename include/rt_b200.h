@@ -109,10 +109,16 @@ int rt_sphere_discriminant(int device, int precision, int m, const double *rays_
 /* m rays through nearestSphereIntersect (+ terminalRGB when rgb_dev != NULL).
  * suppress_dev [m] Sphere.id to suppress or RT_NO_ID (NULL = none); bounces0_dev [m] initial `bounces` (NULL = 0);
  * through0_dev [m] initial through_count (NULL = 0).
- * term_dev [m,10] = hit, scene index, bounces, through_count, point(3), normal(3); rgb_dev [m,3] (miss -> miss[3]). */
+ * term_dev [m,11] = hit, scene index, bounces, through_count, point(3), normal(3), distance (Intersection.distance of
+ * the terminal hit, signed); rgb_dev [m,3] (miss -> miss[3]). */
 int rt_trace_rays(rt_scene *scene, int precision, int m, const double *rays_dev, const int32_t *suppress_dev,
                   const int32_t *bounces0_dev, const int32_t *through0_dev, int max_bounces, int shadow_max_bounces,
                   const double miss[3], double *term_dev, double *rgb_dev, void *stream);
+
+/* Intersection.terminalRGB (ray.py:37-65) at m given hits.  hits_dev [m,7] = scene index, point(3), normal(3) (double);
+ * rgb_dev [m,3] = background + illuminate(...).  shadow_max_bounces = terminalRGB's max_bounces argument. */
+int rt_terminal_rgb(rt_scene *scene, int precision, int m, const double *hits_dev, int shadow_max_bounces,
+                    double *rgb_dev, void *stream);
 
 /* ---- Algorithm A frame: deterministic Whitted-style trace + terminalRGB (drivers: RL/output5.py:416-533
  *      render_true_original, :1420-1525 render_custom_scene('traditional'), notebooks' cell-0 loops) ---------- */

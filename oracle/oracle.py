@@ -64,6 +64,7 @@ def lib():
         _lib.orc_rng_pair.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, c_dp]
         _lib.orc_philox.argtypes = [C.POINTER(C.c_uint32)] * 3
         _lib.orc_trace_rays.argtypes = [C.POINTER(_Scene), C.c_int, c_dp, c_ip, c_ip, C.c_int, C.c_int, c_dp, c_dp, c_dp]
+        _lib.orc_shade_hits.argtypes = [C.POINTER(_Scene), C.c_int, c_dp, C.c_int, c_dp]
         _lib.orc_render_whitted.argtypes = [C.POINTER(_Scene), c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int, C.c_int,
                                             C.c_int, C.c_int, C.c_int, c_dp, C.c_uint64, C.c_int, c_dp, c_ip, c_u64p,
                                             C.c_int]
@@ -158,11 +159,11 @@ def trace_rays(fs, rays, suppress=None, bounces0=None, max_bounces=1, shadow_max
     """Batch of ``Ray.nearestSphereIntersect`` (+ ``terminalRGB``).
 
     rays [m,6] (origin, raw direction).  Returns (term [m,10], rgb [m,3] or None);
-    term = hit, scene index, bounces, through_count, point(3), normal(3)."""
+    term = hit, scene index, bounces, through_count, point(3), normal(3), distance."""
     sc = _scene(fs)
     rays = _d(rays).reshape(-1, 6)
     m = rays.shape[0]
-    term = np.zeros((m, 10))
+    term = np.zeros((m, 11))
     rgb = np.zeros((m, 3)) if shade else None
     sup = None if suppress is None else np.ascontiguousarray(suppress, np.int32)
     b0 = None if bounces0 is None else np.ascontiguousarray(bounces0, np.int32)
@@ -170,6 +171,15 @@ def trace_rays(fs, rays, suppress=None, bounces0=None, max_bounces=1, shadow_max
                          None if b0 is None else _p(b0, c_ip), int(max_bounces), int(shadow_max_bounces),
                          _p(_d(miss), c_dp), _p(term, c_dp), None if rgb is None else _p(rgb, c_dp))
     return term, rgb
+
+
+def shade_hits(fs, hits, shadow_max_bounces=0):
+    """``Intersection.terminalRGB`` at given hits [m,7] = scene index, point(3), normal(3) -> rgb [m,3]."""
+    sc = _scene(fs)
+    hits = _d(hits).reshape(-1, 7)
+    rgb = np.zeros((hits.shape[0], 3))
+    lib().orc_shade_hits(sc.ref, hits.shape[0], _p(hits, c_dp), int(shadow_max_bounces), _p(rgb, c_dp))
+    return rgb
 
 
 # ------------------------------------------------------------------ frames

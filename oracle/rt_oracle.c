@@ -291,7 +291,7 @@ ORC_API int orc_refract(const double *v, const double *n, double ra, double rb, 
     out[0] = r.x; out[1] = r.y; out[2] = r.z; return 1;
 }
 /* batch of rays through nearestSphereIntersect (+ optional terminalRGB).
-   rays [m,6] = origin, raw direction.  term [m,10] = hit, idx, bounces, through, p(3), n(3).
+   rays [m,6] = origin, raw direction.  term [m,11] = hit, idx, bounces, through, p(3), n(3), distance.
    rgb [m,3] (NULL to skip); misses get miss[3].                              */
 ORC_API void orc_trace_rays(const orc_scene *s, int m, const double *rays, const int32_t *suppress, const int32_t *bounces0,
                             int max_bounces, int shadow_max_bounces, const double *miss, double *term, double *rgb) {
@@ -299,13 +299,23 @@ ORC_API void orc_trace_rays(const orc_scene *s, int m, const double *rays, const
         const double *r = rays + 6 * i;
         isect h = trace_terminal(s, V(r[0], r[1], r[2]), vnorm(V(r[3], r[4], r[5])), suppress ? suppress[i] : ORC_NO_ID,
                                  bounces0 ? bounces0[i] : 0, max_bounces, 0);
-        double *t = term + 10 * i;
+        double *t = term + 11 * i;
         t[0] = h.hit; t[1] = h.idx; t[2] = h.bounces; t[3] = h.through;
-        t[4] = h.p.x; t[5] = h.p.y; t[6] = h.p.z; t[7] = h.n.x; t[8] = h.n.y; t[9] = h.n.z;
+        t[4] = h.p.x; t[5] = h.p.y; t[6] = h.p.z; t[7] = h.n.x; t[8] = h.n.y; t[9] = h.n.z; t[10] = h.t;
         if (rgb) {
             if (h.hit) terminal_rgb(s, &h, shadow_max_bounces, rgb + 3 * i);
             else for (int c = 0; c < 3; ++c) rgb[3 * i + c] = miss[c];
         }
+    }
+}
+
+/* Intersection.terminalRGB at given hits: hits [m,7] = scene index, point(3), normal(3) -> rgb [m,3] */
+ORC_API void orc_shade_hits(const orc_scene *s, int m, const double *hits, int shadow_max_bounces, double *rgb) {
+    for (int i = 0; i < m; ++i) {
+        const double *q = hits + 7 * i;
+        isect h; memset(&h, 0, sizeof h);
+        h.hit = 1; h.idx = (int)q[0]; h.p = V(q[1], q[2], q[3]); h.n = V(q[4], q[5], q[6]);
+        terminal_rgb(s, &h, shadow_max_bounces, rgb + 3 * i);
     }
 }
 

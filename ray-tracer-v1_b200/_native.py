@@ -91,6 +91,7 @@ SIGNATURES = {
     "rt_lbvh_drop": (C.c_int, [vp]),
     "rt_sphere_discriminant": (C.c_int, [C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp]),
     "rt_trace_rays": (C.c_int, [vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, c_dp, vp, vp, vp]),
+    "rt_terminal_rgb": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
     "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
     "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
@@ -400,7 +401,8 @@ class DeviceScene:
     # ---- batched primitives ----------------------------------------------------------------------
     def trace_rays(self, rays, suppress=None, bounces0=None, through0=None, max_bounces=1, shadow_max_bounces=0,
                    miss=(0, 0, 0), shade=True, precision=F64):
-        """Batch of ``Ray.nearestSphereIntersect`` (+ ``terminalRGB``): rays [m,6] -> (term [m,10], rgb [m,3] | None)."""
+        """Batch of ``Ray.nearestSphereIntersect`` (+ ``terminalRGB``): rays [m,6] -> (term [m,11], rgb [m,3] | None);
+        term = hit, scene index, bounces, through_count, point(3), normal(3), distance."""
         rays = _d(rays).reshape(-1, 6)
         m = rays.shape[0]
         dev = self.device
@@ -408,12 +410,21 @@ class DeviceScene:
         sup = None if suppress is None else DeviceBuffer.from_host(np.asarray(suppress).reshape(m), np.int32, dev)
         b0 = None if bounces0 is None else DeviceBuffer.from_host(np.asarray(bounces0).reshape(m), np.int32, dev)
         t0 = None if through0 is None else DeviceBuffer.from_host(np.asarray(through0).reshape(m), np.int32, dev)
-        term = DeviceBuffer((m, 10), np.float64, dev)
+        term = DeviceBuffer((m, 11), np.float64, dev)
         rgb = DeviceBuffer((m, 3), np.float64, dev) if shade else None
         missv = (C.c_double * 3)(*[float(c) for c in miss])
         check(lib().rt_trace_rays(self.handle, precision, m, r.ptr, _ptr(sup), _ptr(b0), _ptr(t0), int(max_bounces),
                                   int(shadow_max_bounces), missv, term.ptr, _ptr(rgb), None))
         return term.download(), (rgb.download() if shade else None)
+
+    def shade_hits(self, hits, shadow_max_bounces=0, precision=F64):
+        """Batch of ``Intersection.terminalRGB``: hits [m,7] = scene index, point(3), normal(3) -> rgb [m,3]."""
+        hits = _d(hits).reshape(-1, 7)
+        m = hits.shape[0]
+        h = DeviceBuffer.from_host(hits, np.float64, self.device)
+        rgb = DeviceBuffer((m, 3), np.float64, self.device)
+        check(lib().rt_terminal_rgb(self.handle, precision, m, h.ptr, int(shadow_max_bounces), rgb.ptr, None))
+        return rgb.download()
 
     def close(self):
         if getattr(self, "handle", None):

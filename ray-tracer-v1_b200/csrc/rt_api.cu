@@ -400,6 +400,17 @@ RT_EXPORT int rt_trace_rays(rt_scene *scene, int precision, int m, const double 
     return RT_OK;
 }
 
+RT_EXPORT int rt_terminal_rgb(rt_scene *scene, int precision, int m, const double *hits_dev, int shadow_max_bounces,
+                              double *rgb_dev, void *stream) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (m < 0 || (m > 0 && (!hits_dev || !rgb_dev))) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(scene->device));
+    if (precision == RT_F64) CU(launch_shade_hits<double>(scene->d.view, m, hits_dev, shadow_max_bounces, rgb_dev, S(stream)));
+    else if (precision == RT_F32) CU(launch_shade_hits<float>(scene->f.view, m, hits_dev, shadow_max_bounces, rgb_dev, S(stream)));
+    else return fail(RT_ERR_INVALID, "unknown precision");
+    return RT_OK;
+}
+
 // ------------------------------------------------------------------ Algorithm A frame
 template <typename T>
 static int render_whitted_t(rt_scene *sc, const SceneDev<T> &view, const rt_whitted_params *p, void *accum, int32_t *hit,

@@ -348,10 +348,10 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, 
     Counters ct = {0u, 0u, 0u};
     Hit<T> h = trace_terminal<T, kBvh>(S.g, O, D, suppress ? suppress[i] : RT_NO_ID_DEV, bounces0 ? bounces0[i] : 0,
                                  max_bounces, through0 ? through0[i] : 0, ct);
-    double *t = term + 10 * (size_t)i;
+    double *t = term + 11 * (size_t)i;
     t[0] = h.idx >= 0 ? 1.0 : 0.0; t[1] = (double)h.idx; t[2] = (double)h.bounces; t[3] = (double)h.through;
     t[4] = (double)h.p.x; t[5] = (double)h.p.y; t[6] = (double)h.p.z;
-    t[7] = (double)h.n.x; t[8] = (double)h.n.y; t[9] = (double)h.n.z;
+    t[7] = (double)h.n.x; t[8] = (double)h.n.y; t[9] = (double)h.n.z; t[10] = (double)h.t;
     if (rgb) {
         double *c = rgb + 3 * (size_t)i;
         if (h.idx >= 0) {
@@ -360,6 +360,28 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, 
             c[0] = (double)o[0]; c[1] = (double)o[1]; c[2] = (double)o[2];
         } else { c[0] = miss0; c[1] = miss1; c[2] = miss2; }
     }
+}
+
+template <typename T, int kMode>
+__global__ void __launch_bounds__(256) shade_hits_kernel(SceneDev<T> sc, int m, const double *hits, int shadow_max_bounces,
+                                                         double *rgb) {
+    RT_MODE_DECL;
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double *q = hits + 7 * (size_t)i;
+    Hit<T> h;
+    h.idx = (int)q[0]; h.t = T(0); h.bounces = 0; h.through = 0;
+    h.p = mk<T>(T(q[1]), T(q[2]), T(q[3]));
+    h.n = mk<T>(T(q[4]), T(q[5]), T(q[6]));
+    double *c = rgb + 3 * (size_t)i;
+    if (h.idx < 0 || h.idx >= sc.n) { c[0] = c[1] = c[2] = 0.0; return; }
+    Counters ct = {0u, 0u, 0u};
+    T o[3];
+    terminal_rgb<T, kBvh>(S.g, S.la, h, shadow_max_bounces, o, ct);
+    c[0] = (double)o[0]; c[1] = (double)o[1]; c[2] = (double)o[2];
 }
 
 // ------------------------------------------------------------------ batched RayTracerEnv
@@ -456,7 +478,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         int px, py;
         if (pixels) { px = pixels[2 * b]; py = pixels[2 * b + 1]; }
         else {
-            Philox4 o = philox4x32_10((uint32_t)b, e.episode ? (uint32_t)e.episode[b] : 0u, 0u, 0x52544556u /* "RTEV" */, k0, k1);
+            Philox4 o = philox4x32_10((uint32_t)b, 0u, 0u, 0x52544556u /* "RTEV" */, k0, k1);   // key = per-reset seed
             px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
             py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
         }
@@ -652,6 +674,16 @@ cudaError_t launch_trace_rays(const SceneDev<T> &sc, int m, const double *rays, 
 }
 
 template <typename T>
+cudaError_t launch_shade_hits(const SceneDev<T> &sc, int m, const double *hits, int shadow_max_bounces, double *rgb,
+                              cudaStream_t st) {
+    if (m <= 0) return cudaSuccess;
+    const int block = 256, grid = (m + block - 1) / block;
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, shade_hits_kernel, grid, block, smem_for(sc), st, sc, m, hits, shadow_max_bounces, rgb);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
                              uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st) {
     if (e.B <= 0) return cudaSuccess;
@@ -685,6 +717,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_trace_rays<T>(const SceneDev<T> &, int, const double *, const int *, const int *,       \
                                               const int *, int, int, const double[3], double *, double *,              \
                                               cudaStream_t);                                                            \
+    template cudaError_t launch_shade_hits<T>(const SceneDev<T> &, int, const double *, int, double *, cudaStream_t);    \
     template cudaError_t launch_env_reset<T>(const SceneDev<T> &, const EnvDev<T> &, const int *, const uint8_t *,      \
                                              uint64_t, float *, int *, unsigned long long *, cudaStream_t);             \
     template cudaError_t launch_env_step<T>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, double *,   \

@@ -52,6 +52,9 @@ cudaError_t launch_trace_rays(const SceneDev<T> &sc, int m, const double *rays, 
                               const int *through0, int max_bounces, int shadow_max_bounces, const double miss[3],
                               double *term, double *rgb, cudaStream_t st);
 template <typename T>
+cudaError_t launch_shade_hits(const SceneDev<T> &sc, int m, const double *hits, int shadow_max_bounces, double *rgb,
+                              cudaStream_t st);
+template <typename T>
 cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
                              uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st);
 template <typename T>

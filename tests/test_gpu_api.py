@@ -1,0 +1,198 @@
+"""GPU tests of the reference-facing Python API (the drop-in boundary): Ray / Intersection, the render entry points,
+and RayTracerEnv (scalar and batched), all through the C ABI, against golden vectors recorded from the unmodified
+reference and against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+
+ENVS = ["env_rl_optimized", "env_rl_demo", "env_fb_demo", "env_fb_balls", "env_rl_balls_rotated"]
+
+
+def make_env(rt, z, fs, B, precision):
+    from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
+    return BatchedRayTracerEnv(fs, B, int(z["width"]), int(z["height"]), camera_position=tuple(z["cam"]),
+                               camera_angle=tuple(z["cam_angle"]), fov=float(z["fov"]), max_bounces=int(z["max_bounces"]),
+                               flavour=str(z["flavour"]), precision=precision)
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_batched_env_matches_reference_rollouts(rt, name):
+    """Rollouts recorded from the UNMODIFIED reference env (96 episodes x T steps, stepping on past termination)."""
+    z, fs = load_golden(name)
+    B = z["pixels"].shape[0]
+    env = make_env(rt, z, fs, B, "f64")
+    obs0, _ = env.reset(options={"pixels": z["pixels"]})
+    np.testing.assert_allclose(obs0.cpu().numpy(), z["obs0"], rtol=1e-6, atol=1e-7)
+    # the reference feeds float32 actions into numpy trig, so part of ITS arithmetic is float32 (see test_oracle_golden)
+    for t in range(z["actions"].shape[0]):
+        obs, rew, term, trunc, info = env.step(z["actions"][t])
+        np.testing.assert_allclose(obs.cpu().numpy(), z["obs"][t], rtol=5e-5, atol=5e-6, err_msg=f"obs step {t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), z["reward"][t], rtol=1e-5, atol=1e-6, err_msg=f"reward step {t}")
+        assert np.array_equal(term.cpu().numpy(), z["terminated"][t].astype(bool))
+        assert np.array_equal(trunc.cpu().numpy(), z["truncated"][t].astype(bool))
+        assert np.array_equal(info["reason"].cpu().numpy(), z["reason"][t])
+        np.testing.assert_allclose(info["total_reward"].cpu().numpy(), z["total_reward"][t], rtol=1e-5, atol=1e-5)
+    env.close()
+
+
+@pytest.mark.parametrize("name", ENVS)
+def test_batched_env_fp64_equals_oracle_and_fp32_is_close(rt, orc, name):
+    z, fs = load_golden(name)
+    B = z["pixels"].shape[0]
+    ref = orc.OracleEnv(fs, B, int(z["width"]), int(z["height"]), camera=z["cam"], camera_angle=z["cam_angle"],
+                        fov=float(z["fov"]), max_bounces=int(z["max_bounces"]), flavour=str(z["flavour"]))
+    e64, e32 = make_env(rt, z, fs, B, "f64"), make_env(rt, z, fs, B, "f32")
+    o_ref = ref.reset(z["pixels"])
+    o64, _ = e64.reset(options={"pixels": z["pixels"]})
+    o32, _ = e32.reset(options={"pixels": z["pixels"]})
+    np.testing.assert_allclose(o64.cpu().numpy(), o_ref, rtol=1e-6, atol=1e-7)
+    alive32 = np.ones(B, bool)                      # FP32 episodes that still follow the FP64 trajectory
+    for t in range(z["actions"].shape[0]):
+        a = z["actions"][t]
+        obs_r, rew_r, term_r, trunc_r, reason_r = ref.step(a)
+        obs, rew, term, trunc, info = e64.step(a)
+        np.testing.assert_allclose(obs.cpu().numpy(), obs_r, rtol=1e-6, atol=1e-7)
+        np.testing.assert_allclose(rew.cpu().numpy(), rew_r, rtol=1e-9, atol=1e-12)
+        assert np.array_equal(term.cpu().numpy(), term_r) and np.array_equal(trunc.cpu().numpy(), trunc_r)
+        assert np.array_equal(info["reason"].cpu().numpy(), reason_r)
+        obs3, rew3, term3, trunc3, info3 = e32.step(a)
+        same = info3["reason"].cpu().numpy() == reason_r
+        alive32 &= same                              # a flipped hit/miss sends an episode down another path: drop it
+        ok = alive32
+        np.testing.assert_allclose(obs3.cpu().numpy()[ok], obs_r[ok], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(rew3.cpu().numpy()[ok], rew_r[ok], rtol=2e-3, atol=6e-3)
+    assert alive32.mean() > 0.9
+    e64.close(); e32.close()
+
+
+def test_scalar_env_dropin(rt):
+    """The scalar RayTracerEnv keeps the reference's return types and info keys."""
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.ray_tracer_env import RayTracerEnv, FBRayTracerEnv
+    from ray_tracer_v1_b200 import Vector, Colour
+    z, fs = load_golden("env_rl_optimized")
+    spec = scenes.build_optimized_env_scene()
+    env = RayTracerEnv(spheres=spec.spheres, image_width=320, image_height=240, camera_position=Vector(0, 0, 0), fov=80,
+                       max_bounces=6, background_colour=Colour(0, 0, 0), point_light_sources=spec.point_lights)
+    for b in (0, 3, 17):
+        px = tuple(int(v) for v in z["pixels"][b])
+        obs, info = env.reset(options={"pixel": px})
+        assert obs.shape == (18,) and obs.dtype == np.float32 and info["pixel"] == px and "initial_ray" in info
+        np.testing.assert_allclose(obs, z["obs0"][b], rtol=1e-6, atol=1e-7)
+        for t in range(4):
+            obs, reward, terminated, truncated, info = env.step(z["actions"][t, b])
+            assert isinstance(reward, float) and isinstance(terminated, bool) and isinstance(truncated, bool)
+            np.testing.assert_allclose(obs, z["obs"][t, b], rtol=5e-5, atol=5e-6)
+            np.testing.assert_allclose(reward, z["reward"][t, b], rtol=1e-5, atol=1e-6)
+            assert terminated == bool(z["terminated"][t, b])
+            assert {"bounce_count", "through_count", "total_reward"} <= set(info)
+    env.close()
+    fb = FBRayTracerEnv(spheres=scenes.build_balls_in_space(as_rendered=False).spheres, image_width=160, image_height=120,
+                        camera_position=Vector(0, 0, 1), fov=60, max_bounces=5)
+    obs, _ = fb.reset(options={"pixel": (80, 60)})
+    obs, reward, terminated, truncated, info = fb.step(fb.action_space.sample())
+    assert obs.shape == (18,)
+    fb.close()
+
+
+def test_batched_env_c5_size_and_sharding(rt):
+    """BASELINE config 5: 65,536 parallel envs; env shards are independent, so a shard equals the same rows of the whole."""
+    import torch
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
+    from ray_tracer_v1_b200.distributed import env_slices
+    spec = scenes.build_balls_in_space(as_rendered=False)
+    fs = flatten_scene(spec.spheres, spec.global_lights, [], spec.background)
+    B = 65536
+    kw = dict(image_width=320, image_height=240, camera_position=(0, 0, 1), fov=60, max_bounces=5, flavour="fb")
+    rs = np.random.RandomState(0)
+    pixels = np.stack([rs.randint(0, 320, B), rs.randint(0, 240, B)], 1).astype(np.int32)
+    actions = rs.uniform(-1, 1, (6, B, 2)).astype(np.float32)
+    whole = BatchedRayTracerEnv(fs, B, **kw)
+    o, _ = whole.reset(options={"pixels": pixels})
+    b0, b1 = env_slices(B, 8)[3]
+    part = BatchedRayTracerEnv(fs, b1 - b0, **kw)
+    op, _ = part.reset(options={"pixels": pixels[b0:b1]})
+    assert torch.equal(o[b0:b1], op)
+    done = torch.zeros(B, dtype=torch.bool, device="cuda")
+    for t in range(6):
+        o, r, te, tr, info = whole.step(torch.as_tensor(actions[t], device="cuda"))
+        op, rp, tep, trp, _ = part.step(actions[t, b0:b1])
+        assert torch.equal(o[b0:b1], op) and torch.equal(r[b0:b1], rp) and torch.equal(te[b0:b1], tep)
+        done |= te
+    assert bool(done.all())                       # every episode ends within max_bounces + 1 steps
+    # device-drawn start pixels are reproducible and inside the image
+    whole._resets = 0
+    o1, i1 = whole.reset(seed=11)
+    p1, o1 = i1["pixels"].clone(), o1.clone()
+    whole._resets = 0
+    o2, i2 = whole.reset(seed=11)
+    assert torch.equal(p1, i2["pixels"]) and torch.equal(o1, o2)
+    assert int(p1[:, 0].max()) < 320 and int(p1[:, 1].max()) < 240 and int(p1.min()) >= 0
+    whole.close(); part.close()
+
+
+def test_ray_and_intersection_dropin(rt):
+    """Notebook-style scalar calls: RL/Marbles 1.ipynb cell 7 and a terminalRGB round trip against the frame golden."""
+    from ray_tracer_v1_b200 import Ray, Vector, Sphere, Material, scenes
+    hit = Ray(Vector(0.1, 0, 5), Vector(0, 0, -1)).sphereDiscriminant(Sphere(Vector(0, 0, 0), 1, Material()))
+    assert hit.intersects and hit.point.getXYZ() == (0.1, 0.0, 0.9949874371066194)
+    z, fs = load_golden("whitted_c1_balls_320x240")
+    spec = scenes.build_balls_in_space(as_rendered=True)
+    cam = Vector(*spec.camera)
+    for (yi, xi) in ((120, 160), (60, 100), (200, 250), (10, 10), (150, 40)):
+        d = Vector(float(z["X"][xi]), float(z["Y"][yi]), -1).normalise()
+        t = Ray(cam, d).nearestSphereIntersect(spec.spheres, max_bounces=1)
+        if z["hit"][yi, xi] < 0:
+            assert t is None
+            continue
+        assert t.object is spec.spheres[int(z["hit"][yi, xi])]
+        c = t.terminalRGB(spheres=spec.spheres, background_colour=spec.background, global_light_sources=spec.global_lights,
+                          point_light_sources=spec.point_lights)
+        assert c.getList() == [float(v) for v in z["rgb"][yi, xi]]
+
+
+def test_render_entry_points(rt, orc):
+    from ray_tracer_v1_b200 import scenes, Vector
+    from ray_tracer_v1_b200.renderers import (TraditionalRenderer, ComplexTraditionalRenderer, CustomSceneExperiment)
+    import tempfile
+    # output5: render_custom_scene('traditional') reproduces the reference's own 320x240 image
+    z, _ = load_golden("whitted_c1_balls_320x240")
+    with tempfile.TemporaryDirectory() as tmp:
+        exp = CustomSceneExperiment(output_dir=tmp, precision="f64")
+        exp.config.update(image_width=320, image_height=240, samples_per_pixel=1, max_bounces=1)
+        t, img = exp.render_custom_scene(scenes.build_balls_in_space(as_rendered=False).spheres, "traditional", None)
+        assert np.array_equal(img, z["image"]) and t > 0
+        exp32 = CustomSceneExperiment(output_dir=tmp, precision="f32")
+        exp32.config.update(image_width=320, image_height=240, samples_per_pixel=1, max_bounces=1)
+        _, img32 = exp32.render_custom_scene(scenes.build_balls_in_space(as_rendered=False).spheres, "traditional", None)
+        assert (np.abs(img32 - z["image"]).max(axis=2) > 1.001 / 255).mean() < 2e-3
+        # render_true_original: 601x601 notebook grid; compare its centre crop rows with the 121-grid golden's geometry
+        full = exp.render_true_original(scenes.build_balls_in_space(as_rendered=False).spheres, None)
+        assert full.shape == (601, 601, 3) and full.max() <= 1.0 and full.min() >= 0.0
+    # TraditionalRenderer: attribute injection like the reference's main(), stats keys, image == oracle render
+    spec = scenes.build_chandelier()
+    r = TraditionalRenderer(precision="f64", seed=5)
+    r.scene = spec.spheres
+    r.light_sources = [s for s in spec.spheres if s.material.emitive]
+    r.small_lights = [s for s in r.light_sources if s.radius < 0.5]
+    r.camera_position = Vector(0, 2, 0)
+    img = r.render(64, 36, samples_per_pixel=3, max_bounces=8)
+    sums, st = orc.render_path(r.flat_scene(), (0, 2, 0), 64, 36, 3, 8, 0.0, seed=5)
+    assert np.array_equal(img, orc.resolve(sums, 3))
+    assert r.stats["total_rays"] == st["total_rays"] and r.stats["light_hits"] == st["light_hits"]
+    assert r.stats["rays_per_second"] > 0 and set(r.stats) == {'total_rays', 'total_intersections', 'light_hits',
+                                                              'small_light_hits', 'render_time', 'rays_per_second'}
+    spec.spheres[10].centre = Vector(0.3, 3.0, 7.0)          # scenes are mutable: the next render must see the change
+    img2 = r.render(64, 36, samples_per_pixel=3, max_bounces=8)
+    sums2, _ = orc.render_path(r.flat_scene(), (0, 2, 0), 64, 36, 3, 8, 0.0, seed=5)
+    assert np.array_equal(img2, orc.resolve(sums2, 3)) and not np.array_equal(img, img2)
+    c = ComplexTraditionalRenderer(precision="f32", seed=1)
+    cs = scenes.build_complex()
+    c.scene, c.light_sources = cs.spheres, [s for s in cs.spheres if s.material.emitive]
+    c.small_lights = [s for s in c.light_sources if s.radius < 0.5]
+    im = c.render(96, 54, samples_per_pixel=2, max_bounces=5)
+    assert im.shape == (54, 96, 3) and im.dtype == np.float32 and 5.0 < c.stats["total_rays"] / (96 * 54 * 2) <= 6.0

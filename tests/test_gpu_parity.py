@@ -63,6 +63,10 @@ def test_trace_rays_matches_oracle(nat, orc):
         assert np.array_equal(term[:, :4], term_o[:, :4])
         np.testing.assert_allclose(term[:, 4:], term_o[:, 4:], rtol=1e-9, atol=1e-12)
         assert np.array_equal(rgb, rgb_o)
+        # Intersection.terminalRGB at given hits
+        hit = term_o[:, 0] == 1
+        hits = np.concatenate([term_o[hit, 1:2], term_o[hit, 4:10]], 1)
+        assert np.array_equal(sc.shade_hits(hits, 0, nat.F64), orc.shade_hits(fs, hits, 0))
         term32, rgb32 = sc.trace_rays(rays, suppress=sup, bounces0=b0, max_bounces=depth, miss=z["miss"], precision=nat.F32)
         same = np.all(term32[:, :2] == term_o[:, :2], axis=1)
         assert same.mean() > 0.995
