@@ -80,7 +80,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop_evt.wait(0.05)
+            self._stop_evt.wait(0.01)
 
     def stop(self):
         self._stop_evt.set()
