@@ -61,7 +61,7 @@ struct rt_env {
 
 template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
-    size_t b = v * ((size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
+    size_t b = v * (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
     return (b + 255) & ~size_t(255);
 }
@@ -75,6 +75,7 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
     const int n_pad = (n + 7) & ~7;          // brute_select reads whole groups of 8: pad with never-hit spheres
     v4 *sph = p; p += n_pad;
     for (int i = n; i < n_pad; ++i) { sph[i].x = sph[i].y = sph[i].z = (T)0; sph[i].w = std::numeric_limits<T>::quiet_NaN(); }
+    v4 *pk = p; p += n_pad;                  // sphere pairs for the packed (f32x2) selection loop, rt_trace.cuh
     v4 *mat = p; p += n;
     v4 *col = p; p += n;
     v4 *g_vec = p; p += nG;
@@ -95,8 +96,17 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
         mat[i].x = (T)s->material[4 * i]; mat[i].y = (T)s->material[4 * i + 1]; mat[i].z = (T)s->material[4 * i + 2];
         mat[i].w = (T)s->material[4 * i + 3];
         col[i].x = (T)s->colour[3 * i]; col[i].y = (T)s->colour[3 * i + 1]; col[i].z = (T)s->colour[3 * i + 2];
-        col[i].w = (T)0;
+        col[i].w = (T)(1.0 / s->radius[i]);    // normal = (p - c) * (1/r) in the product path
         ids[i] = s->ids[i];
+    }
+    // pair j = spheres (2j, 2j+1): pk[2j] = (cx0 cx1 cy0 cy1), pk[2j+1] = (cz0 cz1 w0 w1), w = r^2 - |c|^2 evaluated
+    // in double from the T-rounded centre and radius (NaN for padding spheres: never hit)
+    for (int i = 0; i < n_pad; ++i) {
+        const double cx = (double)sph[i].x, cy = (double)sph[i].y, cz = (double)sph[i].z, r = (double)sph[i].w;
+        const T w = (T)(r * r - (cx * cx + cy * cy + cz * cz));
+        v4 &a = pk[i & ~1], &b = pk[(i & ~1) + 1];
+        if (i & 1) { a.y = sph[i].x; a.w = sph[i].y; b.y = sph[i].z; b.w = w; }
+        else { a.x = sph[i].x; a.z = sph[i].y; b.x = sph[i].z; b.z = w; }
     }
     for (int i = 0; i < nG; ++i) {
         g_vec[i].x = (T)s->g_vec[3 * i]; g_vec[i].y = (T)s->g_vec[3 * i + 1]; g_vec[i].z = (T)s->g_vec[3 * i + 2];
@@ -128,6 +138,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     v.n = n; v.nG = nG; v.nP = nP; v.nL = nL;
     v4 *p = reinterpret_cast<v4 *>(b.blob);
     v.sph = p; p += (n + 7) & ~7;
+    v.pk = p; p += (n + 7) & ~7;
     v.mat = p; p += n;
     v.col = p; p += n;
     v.g_vec = p; p += nG;
@@ -143,6 +154,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     v.p_func = q; q += nP;
     v.l_index = q; q += nL;
     v.small = small_dev;
+    v.key_mask = 0x7ffffff8;
     v.bg[0] = (T)s->bg[0]; v.bg[1] = (T)s->bg[1]; v.bg[2] = (T)s->bg[2];
     std::memset(&v.bvh, 0, sizeof v.bvh);
 }

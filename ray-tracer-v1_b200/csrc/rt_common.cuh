@@ -144,17 +144,19 @@ struct PathRng {
 // ------------------------------------------------------------------ scene views
 // Device-resident flattened scene for one precision.  vec4 packing:
 //   sph   cx cy cz r            mat   reflective transparent emitive refractive_index
-//   col   r g b -               g_vec x y z max_angle     g_col r g b strength
+//   pk    sphere pairs (2j, 2j+1): (cx0 cx1 cy0 cy1), (cz0 cz1 w0 w1) with w = r^2 - |c|^2 (packed selection loop)
+//   col   r g b 1/r             g_vec x y z max_angle     g_col r g b strength
 //   p_pos x y z max_angle       p_col r g b strength      l_pos x y z -      l_col r g b -
 template <typename T> struct SceneDev {
     using v4 = typename M<T>::v4;
     int n, nG, nP, nL;
-    const v4 *sph, *mat, *col;
+    const v4 *sph, *pk, *mat, *col;
     const int *ids;
     const v4 *g_vec, *g_col; const int *g_func;
     const v4 *p_pos, *p_col; const int *p_id, *p_func;
     const v4 *l_pos, *l_col; const int *l_index;
     const uint8_t *small;
+    int key_mask;             // 0x7ffffff8, passed as DATA so that the selection loop's (t & mask) | k stays ONE LOP3
     T bg[3];
     BvhView bvh;              // optional LBVH, see rt_lbvh.cuh
 };
@@ -164,7 +166,8 @@ template <typename T> struct SphereView {
     using v4 = typename M<T>::v4;
     int n;
     int n_padded;            // sph[] readable up to here: n rounded up to 8 with NaN-radius spheres (never hit)
-    const v4 *sph, *mat, *col;
+    int key_mask;            // SceneDev::key_mask
+    const v4 *sph, *pk, *mat, *col;
     const int *ids;
 };
 

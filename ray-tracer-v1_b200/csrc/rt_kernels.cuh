@@ -30,7 +30,7 @@ template <typename T> __host__ __device__ inline size_t align32(size_t x) { retu
 template <typename T> __host__ __device__ inline size_t scene_smem_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
     size_t b = 0;
-    b += ((size_t)((n + 7) & ~7) + 2 * (size_t)n) * v;      // sph (padded to 8), mat, col
+    b += (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n) * v;  // sph (padded to 8), pk (sphere pairs), mat, col
     b += 2 * (size_t)nG * v + 2 * (size_t)nP * v + 2 * (size_t)nL * v;
     b = align32<T>(b);
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
@@ -45,12 +45,14 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
     using v4 = typename M<T>::v4;
     S.g.sv.n = sc.n;
     S.g.sv.n_padded = (sc.n + 7) & ~7;      // both the staged copy and the HBM blob are padded
+    S.g.sv.key_mask = sc.key_mask;
     S.g.bvh = sc.bvh;
     S.la.nG = sc.nG; S.la.nP = sc.nP; S.lb.nL = sc.nL;
     S.la.bg[0] = sc.bg[0]; S.la.bg[1] = sc.bg[1]; S.la.bg[2] = sc.bg[2];
     if constexpr (kShared) {
         v4 *p = reinterpret_cast<v4 *>(smem);
         v4 *sph = p; p += (sc.n + 7) & ~7;
+        v4 *pk = p; p += (sc.n + 7) & ~7;
         v4 *mat = p; p += sc.n;
         v4 *col = p; p += sc.n;
         v4 *g_vec = p; p += sc.nG;
@@ -66,19 +68,20 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
         int *p_id = q; q += sc.nP;
         int *p_func = q; q += sc.nP;
         int *l_index = q; q += sc.nL;
-        coop_copy(sph, sc.sph, (sc.n + 7) & ~7); coop_copy(mat, sc.mat, sc.n); coop_copy(col, sc.col, sc.n);
+        coop_copy(sph, sc.sph, 2 * ((sc.n + 7) & ~7));       // sph and pk are adjacent in the blob
+        coop_copy(mat, sc.mat, sc.n); coop_copy(col, sc.col, sc.n);
         coop_copy(ids, sc.ids, sc.n);
         coop_copy(g_vec, sc.g_vec, sc.nG); coop_copy(g_col, sc.g_col, sc.nG); coop_copy(g_func, sc.g_func, sc.nG);
         coop_copy(p_pos, sc.p_pos, sc.nP); coop_copy(p_col, sc.p_col, sc.nP);
         coop_copy(p_id, sc.p_id, sc.nP); coop_copy(p_func, sc.p_func, sc.nP);
         coop_copy(l_pos, sc.l_pos, sc.nL); coop_copy(l_col, sc.l_col, sc.nL); coop_copy(l_index, sc.l_index, sc.nL);
         __syncthreads();
-        S.g.sv.sph = sph; S.g.sv.mat = mat; S.g.sv.col = col; S.g.sv.ids = ids;
+        S.g.sv.sph = sph; S.g.sv.pk = pk; S.g.sv.mat = mat; S.g.sv.col = col; S.g.sv.ids = ids;
         S.la.g_vec = g_vec; S.la.g_col = g_col; S.la.g_func = g_func;
         S.la.p_pos = p_pos; S.la.p_col = p_col; S.la.p_id = p_id; S.la.p_func = p_func;
         S.lb.l_pos = l_pos; S.lb.l_col = l_col; S.lb.l_index = l_index;
     } else {
-        S.g.sv.sph = sc.sph; S.g.sv.mat = sc.mat; S.g.sv.col = sc.col; S.g.sv.ids = sc.ids;
+        S.g.sv.sph = sc.sph; S.g.sv.pk = sc.pk; S.g.sv.mat = sc.mat; S.g.sv.col = sc.col; S.g.sv.ids = sc.ids;
         S.la.g_vec = sc.g_vec; S.la.g_col = sc.g_col; S.la.g_func = sc.g_func;
         S.la.p_pos = sc.p_pos; S.la.p_col = sc.p_col; S.la.p_id = sc.p_id; S.la.p_func = sc.p_func;
         S.lb.l_pos = sc.l_pos; S.lb.l_col = sc.l_col; S.lb.l_index = sc.l_index;

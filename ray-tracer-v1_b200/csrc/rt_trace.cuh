@@ -97,6 +97,59 @@ RT_DEV void brute_select(const float4 *sph, int n_padded, V3<float> O, V3<float>
     }
 }
 
+// ---- packed FP32 (sm_100 f32x2) helpers: one issue slot for two FP32 lanes of work.  A pair lives in a 64-bit register.
+typedef unsigned long long f32x2;
+RT_DEV f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+RT_DEV void unpack2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+RT_DEV f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+RT_DEV f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
+#define RT_KEY_INF 0x7f800000            /* +inf as an int: the empty selection */
+
+// Algorithm B nearest-hit selection over the sphere-pair array (SphereView::pk), branch-free, two spheres per FP32
+// instruction.  With w = r^2 - |c|^2 stored per sphere and, per ray, od = O.D, oo = O.O:
+//     tca  = c.D - od                                 3 FFMA2 per pair
+//     disc = tca^2 + (w - oo + 2 c.O)                 1 FADD2 + 3 FFMA2 + 1 FFMA2 per pair
+// i.e. 4 issue slots per sphere instead of 11 scalar ones.  Then per sphere: LOP3 (tca's sign into disc, so that ONE
+// MUFU.SQRT turns both miss conditions of ray.py:80-90 into NaN), MUFU.SQRT, t = tca - sqrt (FADD2 per pair), and the
+// key = bits(|t|) with the in-group index in the 3 low mantissa bits (LOP3).  Positive floats order like their bit
+// patterns and NaN sorts above +inf, so the running minimum is VIMNMX3 (two keys per instruction) and the group's
+// winner is folded into (best, base) with one compare + two selects per 8 spheres.  First in list wins ties
+// (chandelier.py:438-444 uses a strict <).  Returns the scene index or -1; the caller recomputes the winner's
+// distance with the cancellation-free form.
+RT_DEV int brute_select_pk(const float4 *pk, int n_padded, int key_mask, V3<float> O, V3<float> D) {
+    const float od = dot(O, D), oo = dot(O, O);
+    const f32x2 Dx = pack2(D.x, D.x), Dy = pack2(D.y, D.y), Dz = pack2(D.z, D.z), nod = pack2(-od, -od);
+    const f32x2 Bx = pack2(2.f * O.x, 2.f * O.x), By = pack2(2.f * O.y, 2.f * O.y), Bz = pack2(2.f * O.z, 2.f * O.z);
+    const f32x2 noo = pack2(-oo, -oo), neg1 = pack2(-1.f, -1.f);
+    int best = RT_KEY_INF, bbase = 0;
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(pk);
+    for (int base = 0; base < n_padded; base += 8) {
+        int key[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const ulonglong2 a = q[base + 2 * j], b = q[base + 2 * j + 1];       // (cx, cy) pairs, (cz, w) pairs
+            const f32x2 tca = fma2(b.x, Dz, fma2(a.y, Dy, fma2(a.x, Dx, nod)));
+            const f32x2 nm = fma2(b.x, Bz, fma2(a.y, By, fma2(a.x, Bx, add2(b.y, noo))));
+            const f32x2 disc = fma2(tca, tca, nm);
+            float tc0, tc1, d0, d1;
+            unpack2(tca, tc0, tc1); unpack2(disc, d0, d1);
+            const float s0 = M<float>::sqrt(__int_as_float(__float_as_int(d0) | (__float_as_int(tc0) & (int)0x80000000)));
+            const float s1 = M<float>::sqrt(__int_as_float(__float_as_int(d1) | (__float_as_int(tc1) & (int)0x80000000)));
+            float t0, t1;
+            unpack2(fma2(pack2(s0, s1), neg1, tca), t0, t1);
+            key[2 * j] = (__float_as_int(t0) & key_mask) | (2 * j);
+            key[2 * j + 1] = (__float_as_int(t1) & key_mask) | (2 * j + 1);
+        }
+        int g = __vimin3_s32(key[0], key[1], key[2]);
+        g = __vimin3_s32(g, key[3], key[4]);
+        g = __vimin3_s32(g, key[5], key[6]);
+        g = min(g, key[7]);
+        if (g < best) { best = g; bbase = base; }
+    }
+    return best < RT_KEY_INF ? bbase + (best & 7) : -1;
+}
+
 template <typename T, bool kAbs, bool kBvh>
 RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests) {
     T best = M<T>::inf(), bt = T(0);
@@ -107,7 +160,8 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
         const int n = g.sv.n;
         if (suppress == RT_NO_ID_DEV) {
             if constexpr (!M<T>::exact) {
-                brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
+                if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
+                else brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
                 if (bi >= 0) {
                     // winner's distance, cancellation-free; a silhouette-grazing winner the robust form rejects keeps
                     // the selection's own distance
