@@ -61,7 +61,8 @@ struct rt_env {
 
 template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
-    size_t b = v * (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL);
+    size_t b = v * (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL +
+                    3 * (size_t)((nL + 1) / 2));
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
     return (b + 255) & ~size_t(255);
 }
@@ -84,6 +85,7 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
     v4 *p_col = p; p += nP;
     v4 *l_pos = p; p += nL;
     v4 *l_col = p; p += nL;
+    v4 *lpk = p; p += 3 * ((nL + 1) / 2);    // light pairs for the packed direct-light loop, rt_trace.cuh
     int *q = reinterpret_cast<int *>(p);
     int *ids = q; q += n;
     int *g_func = q; q += nG;
@@ -129,6 +131,18 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
         l_col[i].w = (T)0;
         l_index[i] = s->l_index[i];
     }
+    // pair j = lights (2j, 2j+1): lpk[3j] = 128*(x0 x1 y0 y1), lpk[3j+1] = (128*z0 128*z1 R0 R1), lpk[3j+2] = (G0 G1 B0 B1)
+    // with (R,G,B) = colour * 0.3 * 16384 (direct_light_pk saturates dn/d^3 / 16384 to [0,1]); the odd slot of the
+    // last pair is a black light at the origin
+    for (int i = 0; i < 2 * ((nL + 1) / 2); ++i) {
+        const bool real = i < nL;
+        const double x = real ? s->l_centre[3 * i] : 0.0, y = real ? s->l_centre[3 * i + 1] : 0.0, z = real ? s->l_centre[3 * i + 2] : 0.0;
+        const double k = 0.3 * 16384.0;
+        const double r = real ? s->l_colour[3 * i] * k : 0.0, g = real ? s->l_colour[3 * i + 1] * k : 0.0, b = real ? s->l_colour[3 * i + 2] * k : 0.0;
+        v4 *t = lpk + 3 * (i / 2);
+        if (i & 1) { t[0].y = (T)(128.0 * x); t[0].w = (T)(128.0 * y); t[1].y = (T)(128.0 * z); t[1].w = (T)r; t[2].y = (T)g; t[2].w = (T)b; }
+        else { t[0].x = (T)(128.0 * x); t[0].z = (T)(128.0 * y); t[1].x = (T)(128.0 * z); t[1].z = (T)r; t[2].x = (T)g; t[2].z = (T)b; }
+    }
 }
 
 template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc *s, const uint8_t *small_dev) {
@@ -147,6 +161,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     v.p_col = p; p += nP;
     v.l_pos = p; p += nL;
     v.l_col = p; p += nL;
+    v.lpk = p; p += 3 * ((nL + 1) / 2);
     int *q = reinterpret_cast<int *>(p);
     v.ids = q; q += n;
     v.g_func = q; q += nG;

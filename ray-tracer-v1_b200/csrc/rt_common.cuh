@@ -147,6 +147,7 @@ struct PathRng {
 //   pk    sphere pairs (2j, 2j+1): (cx0 cx1 cy0 cy1), (cz0 cz1 w0 w1) with w = r^2 - |c|^2 (packed selection loop)
 //   col   r g b 1/r             g_vec x y z max_angle     g_col r g b strength
 //   p_pos x y z max_angle       p_col r g b strength      l_pos x y z -      l_col r g b -
+//   lpk   light pairs (2j, 2j+1): 128*(x0 x1 y0 y1), (128*z0 128*z1 R0 R1), (G0 G1 B0 B1), RGB = colour*0.3*16384
 template <typename T> struct SceneDev {
     using v4 = typename M<T>::v4;
     int n, nG, nP, nL;
@@ -154,7 +155,7 @@ template <typename T> struct SceneDev {
     const int *ids;
     const v4 *g_vec, *g_col; const int *g_func;
     const v4 *p_pos, *p_col; const int *p_id, *p_func;
-    const v4 *l_pos, *l_col; const int *l_index;
+    const v4 *l_pos, *l_col, *lpk; const int *l_index;
     const uint8_t *small;
     int key_mask;             // 0x7ffffff8, passed as DATA so that the selection loop's (t & mask) | k stays ONE LOP3
     T bg[3];

@@ -163,14 +163,13 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
                 if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
                 else brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
                 if (bi >= 0) {
-                    // winner's distance, cancellation-free; a silhouette-grazing winner the robust form rejects keeps
-                    // the selection's own distance
-                    if (!sphere_test<T>(O, D, g.sv.sph[bi], 0, bt)) {
-                        const typename M<T>::v4 w = g.sv.sph[bi];
-                        const V3<T> L = centre_of<T>(w) - O;
-                        const T tca = dot(L, D);
-                        bt = tca - M<T>::sqrt(fmaxf(fmaf(tca, tca, fmaf(w.w, w.w, -dot(L, L))), 0.f));
-                    }
+                    // winner's distance from the cancellation-free form |L - tca D|^2; a silhouette-grazing winner
+                    // whose robust discriminant rounds below zero gets thc = 0
+                    const typename M<T>::v4 w = g.sv.sph[bi];
+                    const V3<T> L = centre_of<T>(w) - O;
+                    const T tca = dot(L, D);
+                    const V3<T> f = L - D * tca;
+                    bt = tca - M<T>::sqrt(fmaxf(fmaf(w.w, w.w, -dot(f, f)), 0.f));
                 }
             } else {
 #pragma unroll 2
@@ -236,7 +235,8 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
 template <typename T> RT_DEV void finish_hit(const Geo<T> &g, V3<T> O, V3<T> D, int i, T t, Hit<T> &h) {
     h.idx = i; h.t = t;
     h.p = O + D * t;                                          // ray.py:99
-    h.n = normalise(h.p - centre_of<T>(g.sv.sph[i]));         // ray.py:100
+    if constexpr (M<T>::exact) h.n = normalise(h.p - centre_of<T>(g.sv.sph[i]));      // ray.py:100
+    else h.n = (h.p - centre_of<T>(g.sv.sph[i])) * g.sv.col[i].w;                     // col.w = 1/r
 }
 
 // Ray.sphereExitRay (ray.py:109-157).  false = trapped (reference prints + returns None) or the reference would
@@ -363,7 +363,7 @@ RT_DEV void terminal_rgb(const Geo<T> &g, const LightsA<T> &lt, const Hit<T> &h,
 template <typename T> struct LightsB {
     using v4 = typename M<T>::v4;
     int nL;
-    const v4 *l_pos, *l_col;
+    const v4 *l_pos, *l_col, *lpk;
     const int *l_index;
 };
 
@@ -432,29 +432,85 @@ RT_DEV uint32_t direct_light(const LightsB<T> &lb, int hit_idx, V3<T> p, V3<T> n
     return (uint32_t)d0 | ((uint32_t)d1 << 8) | ((uint32_t)d2 << 16);
 }
 
+// FP32 product form of direct_light over the light-pair array (SceneDev::lpk), branch-free, two lights per FP32
+// instruction.  Positions are stored times 128 and colours times 0.3 * 16384, so with tl' = 128 (l - p):
+//     s' = sat(n.tl' * rsqrt(tl'.tl')^3) = sat(cos / d^2 / 16384),     x = colour' * s' = colour * cos * 0.3 / d^2
+// and a contribution that saturates is >= 255 on every channel with colour >= 0.052, i.e. the final min(255, .)
+// hides the clamp.  cos <= 0 saturates to 0 (chandelier.py:470: `if cos_angle > 0`); the self test of
+// chandelier.py:465 is implied: for a light that is itself the (non-emissive) hit sphere, l - p = -r n, cos = -1.
+// int() is FFMA2.RZ onto 2^23 (the mantissa then holds floor(x) for 0 <= x < 2^23) and the sums are integer adds.
+RT_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+RT_DEV f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+RT_DEV float mul_sat(float a, float b) { float d; asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
+RT_DEV uint32_t direct_light_pk(const float4 *lpk, int n_pairs, V3<float> p, V3<float> n) {
+    const float qx = -128.f * p.x, qy = -128.f * p.y, qz = -128.f * p.z;
+    const f32x2 px = pack2(qx, qx), py = pack2(qy, qy), pz = pack2(qz, qz);
+    const f32x2 nx = pack2(n.x, n.x), ny = pack2(n.y, n.y), nz = pack2(n.z, n.z);
+    const f32x2 magic = pack2(8388608.f, 8388608.f);
+    unsigned a0 = 0u, a1 = 0u, a2 = 0u;
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(lpk);
+#pragma unroll 2
+    for (int j = 0; j < n_pairs; ++j) {
+        const ulonglong2 A = q[3 * j], B = q[3 * j + 1], C = q[3 * j + 2];
+        const f32x2 tx = add2(A.x, px), ty = add2(A.y, py), tz = add2(B.x, pz);
+        const f32x2 qq = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
+        const f32x2 dn = fma2(tz, nz, fma2(ty, ny, mul2(tx, nx)));
+        float q0, q1;
+        unpack2(qq, q0, q1);
+        const f32x2 inv = pack2(M<float>::rsqrt(q0), M<float>::rsqrt(q1));
+        float a_lo, a_hi, b_lo, b_hi;
+        unpack2(mul2(dn, inv), a_lo, a_hi);
+        unpack2(mul2(inv, inv), b_lo, b_hi);
+        const f32x2 s = pack2(mul_sat(a_lo, b_lo), mul_sat(a_hi, b_hi));
+        unsigned r_lo, r_hi, g_lo, g_hi, b0, b1;
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(r_lo), "=r"(r_hi) : "l"(fma2_rz(B.y, s, magic)));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(g_lo), "=r"(g_hi) : "l"(fma2_rz(C.x, s, magic)));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(b0), "=r"(b1) : "l"(fma2_rz(C.y, s, magic)));
+        a0 += r_lo + r_hi; a1 += g_lo + g_hi; a2 += b0 + b1;
+    }
+    const unsigned bias = 2u * (unsigned)n_pairs * 0x4B000000u;          // bits of 2^23, once per light
+    a0 = min(a0 - bias, 255u); a1 = min(a1 - bias, 255u); a2 = min(a2 - bias, 255u);
+    return a0 | (a1 << 8) | (a2 << 16);
+}
+
 // next ray of a path after a non-emissive hit (chandelier.py:479-507): mirror if reflective > threshold, else a
 // cosine-weighted direction around the normal from two uniforms.
 template <typename T>
 RT_DEV V3<T> bounce_direction(V3<T> D, V3<T> n, bool mirror, T r1, T r2) {
-    if (mirror) {
-        V3<T> r = reflect<T>(D, n);
-        return M<T>::exact ? normalise(r) : r;
-    }
-    T st, ct, sp, cp;
     if constexpr (M<T>::exact) {
+        if (mirror) return normalise(reflect<T>(D, n));
         T theta = ::acos(::sqrt(r1)), phi = 2 * 3.14159265358979323846 * r2;
-        st = ::sin(theta); ct = ::cos(theta); sp = ::sin(phi); cp = ::cos(phi);
+        T st = ::sin(theta), ct = ::cos(theta), sp = ::sin(phi), cp = ::cos(phi);
+        V3<T> tg = ::fabs(n.z) > T(0.9) ? mk<T>(1, 0, 0) : cross(mk<T>(0, 0, 1), n);
+        tg = normalise(tg);
+        V3<T> bt = normalise(cross(n, tg));
+        T lx = st * cp, ly = st * sp, lz = ct;
+        V3<T> bd = normalise(mk<T>(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y,
+                                   lx * tg.z + ly * bt.z + lz * n.z));
+        return normalise(bd);
     } else {
-        ct = M<T>::sqrt(r1); st = M<T>::sqrt(1.f - r1);                 // cos/sin(acos(sqrt r1))
-        sincospif(2.f * r2, &sp, &cp);
+        // unit D and n: the mirror direction is unit already
+        if (mirror) return D - n * (2.f * dot(D, n));
+        // cos/sin(acos(sqrt r1)) = sqrt(r1), sqrt(1 - r1); phi - pi in [-pi, pi) for MUFU.SIN/COS (abs error 2^-20.9),
+        // sin(phi) = -sin(phi - pi), cos(phi) = -cos(phi - pi)
+        const float ct = M<float>::sqrt(r1), st = M<float>::sqrt(1.f - r1);
+        const float x = fmaf(r2, 6.28318530717958647692f, -3.14159265358979323846f);
+        float sp, cp;
+        asm("sin.approx.ftz.f32 %0, %1;" : "=f"(sp) : "f"(x));
+        asm("cos.approx.ftz.f32 %0, %1;" : "=f"(cp) : "f"(x));
+        // tangent (1,0,0) or (0,0,1) x n = (-n.y, n.x, 0): z is 0 either way (chandelier.py:493-496)
+        const bool deg = fabsf(n.z) > 0.9f;
+        float tx = deg ? 1.f : -n.y, ty = deg ? 0.f : n.x;
+        const float k1 = M<float>::rsqrt(fmaf(tx, tx, ty * ty));
+        tx *= k1; ty *= k1;
+        const float bx = -n.z * ty, by = n.z * tx, bz = fmaf(n.x, ty, -n.y * tx);            // n x tangent
+        const float k2 = M<float>::rsqrt(fmaf(bx, bx, fmaf(by, by, bz * bz)));
+        const float lx = -st * cp, ly = -st * sp * k2, lz = ct;
+        const float dx = fmaf(lx, tx, fmaf(ly, bx, lz * n.x)), dy = fmaf(lx, ty, fmaf(ly, by, lz * n.y)),
+                    dz = fmaf(ly, bz, lz * n.z);
+        const float k3 = M<float>::rsqrt(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+        return mk<float>(dx * k3, dy * k3, dz * k3);
     }
-    V3<T> tg = M<T>::fabs(n.z) > T(0.9) ? mk<T>(1, 0, 0) : cross(mk<T>(0, 0, 1), n);
-    tg = normalise(tg);
-    V3<T> bt = normalise(cross(n, tg));
-    T lx = st * cp, ly = st * sp, lz = ct;
-    V3<T> bd = normalise(mk<T>(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y,
-                               lx * tg.z + ly * bt.z + lz * n.z));
-    return M<T>::exact ? normalise(bd) : bd;
 }
 
 }  // namespace rt
