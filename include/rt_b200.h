@@ -169,6 +169,56 @@ int rt_render_path(rt_scene *scene, int precision, const rt_path_params *p, void
 int rt_resolve(int device, int precision, const void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1,
                int32_t spp, float *image_dev, void *stream);
 
+/* ---- fused multi-GPU sinks for Algorithm B frames ---------------------------------------------
+ * One process per GPU; a rank's path kernel stores its result where it is needed -- its own accumulators, the
+ * final image on the collecting rank, or the accumulators of the rank that owns the pixel -- through NVLink peer
+ * mappings, so the tile gather / sample reduce is the render kernel's own epilogue instead of a second pass.
+ *
+ *   RT_SINK_ACCUM        accum_dev of rt_render_path (no sink).
+ *   RT_SINK_IMAGE        tile sharding.  The launch covers the 8-row tiles tile_first, tile_first + tile_step, ...
+ *                        (interleaved stripes: load balance with no contiguity constraint), all spp samples, and
+ *                        stores min(1, floor(sum/spp)/255) as float32 [H,W,3] straight into `image` (local or a peer
+ *                        mapping of the collecting rank's image).
+ *   RT_SINK_SCATTER_ADD  sample sharding.  The launch covers every pixel for its sample range and adds
+ *                        (r, g, b, samples) with one 16-byte system-scope reduction per pixel into accum[k], k = the
+ *                        rank whose row band [band_y[k], band_y[k+1]) holds the pixel (reduce-scatter by direct
+ *                        NVLink atomics; integer-valued FP32 sums < 2^24 are exact and order-independent).
+ *                        Needs integer colours (every scene of the reference); RT_ERR_UNSUPPORTED otherwise.
+ * Cross-rank ordering uses epoch flags in peer memory: rt_peer_signal after the writes, rt_peer_wait before the
+ * reads (stream-ordered, system-scope release/acquire). */
+enum { RT_SINK_ACCUM = 0, RT_SINK_IMAGE = 1, RT_SINK_SCATTER_ADD = 2 };
+#define RT_MAX_PEERS 16
+#define RT_IPC_HANDLE_BYTES 64
+typedef struct rt_path_sink {
+    int32_t mode;
+    int32_t world;                    /* ranks (SCATTER_ADD) */
+    int32_t tile_first, tile_step;    /* IMAGE: 8-row tiles rendered by this launch */
+    float *image;                     /* IMAGE: [H,W,3] float32, device or peer pointer */
+    void *accum[RT_MAX_PEERS];        /* SCATTER_ADD: per-owner [H,W,4] float32 accumulators (zeroed by the owner) */
+    int32_t band_y[RT_MAX_PEERS + 1]; /* SCATTER_ADD: owner row bands */
+} rt_path_sink;
+/* FP32 product path only.  p->y0/y1 are ignored for RT_SINK_IMAGE (the tiles say which rows); p->s0/s1 must be the
+ * full [0, spp) range there. */
+int rt_render_path_sink(rt_scene *scene, const rt_path_params *p, const rt_path_sink *sink, uint64_t *stats_dev,
+                        void *stream);
+/* resolve rows [y0,y1) of accum into image (device or peer pointer) and, when clear != 0, zero those accum rows for
+ * the next frame. */
+int rt_resolve_clear(int device, void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1, int32_t spp,
+                     float *image_dev, int32_t clear, void *stream);
+
+/* peer memory (CUDA IPC): rt_peer_alloc = cudaMalloc + zero + export; the handle travels to the other ranks by any
+ * means (torch.distributed.all_gather_object), which open it with rt_peer_open. */
+int rt_peer_alloc(int device, size_t bytes, void **out_dev, unsigned char handle[RT_IPC_HANDLE_BYTES]);
+int rt_peer_open(int device, const unsigned char handle[RT_IPC_HANDLE_BYTES], void **out_dev);
+int rt_peer_close(int device, void *ptr_dev);
+int rt_peer_free(int device, void *ptr_dev);
+/* store `epoch` (system-scope release, after a system fence) into n flag words, typically one per peer */
+int rt_peer_signal(int device, uint32_t *const *flag_ptrs, int32_t n, uint32_t epoch, void *stream);
+/* spin (system-scope acquire) until flags_dev[i] - epoch >= 0 for all i < n; gives up after timeout_ms and sets
+ * *timed_out_dev (device int32, optional) to 1 */
+int rt_peer_wait(int device, const uint32_t *flags_dev, int32_t n, uint32_t epoch, int32_t timeout_ms,
+                 int32_t *timed_out_dev, void *stream);
+
 /* Host-buffer convenience entries (what a ctypes/cffi binding of the reference's render() calls): upload nothing
  * but the parameters, render, resolve, copy the float32 [H,W,3] image (and optionally the raw sums [H,W,4] in the
  * accum type, and stats) back to HOST memory.  Synchronous. */

@@ -62,6 +62,15 @@ class PathParams(C.Structure):
                 ("schedule", C.c_int32)]
 
 
+RT_MAX_PEERS, IPC_HANDLE_BYTES = 16, 64
+SINK_ACCUM, SINK_IMAGE, SINK_SCATTER_ADD = 0, 1, 2
+
+
+class PathSink(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("world", C.c_int32), ("tile_first", C.c_int32), ("tile_step", C.c_int32),
+                ("image", C.c_void_p), ("accum", C.c_void_p * RT_MAX_PEERS), ("band_y", C.c_int32 * (RT_MAX_PEERS + 1))]
+
+
 class EnvDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("cam", C.c_double * 3),
                 ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("max_bounces", C.c_int32),
@@ -95,6 +104,14 @@ SIGNATURES = {
     "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
     "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "rt_render_path_sink": (C.c_int, [vp, C.POINTER(PathParams), C.POINTER(PathSink), vp, vp]),
+    "rt_resolve_clear": (C.c_int, [C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]),
+    "rt_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
+    "rt_peer_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(vp)]),
+    "rt_peer_close": (C.c_int, [C.c_int, vp]),
+    "rt_peer_free": (C.c_int, [C.c_int, vp]),
+    "rt_peer_signal": (C.c_int, [C.c_int, C.POINTER(vp), C.c_int32, C.c_uint32, vp]),
+    "rt_peer_wait": (C.c_int, [C.c_int, vp, C.c_int32, C.c_uint32, C.c_int32, vp, vp]),
     "rt_render_whitted_host": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path_host": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
     "rt_env_create": (C.c_int, [vp, C.c_int, C.POINTER(EnvDesc), C.POINTER(vp)]),
@@ -369,6 +386,10 @@ class DeviceScene:
 
     def render_path(self, params, accum, precision=F32, stats=None, stream=None):
         check(lib().rt_render_path(self.handle, precision, C.byref(params), _ptr(accum), _ptr(stats), stream))
+
+    def render_path_sink(self, params, sink, stats=None, stream=None):
+        """FP32 path kernel with a fused multi-GPU sink (``PathSink``: image store / scatter-add over peer memory)."""
+        check(lib().rt_render_path_sink(self.handle, C.byref(params), C.byref(sink), _ptr(stats), stream))
 
     def resolve(self, accum, W, H, spp, image, precision=F32, rows=None, stream=None):
         y0, y1 = (0, H) if rows is None else rows

@@ -250,8 +250,12 @@ RT_EXPORT int rt_device_count(int *count) {
 RT_EXPORT int rt_device_props(int device, int64_t *props6, size_t *total_mem) {
     cudaDeviceProp p;
     CU(cudaGetDeviceProperties(&p, device));
-    int khz = 0;
-    CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    static int khz_cache[64] = {0};        // cudaDevAttrClockRate is a slow query: once per device
+    int khz = device >= 0 && device < 64 ? khz_cache[device] : 0;
+    if (khz == 0) {
+        CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        if (device >= 0 && device < 64) khz_cache[device] = khz;
+    }
     if (props6) {
         props6[0] = p.multiProcessorCount; props6[1] = p.major; props6[2] = p.minor; props6[3] = khz;
         props6[4] = p.l2CacheSize; props6[5] = (int64_t)p.sharedMemPerBlockOptin;
@@ -488,8 +492,9 @@ RT_EXPORT int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted
 // ------------------------------------------------------------------ Algorithm B frame
 template <typename T>
 static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_path_params *p, void *accum, uint64_t *stats,
-                         cudaStream_t st) {
+                         cudaStream_t st, const rt_path_sink *sink = nullptr) {
     PathDev<T> pp;
+    std::memset(&pp, 0, sizeof pp);
     pp.cam[0] = (T)p->cam[0]; pp.cam[1] = (T)p->cam[1]; pp.cam[2] = (T)p->cam[2];
     pp.W = p->W; pp.H = p->H; pp.y0 = p->y0; pp.y1 = p->y1; pp.s0 = p->s0; pp.s1 = p->s1; pp.max_bounces = p->max_bounces;
     // chandelier.py:412-415: aspect = W/H; half_height = tan(radians(fov)/2); half_width = half_height*aspect
@@ -501,6 +506,28 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     pp.accumulate = p->accumulate;
     pp.int_fold = sc->int_colours && (p->s1 - p->s0) <= 65536;
     pp.regenerate = p->schedule == 1;
+    pp.sink = RT_SINK_ACCUM; pp.tile_step = 1; pp.world = 1; pp.spp_total = p->s1 - p->s0;
+    if (sink && sink->mode != RT_SINK_ACCUM) {
+        if (!pp.int_fold) return fail(RT_ERR_UNSUPPORTED, "fused sinks need integer colours and <= 65536 samples per launch");
+        pp.sink = sink->mode;
+        if (sink->mode == RT_SINK_IMAGE) {
+            if (!sink->image || sink->tile_step < 1 || sink->tile_first < 0) return fail(RT_ERR_INVALID, "bad image sink");
+            pp.image = sink->image; pp.tile_step = sink->tile_step;
+            pp.y0 = sink->tile_first * 8; pp.y1 = p->H;
+            if (p->s0 != 0) return fail(RT_ERR_INVALID, "an image sink resolves in the kernel: the launch must cover all samples");
+        } else if (sink->mode == RT_SINK_SCATTER_ADD) {
+            if (sink->world < 1 || sink->world > RT_MAX_PEERS) return fail(RT_ERR_INVALID, "bad world size");
+            if ((double)(p->s1 - p->s0) * 65535.0 >= 16777216.0 * 255.0)      // sums stay exact in FP32 for 8-bit colours
+                return fail(RT_ERR_UNSUPPORTED, "sample range too long for exact FP32 sums");
+            pp.world = sink->world;
+            for (int k = 0; k < sink->world; ++k) {
+                if (!sink->accum[k]) return fail(RT_ERR_INVALID, "missing peer accumulator");
+                pp.peer_accum[k] = reinterpret_cast<float4 *>(sink->accum[k]);
+            }
+            for (int k = 0; k <= sink->world; ++k) pp.band_y[k] = sink->band_y[k];
+            if (pp.band_y[0] != 0 || pp.band_y[sink->world] != p->H) return fail(RT_ERR_INVALID, "owner bands must cover the image");
+        } else return fail(RT_ERR_INVALID, "unknown sink mode");
+    }
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st));
     return RT_OK;
 }
@@ -515,6 +542,92 @@ RT_EXPORT int rt_render_path(rt_scene *scene, int precision, const rt_path_param
     if (precision == RT_F64) return render_path_t<double>(scene, scene->d.view, p, accum_dev, stats_dev, S(stream));
     if (precision == RT_F32) return render_path_t<float>(scene, scene->f.view, p, accum_dev, stats_dev, S(stream));
     return fail(RT_ERR_INVALID, "unknown precision");
+}
+
+RT_EXPORT int rt_render_path_sink(rt_scene *scene, const rt_path_params *p, const rt_path_sink *sink, uint64_t *stats_dev,
+                                  void *stream) {
+    if (!scene || !p || !sink) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_band(p->W, p->H, 0, p->H, p->s0, p->s1);
+    if (rc) return rc;
+    if (p->max_bounces > RT_PATH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "max_bounces above 32 is not supported by the path kernel");
+    if (sink->mode == RT_SINK_ACCUM) return fail(RT_ERR_INVALID, "use rt_render_path for the accumulator sink");
+    CU(cudaSetDevice(scene->device));
+    rt_path_params q = *p;
+    q.y0 = 0; q.y1 = p->H;
+    return render_path_t<float>(scene, scene->f.view, &q, nullptr, stats_dev, S(stream), sink);
+}
+
+RT_EXPORT int rt_resolve_clear(int device, void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1, int32_t spp,
+                               float *image_dev, int32_t clear, void *stream) {
+    if (!accum_dev || !image_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (W <= 0 || H <= 0 || y0 < 0 || y1 > H || y0 > y1 || spp <= 0) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    CU(launch_resolve_clear(reinterpret_cast<float4 *>(accum_dev), W, y0, y1, spp, image_dev, clear, S(stream)));
+    return RT_OK;
+}
+
+// ------------------------------------------------------------------ peer memory (CUDA IPC) and epoch flags
+static_assert(sizeof(cudaIpcMemHandle_t) == RT_IPC_HANDLE_BYTES, "IPC handle size");
+RT_EXPORT int rt_peer_alloc(int device, size_t bytes, void **out_dev, unsigned char handle[RT_IPC_HANDLE_BYTES]) {
+    if (!out_dev || !handle || bytes == 0) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    void *p = nullptr;
+    CU(cudaMalloc(&p, bytes));
+    cudaError_t e = cudaMemset(p, 0, bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return cuda_fail(e, "rt_peer_alloc"); }
+    std::memcpy(handle, &h, sizeof h);
+    *out_dev = p;
+    return RT_OK;
+}
+RT_EXPORT int rt_peer_open(int device, const unsigned char handle[RT_IPC_HANDLE_BYTES], void **out_dev) {
+    if (!out_dev || !handle) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof h);
+    CU(cudaIpcOpenMemHandle(out_dev, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+RT_EXPORT int rt_peer_close(int device, void *ptr_dev) {
+    if (!ptr_dev) return RT_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(ptr_dev));
+    return RT_OK;
+}
+RT_EXPORT int rt_peer_free(int device, void *ptr_dev) {
+    if (!ptr_dev) return RT_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr_dev));
+    return RT_OK;
+}
+RT_EXPORT int rt_peer_signal(int device, uint32_t *const *flag_ptrs, int32_t n, uint32_t epoch, void *stream) {
+    if (!flag_ptrs || n < 1 || n > 32) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    PeerFlagTable tab;
+    std::memset(&tab, 0, sizeof tab);
+    for (int i = 0; i < n; ++i) {
+        if (!flag_ptrs[i]) return fail(RT_ERR_INVALID, "NULL flag pointer");
+        tab.p[i] = flag_ptrs[i];
+    }
+    cudaError_t e = launch_peer_signal(tab, n, epoch, S(stream));
+    if (e != cudaSuccess) return cuda_fail(e, "rt_peer_signal");
+    return RT_OK;
+}
+RT_EXPORT int rt_peer_wait(int device, const uint32_t *flags_dev, int32_t n, uint32_t epoch, int32_t timeout_ms,
+                           int32_t *timed_out_dev, void *stream) {
+    if (!flags_dev || n < 1 || n > 32) return fail(RT_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(device));
+    static int khz_cache[64] = {0};        // cudaDevAttrClockRate is a slow query: once per device
+    int khz = device >= 0 && device < 64 ? khz_cache[device] : 0;
+    if (khz == 0) {
+        CU(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+        if (device >= 0 && device < 64) khz_cache[device] = khz;
+    }
+    const long long cycles = (long long)(timeout_ms > 0 ? timeout_ms : 2000) * (long long)(khz > 0 ? khz : 2000000);
+    CU(launch_peer_wait(flags_dev, n, epoch, cycles, timed_out_dev, S(stream)));
+    return RT_OK;
 }
 
 RT_EXPORT int rt_resolve(int device, int precision, const void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1,

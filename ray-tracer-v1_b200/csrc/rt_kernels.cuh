@@ -191,7 +191,8 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     if constexpr (!kShared) __syncthreads();
     int x, yr;
     tile_pixel(x, yr);
-    const int y = pp.y0 + yr;
+    // tile_step > 1: this launch owns every tile_step-th 8-row tile starting at y0 (interleaved stripes)
+    const int y = pp.y0 + yr + (int)blockIdx.y * 8 * (pp.tile_step - 1);
     const bool has_pixel = x < pp.W && y < pp.y1;
     unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
     const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
@@ -286,12 +287,34 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     }
     if (has_pixel && ns > 0) {
         const size_t o = (size_t)y * pp.W + x;
-        typename M<T>::v4 out = M<T>::make4(T(a0), T(a1), T(a2), T(ns));
-        if (pp.accumulate) {
-            const typename M<T>::v4 old = accum[o];
-            out.x += old.x; out.y += old.y; out.z += old.z; out.w += old.w;
+        bool to_accum = true;
+        if constexpr (!M<T>::exact && kIntFold) {
+            if (pp.sink == 1) {
+                // tile sharding: the resolved pixel goes straight to the final image (possibly a peer mapping)
+                const double s = (double)pp.spp_total;
+                const double r = floor((double)a0 / s) / 255.0, g = floor((double)a1 / s) / 255.0, b = floor((double)a2 / s) / 255.0;
+                float *px = pp.image + 3 * o;
+                px[0] = (float)(r < 1.0 ? r : 1.0); px[1] = (float)(g < 1.0 ? g : 1.0); px[2] = (float)(b < 1.0 ? b : 1.0);
+                to_accum = false;
+            } else if (pp.sink == 2) {
+                // sample sharding: one 16-byte system-scope reduction into the accumulators of the pixel's owner
+                int k = min(pp.world - 1, (int)(((long long)y * pp.world) / pp.H));
+                while (y >= pp.band_y[k + 1]) ++k;
+                while (y < pp.band_y[k]) --k;
+                float4 *dst = pp.peer_accum[k] + o;
+                asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                             :: "l"(dst), "f"((float)a0), "f"((float)a1), "f"((float)a2), "f"((float)ns) : "memory");
+                to_accum = false;
+            }
         }
-        accum[o] = out;
+        if (to_accum) {
+            typename M<T>::v4 out = M<T>::make4(T(a0), T(a1), T(a2), T(ns));
+            if (pp.accumulate) {
+                const typename M<T>::v4 old = accum[o];
+                out.x += old.x; out.y += old.y; out.z += old.z; out.w += old.w;
+            }
+            accum[o] = out;
+        }
     }
     if (stats) {
         flush_stats(stats, STAT_RAYS, n_rays);
@@ -630,7 +653,8 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
                         cudaStream_t st) {
     const int rows = pp.y1 - pp.y0;
     if (rows <= 0 || pp.W <= 0) return cudaSuccess;
-    dim3 grid((pp.W + 31) / 32, (rows + 7) / 8), block(256);
+    const int tiles = (rows + 7) / 8, step = pp.tile_step > 1 ? pp.tile_step : 1;
+    dim3 grid((pp.W + 31) / 32, (tiles + step - 1) / step), block(256);
     using v4 = typename M<T>::v4;
     const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold
     const int mode = mode_for(sc, extra);

@@ -26,6 +26,11 @@ template <typename T> struct PathDev {
     int accumulate;
     int int_fold;                // every leaf colour is an integer in [0, 65535]: integer fold + uint32 accumulators
     int regenerate;              // 1: path-regeneration schedule, 0: lock-step schedule (rt_kernels.cuh)
+    // fused multi-GPU sinks (rt_path_sink, include/rt_b200.h); sink == 0: accum only
+    int sink, tile_step, world, spp_total;
+    float *image;
+    float4 *peer_accum[16];
+    int band_y[17];
 };
 
 // batched RayTracerEnv state (SoA, [3][B] for vectors)
@@ -45,6 +50,12 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
                         cudaStream_t st);
 template <typename T>
 cudaError_t launch_resolve(const void *accum, int W, int y0, int y1, int spp, float *image, cudaStream_t st);
+// rt_f32.cu: resolve + clear, peer flags
+cudaError_t launch_resolve_clear(float4 *accum, int W, int y0, int y1, int spp, float *image, int clear, cudaStream_t st);
+struct PeerFlagTable { unsigned *p[32]; };      // flag addresses ride in the kernel's parameter block
+cudaError_t launch_peer_signal(const PeerFlagTable &flags, int n, unsigned epoch, cudaStream_t st);
+cudaError_t launch_peer_wait(const unsigned *flags, int n, unsigned epoch, long long timeout_cycles, int *timed_out,
+                             cudaStream_t st);
 template <typename T>
 cudaError_t launch_sphere_disc(int m, const double *rays, const double *spheres, int point, double *out, cudaStream_t st);
 template <typename T>

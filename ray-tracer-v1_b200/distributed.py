@@ -15,7 +15,8 @@ world_size-2 ``gloo`` tests on CPU exercise exactly this code with a stand-in re
 """
 import numpy as np
 
-__all__ = ["row_bands", "sample_ranges", "env_slices", "gather_row_bands", "reduce_sample_sums", "ShardedPathRenderer"]
+__all__ = ["row_bands", "sample_ranges", "env_slices", "tile_stripes", "gather_row_bands", "reduce_sample_sums",
+           "PeerFabric", "ShardedPathRenderer"]
 
 
 def _split(total, world):
@@ -35,6 +36,12 @@ def sample_ranges(spp, world):
 def env_slices(n_envs, world):
     """Contiguous [b0, b1) environment slices."""
     return _split(int(n_envs), int(world))
+
+
+def tile_stripes(height, world, rank, tile_rows=8):
+    """Rows of the interleaved 8-row stripes rank ``rank`` renders in the fused tile mode: tiles rank, rank + world, ..."""
+    tiles = (int(height) + tile_rows - 1) // tile_rows
+    return [(t * tile_rows, min(int(height), (t + 1) * tile_rows)) for t in range(int(rank), tiles, int(world))]
 
 
 def _dist():
@@ -94,6 +101,74 @@ def reduce_sample_sums(accum, group=None, dst=0):
     dst_global = dist.get_global_rank(group, dst) if group is not None else dst
     dist.reduce(accum, dst=dst_global, op=dist.ReduceOp.SUM, group=group)
     return accum
+
+
+class _DevArray:
+    """Zero-copy view of raw device memory for ``torch.as_tensor`` (CUDA array interface v3)."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                         "strides": None}
+
+
+class PeerFabric:
+    """Buffers of every rank of a process group mapped into this process (CUDA IPC, NVLink peer access), plus the
+    epoch flags that order writers and readers across ranks.  One instance per rank; collective construction.
+
+    ``alloc(name, nbytes)`` allocates ``nbytes`` on every rank and returns the list of the ``world`` device pointers
+    (own buffer at index ``rank``, peer mappings elsewhere).  The handles travel by ``all_gather_object``: this is the
+    only use of the process group; the data path is the kernels' own loads/stores/reductions over NVLink."""
+
+    def __init__(self, device, group=None):
+        from . import _native as nat
+        self.nat, self.device, self.group = nat, int(device), group
+        self.rank, self.world = _world(group)
+        if self.world > nat.RT_MAX_PEERS:
+            raise ValueError(f"at most {nat.RT_MAX_PEERS} ranks")
+        self.ptrs, self._own, self._opened = {}, [], []
+
+    def alloc(self, name, nbytes):
+        import ctypes as C
+        nat, dist = self.nat, _dist()
+        own, handle = C.c_void_p(), C.create_string_buffer(nat.IPC_HANDLE_BYTES)
+        nat.check(nat.lib().rt_peer_alloc(self.device, int(nbytes), C.byref(own), handle))
+        self._own.append(own.value)
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, handle.raw, group=self.group)
+        ptrs = []
+        for r in range(self.world):
+            if r == self.rank:
+                ptrs.append(own.value)
+            else:
+                q = C.c_void_p()
+                nat.check(nat.lib().rt_peer_open(self.device, handles[r], C.byref(q)))
+                self._opened.append(q.value)
+                ptrs.append(q.value)
+        self.ptrs[name] = ptrs
+        return ptrs
+
+    def signal(self, name, word, targets, epoch, stream=None):
+        """Store ``epoch`` into flag word ``word`` of buffer ``name`` on every rank in ``targets`` (after all writes
+        this stream issued so far)."""
+        import ctypes as C
+        nat = self.nat
+        tab = (C.c_void_p * len(targets))(*[self.ptrs[name][t] + 4 * int(word) for t in targets])
+        nat.check(nat.lib().rt_peer_signal(self.device, tab, len(targets), int(epoch) & 0xFFFFFFFF, stream))
+
+    def wait(self, name, first_word, n, epoch, timed_out=None, timeout_ms=4000, stream=None):
+        """Block the stream until the ``n`` local flag words from ``first_word`` have reached ``epoch``."""
+        nat = self.nat
+        nat.check(nat.lib().rt_peer_wait(self.device, self.ptrs[name][self.rank] + 4 * int(first_word), int(n),
+                                         int(epoch) & 0xFFFFFFFF, int(timeout_ms), nat._ptr(timed_out), stream))
+
+    def close(self):
+        nat = self.nat
+        for q in self._opened:
+            nat.load_symbols().rt_peer_close(self.device, q)
+        for q in self._own:
+            nat.load_symbols().rt_peer_free(self.device, q)
+        self._opened, self._own, self.ptrs = [], [], {}
 
 
 class ShardedPathRenderer:
@@ -176,7 +251,90 @@ class ShardedPathRenderer:
             return self.host_image.numpy(), self.stats
         return self.image, self.stats
 
+    # ---- fused sinks over NVLink peer memory ------------------------------------------------------------------
+    def _ensure_fabric(self, W, H):
+        """Peer-mapped, double-buffered frame storage: the final image on rank 0, one accumulator per rank, flags."""
+        torch = self.torch
+        if getattr(self, "_fab_key", None) == (W, H):
+            return
+        if getattr(self, "fabric", None) is not None:
+            self.fabric.close()
+        fab = self.fabric = PeerFabric(self.device, self.group)
+        fab.alloc("image0", H * W * 3 * 4); fab.alloc("image1", H * W * 3 * 4)
+        fab.alloc("accum0", H * W * 16); fab.alloc("accum1", H * W * 16)
+        fab.alloc("flags", 4 * 64)          # words 0..15 added[rank], 16..31 done[rank], 32 go
+        self._epoch = 0
+        self._timed_out = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", self.device))
+        self._fused_images = [torch.as_tensor(_DevArray(fab.ptrs[f"image{k}"][self.rank], (H, W, 3), "<f4"),
+                                              device=torch.device("cuda", self.device)) for k in (0, 1)]
+        if not hasattr(self, "host_image") or self._key != (W, H):
+            self._ensure(W, H)
+        self._fab_key = (W, H)
+
+    def render_fused(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, mode="tiles", to_host=False):
+        """The same frame as ``render`` with the collective fused into the kernels: no NCCL call on the data path.
+
+        tiles    every rank renders interleaved 8-row stripes (tile_stripes) and its path kernel stores the resolved
+                 float32 pixels straight into rank 0's image through the NVLink peer mapping.
+        samples  every rank renders its sample range of all pixels; the path kernel's epilogue adds each pixel's sums
+                 into the accumulators of the rank that owns the pixel's row band (one 16-byte system-scope reduction
+                 per pixel: a reduce-scatter), then every rank resolves its band into rank 0's image.
+        Ordering across ranks: epoch flags in peer memory (signal after the writes, wait before the reads), frames
+        double-buffered so rank 0 can still be reading frame f while frame f+1 is written."""
+        nat, sc, torch = self.nat, self.scene, self.torch
+        self._ensure_fabric(W, H)
+        fab, rank, world = self.fabric, self.rank, self.world
+        self._epoch += 1
+        e, buf = self._epoch, self._epoch & 1
+        everyone = list(range(world))
+        self.stats.zero_()
+        fab.wait("flags", 32, 1, e - 2, self._timed_out)                  # rank 0 has consumed this image buffer
+        p = sc.path_params(cam, W, H, spp, max_bounces, mirror_threshold, seed=seed, fov=fov)
+        sink = nat.PathSink()
+        if mode == "tiles":
+            sink.mode, sink.tile_first, sink.tile_step = nat.SINK_IMAGE, rank, world
+            sink.image = fab.ptrs[f"image{buf}"][0]
+            sc.render_path_sink(p, sink, stats=self.stats)
+            self.launches = 1
+        elif mode == "samples":
+            s0, s1 = sample_ranges(spp, world)[rank]
+            bands = row_bands(H, world)
+            if s1 > s0:
+                p.s0, p.s1 = s0, s1
+                sink.mode, sink.world = nat.SINK_SCATTER_ADD, world
+                for k in range(world):
+                    sink.accum[k] = fab.ptrs[f"accum{buf}"][k]
+                    sink.band_y[k] = bands[k][0]
+                sink.band_y[world] = H
+                sc.render_path_sink(p, sink, stats=self.stats)
+            fab.signal("flags", rank, everyone, e)                         # my sums have been added everywhere
+            fab.wait("flags", 0, world, e, self._timed_out)                # everyone's sums are in my band
+            y0, y1 = bands[rank]
+            nat.check(nat.lib().rt_resolve_clear(self.device, fab.ptrs[f"accum{buf}"][rank], W, H, y0, y1, spp,
+                                                 fab.ptrs[f"image{buf}"][0], 1, None))
+            self.launches = 2
+        else:
+            raise ValueError("mode must be 'tiles' or 'samples'")
+        fab.signal("flags", 16 + rank, [0], e)                             # my part of rank 0's image is written
+        out = None
+        if rank == 0:
+            fab.wait("flags", 16, world, e, self._timed_out)
+            out = self._fused_images[buf]
+            if to_host:
+                self.host_image.copy_(out, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                self.d2h_bytes = self.host_image.numel() * 4
+                out = self.host_image.numpy()
+            fab.signal("flags", 32, everyone, e)                           # this image buffer may be reused at e + 2
+        return out, self.stats
+
+    def fused_timed_out(self):
+        return bool(int(self._timed_out.item())) if getattr(self, "_timed_out", None) is not None else False
+
     def close(self):
+        if getattr(self, "fabric", None) is not None:
+            self.fabric.close()
+            self.fabric = None
         if self.scene is not None:
             self.scene.close()
             self.scene = None
