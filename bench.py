@@ -29,7 +29,7 @@ W, H, SPP, DEPTH, THRESHOLD, FOV = 1920, 1080, 64, 5, 0.9, 60.0
 NCU_DRAM_BYTES_PER_LAUNCH = 73472 + 1939200    # profiles/ncu_path_kernel_r1f.txt (one ncu --set full capture of a bench launch)
 CPU_W, CPU_H, CPU_SPP = 960, 540, 16          # bounded CPU sample: 1/16 of the frame's pixel-samples
 METRIC, UNIT = "Mrays/s (complex scene, 1920x1080, 64 spp)", "Mrays/s"
-WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer), tile-sharded"
+WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer)"
 
 
 def complex_scene():
@@ -158,13 +158,19 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="tiles", choices=["tiles", "samples"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "tiles", "samples"],
+                    help="auto: tiles at N=1 (one band = the frame), sample ranges at N>1 (8100 CTAs per GPU keep the last "
+                         "wave full; 8-row tile stripes leave 1.7 waves per GPU at N=8)")
+    ap.add_argument("--collective", default="fused", choices=["fused", "nccl"],
+                    help="N>1: fused = the kernels' own stores/reductions over NVLink peer memory; nccl = gather/reduce")
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
+    if args.mode == "auto":
+        args.mode = "tiles" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "samples"
 
     import torch
     import torch.distributed as dist
@@ -192,8 +198,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i):
-        return r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode)
+    fused = world > 1 and args.collective == "fused"
+
+    def step(i, **kw):
+        if fused:
+            return r.render_fused(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, **kw)
+        return r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, **kw)
 
     fp32_peak, _ = nat.measure_fp32_peak(local, 5)
     for i in range(args.warmup):
@@ -213,27 +223,31 @@ def main():
         barrier()
         ev[i][0].record()
         # the step, with the dominant kernel bracketed separately for the roofline
-        r._ensure(W, H)
-        rows = row_bands(H, world)[rank] if args.mode == "tiles" else (0, H)
-        smp = sample_ranges(spp, world)[rank] if args.mode == "samples" else (0, spp)
-        r.stats.zero_()
-        p = r.scene.path_params(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, rows=rows, samples=smp)
-        kev[i][0].record()
-        r.scene.render_path(p, r.accum, nat.F32, stats=r.stats)
-        kev[i][1].record()
-        if args.mode == "tiles":
-            r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32, rows=rows)
-            launches += 2
-            if world > 1:
-                from ray_tracer_v1_b200.distributed import gather_row_bands
-                gather_row_bands(r.image, row_bands(H, world))
+        if fused:
+            r.render_fused(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, kernel_events=kev[i])
+            launches += r.launches
         else:
-            from ray_tracer_v1_b200.distributed import reduce_sample_sums
-            reduce_sample_sums(r.accum)
-            launches += 1
-            if rank == 0:
-                r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32)
+            r._ensure(W, H)
+            rows = row_bands(H, world)[rank] if args.mode == "tiles" else (0, H)
+            smp = sample_ranges(spp, world)[rank] if args.mode == "samples" else (0, spp)
+            r.stats.zero_()
+            p = r.scene.path_params(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, rows=rows, samples=smp)
+            kev[i][0].record()
+            r.scene.render_path(p, r.accum, nat.F32, stats=r.stats)
+            kev[i][1].record()
+            if args.mode == "tiles":
+                r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32, rows=rows)
+                launches += 2
+                if world > 1:
+                    from ray_tracer_v1_b200.distributed import gather_row_bands
+                    gather_row_bands(r.image, row_bands(H, world))
+            else:
+                from ray_tracer_v1_b200.distributed import reduce_sample_sums
+                reduce_sample_sums(r.accum)
                 launches += 1
+                if rank == 0:
+                    r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32)
+                    launches += 1
         ev[i][1].record()
         counters += r.stats
     barrier()
@@ -254,13 +268,13 @@ def main():
     e2e_q = torch.zeros(1, dtype=torch.int64, device="cuda")
     for i in range(2):
         r.set_scene(fs)
-        r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=2000 + i, fov=FOV, mode=args.mode, to_host=True)
+        step(2000 + i, to_host=True)
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
         spec_i, fs_i = (spec, fs)
         r.set_scene(fs_i)                                     # H2D: the flattened scene, re-uploaded every frame
-        img, st = r.render(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, to_host=True)   # D2H: image
+        img, st = step(i, to_host=True)                        # D2H: the float32 image into pinned host memory
         e2e_q += st[4:5]
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -282,7 +296,9 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": spp, "max_bounces": DEPTH,
-                       "sharding": args.mode, "l2": "flushed between steps (256 MiB memset, untimed); inputs are a 3 KB scene",
+                       "sharding": args.mode if world == 1 else f"{args.mode}, {args.collective} collective "
+                       + ("(path-kernel epilogue stores/reductions over NVLink peer memory, epoch flags)" if fused else "(NCCL)"),
+                       "l2": "flushed between steps (256 MiB memset, untimed); inputs are a 3 KB scene",
                        "ray_definition": "one nearest-hit query over the scene (SURVEY 8d)"},
             "rays_ref_compatible_per_s": rays_ref / (total_ms * 1e-3) / 1e6,
             "rays_per_pixel_sample": rays_ref / (args.steps * W * H * spp),

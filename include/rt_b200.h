@@ -157,6 +157,9 @@ typedef struct rt_path_params {
     uint64_t seed;
     int32_t accumulate;
     int32_t schedule;       /* 0 = lock-step warps (default), 1 = per-lane path regeneration; same image either way */
+    int32_t ksplit;         /* lanes sharing one pixel's samples: -1 = automatic (keeps >= 64 waves of CTAs in the grid),
+                               0 or 1 = one thread per pixel, 2..32 = that power of two.  Same image either way. */
+    int32_t reserved_;
 } rt_path_params;
 /* accum_dev as above.  stats_dev (optional) uint64[8]: [0] total_rays (trace calls, reference-compatible),
  * [1] total_intersections, [2] light_hits, [3] small_light_hits, [4] nearest-hit queries,

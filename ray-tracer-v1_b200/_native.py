@@ -59,7 +59,7 @@ class PathParams(C.Structure):
     _fields_ = [("cam", C.c_double * 3), ("W", C.c_int32), ("H", C.c_int32), ("fov_deg", C.c_double),
                 ("y0", C.c_int32), ("y1", C.c_int32), ("s0", C.c_int32), ("s1", C.c_int32), ("max_bounces", C.c_int32),
                 ("mirror_threshold", C.c_double), ("seed", C.c_uint64), ("accumulate", C.c_int32),
-                ("schedule", C.c_int32)]
+                ("schedule", C.c_int32), ("ksplit", C.c_int32), ("reserved_", C.c_int32)]
 
 
 RT_MAX_PEERS, IPC_HANDLE_BYTES = 16, 64
@@ -369,7 +369,7 @@ class DeviceScene:
         return p
 
     def path_params(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, rows=None, samples=None,
-                    accumulate=False, schedule=0):
+                    accumulate=False, schedule=0, ksplit=-1):
         p = PathParams()
         p.cam[:] = [float(c) for c in cam]
         p.W, p.H, p.fov_deg = int(W), int(H), float(fov)
@@ -378,6 +378,7 @@ class DeviceScene:
         p.max_bounces, p.mirror_threshold, p.seed = int(max_bounces), float(mirror_threshold), int(seed)
         p.accumulate = int(bool(accumulate))
         p.schedule = int(schedule)
+        p.ksplit = int(ksplit)
         return p
 
     def render_whitted(self, params, accum, precision=F32, hit=None, stats=None, stream=None):

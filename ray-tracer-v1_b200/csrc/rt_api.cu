@@ -507,6 +507,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     pp.int_fold = sc->int_colours && (p->s1 - p->s0) <= 65536;
     pp.regenerate = p->schedule == 1;
     pp.sink = RT_SINK_ACCUM; pp.tile_step = 1; pp.world = 1; pp.spp_total = p->s1 - p->s0;
+    pp.ksplit_log2 = 0;
     if (sink && sink->mode != RT_SINK_ACCUM) {
         if (!pp.int_fold) return fail(RT_ERR_UNSUPPORTED, "fused sinks need integer colours and <= 65536 samples per launch");
         pp.sink = sink->mode;
@@ -527,6 +528,22 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             for (int k = 0; k <= sink->world; ++k) pp.band_y[k] = sink->band_y[k];
             if (pp.band_y[0] != 0 || pp.band_y[sink->world] != p->H) return fail(RT_ERR_INVALID, "owner bands must cover the image");
         } else return fail(RT_ERR_INVALID, "unknown sink mode");
+    }
+    // sample split: grow k while the grid has fewer than ~64 waves of 256-thread CTAs and every lane keeps >= 2 samples
+    if (pp.int_fold && p->ksplit != 0) {
+        static int sm_cache[64] = {0};
+        int sms = sc->device >= 0 && sc->device < 64 ? sm_cache[sc->device] : 0;
+        if (sms == 0) {
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device) != cudaSuccess || sms <= 0) sms = 148;
+            if (sc->device >= 0 && sc->device < 64) sm_cache[sc->device] = sms;
+        }
+        const long long want = 64LL * 4 * sms;
+        const int rows = pp.y1 - pp.y0, step = pp.tile_step > 1 ? pp.tile_step : 1, ns = p->s1 - p->s0;
+        const long long pixels = (long long)pp.W * ((rows + step - 1) / step);
+        int lk = 0;
+        if (p->ksplit > 0) { while ((1 << (lk + 1)) <= p->ksplit && lk < 5) ++lk; }
+        else { while (lk < 5 && (pixels << lk) / 256 < want && (ns >> (lk + 1)) >= 2) ++lk; }
+        pp.ksplit_log2 = lk;
     }
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st));
     return RT_OK;

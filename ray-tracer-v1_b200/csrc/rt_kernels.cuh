@@ -189,10 +189,21 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem + 256 * sizeof(double), S);        // ends with __syncthreads() when staging
     if constexpr (!kShared) __syncthreads();
-    int x, yr;
-    tile_pixel(x, yr);
-    // tile_step > 1: this launch owns every tile_step-th 8-row tile starting at y0 (interleaved stripes)
-    const int y = pp.y0 + yr + (int)blockIdx.y * 8 * (pp.tile_step - 1);
+    // Sample split: k = 2^ksplit_log2 lanes share one pixel, lane `sub` tracing samples s0 + sub, s0 + sub + k, ...
+    // (summed with shuffles at the end).  A warp then covers 32/k pixels -- pw x ph = 8x4, 8x2, 4x2, 2x2, 2x1, 1x1 --
+    // and a CTA (4 x 2 warps) 256/k pixels: finer work units for small frames, row bands and sample ranges, so the
+    // grid keeps tens of waves and the drain at the end of the launch stays short.
+    const int lk = pp.ksplit_log2, kk = 1 << lk;
+    const int pw_sh = lk == 0 ? 3 : lk == 1 ? 3 : lk == 2 ? 2 : lk <= 4 ? 1 : 0;
+    const int ph_sh = (5 - lk) - pw_sh;
+    const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    const int sub = lane_ & (kk - 1), pl = lane_ >> lk;
+    const int x = ((((int)blockIdx.x << 2) + (w_ & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
+    // CTA rows: cth = 2 << ph_sh of them; tile_step > 1: this launch owns every tile_step-th 8-row stripe from y0
+    const int cth_sh = ph_sh + 1, cps_sh = 3 - cth_sh;                 // CTA rows per stripe = 1 << cps_sh
+    const int by = (int)blockIdx.y;
+    const int y = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
+                  ((w_ >> 2) << ph_sh) + (pl >> pw_sh);
     const bool has_pixel = x < pp.W && y < pp.y1;
     unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
     const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
@@ -204,11 +215,12 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     const int ns = pp.s1 - pp.s0;
 
     if (pp.max_bounces <= 0) {                        // degenerate: every call returns (2,2,5) at the depth check
-        n_rays = has_pixel ? (unsigned)ns : 0u;
-        a0 = 2 * ns; a1 = 2 * ns; a2 = 5 * ns;
+        const int mine = has_pixel ? (ns - sub + kk - 1) >> lk : 0;      // samples of this lane
+        n_rays = (unsigned)mine;
+        a0 = 2 * mine; a1 = 2 * mine; a2 = 5 * mine;
     } else {
-        int s = pp.s0, depth = 0;
-        bool alive = has_pixel && ns > 0;             // lane has a path in flight
+        int s = pp.s0 + sub, depth = 0;
+        bool alive = has_pixel && s < pp.s1;          // lane has a path in flight
         bool more = alive;                            // lane still has samples to do (regen schedule)
         V3<T> O = cam, D = mk<T>(T(0), T(0), T(-1));
         auto start_sample = [&](int smp) {
@@ -273,19 +285,26 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     a0 += c[0]; a1 += c[1]; a2 += c[2];
                 }
                 if constexpr (kRegen) {
-                    if (++s < pp.s1) { alive = true; start_sample(s); } else more = false;
+                    if ((s += kk) < pp.s1) { alive = true; start_sample(s); } else more = false;
                 }
             }
             if constexpr (kRegen) {
                 if (!more) break;
             } else {
                 if (__any_sync(0xffffffffu, alive)) continue;      // wait for the warp's longest path
-                if (++s >= pp.s1) break;                           // s is warp-uniform in this schedule
-                if (has_pixel) { alive = true; start_sample(s); }
+                s += kk;
+                if (s - sub >= pp.s1) break;                       // s - sub is warp-uniform in this schedule
+                if (has_pixel && s < pp.s1) { alive = true; start_sample(s); }
             }
         }
     }
-    if (has_pixel && ns > 0) {
+    if constexpr (kIntFold) {                        // the k lanes of a pixel are adjacent: butterfly sum
+        for (int o = 1; o < kk; o <<= 1) {
+            a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+            a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+        }
+    }
+    if (has_pixel && ns > 0 && sub == 0) {
         const size_t o = (size_t)y * pp.W + x;
         bool to_accum = true;
         if constexpr (!M<T>::exact && kIntFold) {
@@ -654,7 +673,12 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     const int rows = pp.y1 - pp.y0;
     if (rows <= 0 || pp.W <= 0) return cudaSuccess;
     const int tiles = (rows + 7) / 8, step = pp.tile_step > 1 ? pp.tile_step : 1;
-    dim3 grid((pp.W + 31) / 32, (tiles + step - 1) / step), block(256);
+    const int lk = pp.ksplit_log2;
+    const int pw_sh = lk == 0 ? 3 : lk == 1 ? 3 : lk == 2 ? 2 : lk <= 4 ? 1 : 0, ph_sh = (5 - lk) - pw_sh;
+    const int ctw = 4 << pw_sh, cth = 2 << ph_sh;
+    // stripes of 8 rows (8 / cth CTA rows each); without interleaving the last stripe may be cut short
+    const unsigned gy = step > 1 ? (unsigned)((tiles + step - 1) / step) * (8 / cth) : (unsigned)((rows + cth - 1) / cth);
+    dim3 grid((pp.W + ctw - 1) / ctw, gy), block(256);
     using v4 = typename M<T>::v4;
     const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold
     const int mode = mode_for(sc, extra);

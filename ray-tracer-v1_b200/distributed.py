@@ -197,7 +197,10 @@ class ShardedPathRenderer:
         else:
             self.scene.update(fs)
         n, nG, nP, nL = fs.radius.shape[0], fs.g_strength.shape[0], fs.p_strength.shape[0], fs.l_index.shape[0]
-        self.h2d_bytes = (16 + 32) * (3 * n + 2 * (nG + nP + nL)) + 2 * 4 * (n + nG + 2 * nP + nL) + n
+        n_pad, l_pairs = (n + 7) & ~7, (nL + 1) // 2
+        # FP32 + FP64 vec4 arrays (sph, sphere pairs, mat, col, lights, light pairs), int arrays, small-light mask
+        self.h2d_bytes = ((16 + 32) * (2 * n_pad + 2 * n + 2 * (nG + nP + nL) + 3 * l_pairs)
+                          + 2 * 4 * (n + nG + 2 * nP + nL) + n)
         if lbvh or (lbvh is None and self.scene.n > 256):
             self.scene.build_lbvh()
 
@@ -271,7 +274,8 @@ class ShardedPathRenderer:
             self._ensure(W, H)
         self._fab_key = (W, H)
 
-    def render_fused(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, mode="tiles", to_host=False):
+    def render_fused(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, mode="tiles", to_host=False,
+                     kernel_events=None):
         """The same frame as ``render`` with the collective fused into the kernels: no NCCL call on the data path.
 
         tiles    every rank renders interleaved 8-row stripes (tile_stripes) and its path kernel stores the resolved
@@ -280,7 +284,9 @@ class ShardedPathRenderer:
                  into the accumulators of the rank that owns the pixel's row band (one 16-byte system-scope reduction
                  per pixel: a reduce-scatter), then every rank resolves its band into rank 0's image.
         Ordering across ranks: epoch flags in peer memory (signal after the writes, wait before the reads), frames
-        double-buffered so rank 0 can still be reading frame f while frame f+1 is written."""
+        double-buffered so rank 0 can still be reading frame f while frame f+1 is written: a returned CUDA image stays
+        valid until the frame after the next one is rendered.  kernel_events = (start, end) CUDA events recorded
+        around the path kernel alone (bench.py's roofline)."""
         nat, sc, torch = self.nat, self.scene, self.torch
         self._ensure_fabric(W, H)
         fab, rank, world = self.fabric, self.rank, self.world
@@ -294,8 +300,12 @@ class ShardedPathRenderer:
         if mode == "tiles":
             sink.mode, sink.tile_first, sink.tile_step = nat.SINK_IMAGE, rank, world
             sink.image = fab.ptrs[f"image{buf}"][0]
+            if kernel_events:
+                kernel_events[0].record()
             sc.render_path_sink(p, sink, stats=self.stats)
-            self.launches = 1
+            if kernel_events:
+                kernel_events[1].record()
+            self.launches = 3 + (2 if rank == 0 else 0)
         elif mode == "samples":
             s0, s1 = sample_ranges(spp, world)[rank]
             bands = row_bands(H, world)
@@ -306,13 +316,17 @@ class ShardedPathRenderer:
                     sink.accum[k] = fab.ptrs[f"accum{buf}"][k]
                     sink.band_y[k] = bands[k][0]
                 sink.band_y[world] = H
+                if kernel_events:
+                    kernel_events[0].record()
                 sc.render_path_sink(p, sink, stats=self.stats)
+                if kernel_events:
+                    kernel_events[1].record()
             fab.signal("flags", rank, everyone, e)                         # my sums have been added everywhere
             fab.wait("flags", 0, world, e, self._timed_out)                # everyone's sums are in my band
             y0, y1 = bands[rank]
             nat.check(nat.lib().rt_resolve_clear(self.device, fab.ptrs[f"accum{buf}"][rank], W, H, y0, y1, spp,
                                                  fab.ptrs[f"image{buf}"][0], 1, None))
-            self.launches = 2
+            self.launches = 6 + (2 if rank == 0 else 0)     # wait, path, signal, wait, resolve, signal (+ wait, signal)
         else:
             raise ValueError("mode must be 'tiles' or 'samples'")
         fab.signal("flags", 16 + rank, [0], e)                             # my part of rank 0's image is written

@@ -35,10 +35,11 @@ def test_header_symbols_exported(native):
 def test_struct_layouts_match_header(native):
     """ctypes mirrors of the parameter blocks have the C sizes (LP64)."""
     import ctypes as C
-    assert C.sizeof(native.PathParams) == 88
+    assert C.sizeof(native.PathParams) == 96
     assert C.sizeof(native.WhittedParams) == 120
     assert C.sizeof(native.EnvDesc) == 88
     assert C.sizeof(native.SceneDesc) == 216
+    assert C.sizeof(native.PathSink) == 4 * 4 + 8 + 16 * 8 + 17 * 4 + 4      # 17 ints, padded to 8
 
 
 def test_no_cpu_fallback(native):

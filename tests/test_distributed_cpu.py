@@ -84,3 +84,21 @@ def test_partitions():
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
     assert row_bands(1080, 8)[3] == (405, 540)
+
+
+def test_tile_stripes_cover_the_frame_once():
+    """Fused tile mode: the interleaved 8-row stripes of all ranks partition the rows; the owner-band lookup of the
+    scatter-add sink (rt_kernels.cuh: start from y*world//H, then walk) lands in the band that holds the row."""
+    from ray_tracer_v1_b200.distributed import tile_stripes, row_bands
+    for H, world in ((1080, 8), (1080, 3), (27, 2), (7, 4), (600, 16)):
+        rows = sorted(y for r in range(world) for a, b in tile_stripes(H, world, r) for y in range(a, b))
+        assert rows == list(range(H))
+        bands = row_bands(H, world)
+        bound = [b[0] for b in bands] + [H]
+        for y in range(H):
+            k = min(world - 1, y * world // H)
+            while y >= bound[k + 1]:
+                k += 1
+            while y < bound[k]:
+                k -= 1
+            assert bands[k][0] <= y < bands[k][1]

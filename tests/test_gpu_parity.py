@@ -273,3 +273,95 @@ def test_c3_full_size_properties(nat):
     im = img.download()
     assert np.array_equal(im, np.minimum(1.0, np.floor(a[..., :3].astype(np.float64) / spp) / 255.0).astype(np.float32))
     sc.close()
+
+
+# ------------------------------------------------------------------ fused multi-GPU sinks (one rank: peers = self)
+def test_fused_sinks_equal_accumulate_then_resolve(nat):
+    """rt_render_path_sink: the image sink (interleaved stripes rendered by separate launches) and the scatter-add
+    sink (two sample ranges added into IPC-exported accumulators, then rt_resolve_clear) both reproduce the frame of
+    rt_render_path + rt_resolve bit for bit; epoch flags order a signal before a wait."""
+    import torch
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.distributed import PeerFabric, row_bands
+    spec = scenes.build_complex()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp = 200, 117, 6
+    p = sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=4)
+    ref, _, st_ref = sc.render_path_host(p, nat.F32)
+    fab = PeerFabric(0)
+    img = fab.alloc("image", H * W * 12)[0]
+    acc = fab.alloc("accum", H * W * 16)[0]
+    fab.alloc("flags", 256)
+    stats = torch.zeros(8, dtype=torch.int64, device="cuda")
+    out = np.zeros((H, W, 3), np.float32)
+    # tiles: three "ranks" render stripes 0,3,6.. / 1,4,7.. / 2,5,8.. into the same image
+    for r in range(3):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step, sink.image = nat.SINK_IMAGE, r, 3, img
+        sc.render_path_sink(p, sink, stats=stats)
+    nat.check(nat.lib().rt_memcpy_d2h(0, out.ctypes.data, img, out.nbytes, None))
+    nat.check(nat.lib().rt_stream_sync(0, None))
+    assert np.array_equal(out, ref)
+    assert np.array_equal(stats.cpu().numpy()[:5].astype(np.uint64), st_ref[:5])
+    # samples: two "ranks" add their sample ranges; owner bands of a world of 2 both live in this process
+    bands = row_bands(H, 2)
+    for s0, s1 in ((0, 4), (4, 6)):
+        q = sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=4, samples=(s0, s1))
+        sink = nat.PathSink()
+        sink.mode, sink.world = nat.SINK_SCATTER_ADD, 2
+        sink.accum[0] = sink.accum[1] = acc
+        sink.band_y[0], sink.band_y[1], sink.band_y[2] = 0, bands[0][1], H
+        sc.render_path_sink(q, sink)
+    fab.signal("flags", 3, [0], 7)
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    fab.wait("flags", 3, 1, 7, flag, timeout_ms=500)
+    nat.check(nat.lib().rt_memset_dev(0, img, 0, H * W * 12, None))
+    nat.check(nat.lib().rt_resolve_clear(0, acc, W, H, 0, H, spp, img, 1, None))
+    nat.check(nat.lib().rt_memcpy_d2h(0, out.ctypes.data, img, out.nbytes, None))
+    left = np.ones((H, W, 4), np.float32)
+    nat.check(nat.lib().rt_memcpy_d2h(0, left.ctypes.data, acc, left.nbytes, None))
+    nat.check(nat.lib().rt_stream_sync(0, None))
+    assert np.array_equal(out, ref) and not left.any() and int(flag.item()) == 0
+    # a wait nobody signals gives up and says so
+    fab.wait("flags", 9, 1, 1, flag, timeout_ms=20)
+    assert int(flag.item()) == 1
+    fab.close()
+    sc.close()
+
+
+def test_sample_split_gives_the_same_frame(nat):
+    """ksplit: 1..32 lanes sharing a pixel's samples (butterfly-summed) render the frame of one thread per pixel, for
+    ragged sizes, row bands, sample ranges that do not divide by k, both schedules and the image sink."""
+    import torch
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    spec = scenes.build_chandelier()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp = 101, 45, 11
+    base = sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, ksplit=0)
+    _, ref, st_ref = sc.render_path_host(base, nat.F32)
+    for k in (-1, 2, 4, 8, 16, 32):
+        for schedule in (0, 1):
+            p = sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, ksplit=k, schedule=schedule)
+            _, out, st = sc.render_path_host(p, nat.F32)
+            assert np.array_equal(out, ref), (k, schedule)
+            assert np.array_equal(st[:6], st_ref[:6]), (k, schedule)
+    # row band + sample range, accumulated in two launches with different k
+    acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    for (s0, s1), k in (((0, 7), 4), ((7, 11), 8)):
+        p = sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, rows=(9, 30), samples=(s0, s1), accumulate=s0 > 0, ksplit=k)
+        sc.render_path(p, acc, nat.F32)
+    got = acc.cpu().numpy()
+    assert np.array_equal(got[9:30], ref[9:30]) and not got[:9].any() and not got[30:].any()
+    # image sink, interleaved stripes, k = 8: CTA rows of 4 inside 8-row stripes
+    img = torch.zeros((H, W, 3), dtype=torch.float32, device="cuda")
+    for r in range(2):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step, sink.image = nat.SINK_IMAGE, r, 2, img.data_ptr()
+        sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, ksplit=8), sink)
+    want = np.minimum(1.0, np.floor(ref[..., :3].astype(np.float64) / spp) / 255.0).astype(np.float32)
+    assert np.array_equal(img.cpu().numpy(), want)
+    sc.close()
