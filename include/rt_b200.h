@@ -172,6 +172,32 @@ int rt_render_path(rt_scene *scene, int precision, const rt_path_params *p, void
 int rt_resolve(int device, int precision, const void *accum_dev, int32_t W, int32_t H, int32_t y0, int32_t y1,
                int32_t spp, float *image_dev, void *stream);
 
+/* ---- "Algorithm C" frame: SimplifiedFBRenderer.render_original_style / trace_ray_simple /
+ *      calculate_lighting_exact_original in traditional mode (fb_usage_prob = 0): FB/output6.py:197-306, :434-654.
+ *      Per-bounce lighting (global 0.3 cos + shadowed sun, int() truncations) accumulated with min(255, .), mirrors
+ *      for a truthy `reflective`, glass 50/50 reflect / straight, cosine-weighted diffuse bounces, stop on the sun id. */
+typedef struct rt_simple_params {
+    double cam[3];           /* Vector(0, 0, 1), output6.py:605 */
+    int32_t W, H;            /* camera grid; ignored when rays_dev != NULL */
+    double fov_rad;          /* np.pi / 3, output6.py:622 */
+    double sun_pos[3];       /* self.sun_position */
+    double sun_col[3];       /* self.sun_color */
+    int32_t sun_id;          /* 7 */
+    int32_t max_bounces;     /* self.max_bounces = 5 */
+    uint64_t seed;           /* Philox key; slot bounce+1 of (pixel, sample 0): glass draws word 0, diffuse words 0,1 */
+    int32_t m;               /* number of explicit rays when rays_dev != NULL */
+    int32_t reserved_;
+    const double *rays_dev;  /* optional [m,6] origin + raw direction (scalar trace_ray_simple = a batch of one) */
+} rt_simple_params;
+/* rgb_dev [n,4] int32 = accumulated r, g, b, bounce_count (n = W*H or m); image_dev (optional) [n,3] float32 =
+ * min(1, c/255) (output6.py:628-632).  stats_dev (optional) uint64[8]: [0] total_rays, [1] sun_hits, [4] queries
+ * (nearest-hit + shadow tests). */
+int rt_render_simple(rt_scene *scene, int precision, const rt_simple_params *p, int32_t *rgb_dev, float *image_dev,
+                     uint64_t *stats_dev, void *stream);
+/* host buffers; rays_host replaces p->rays_dev when not NULL.  Synchronous. */
+int rt_render_simple_host(rt_scene *scene, int precision, const rt_simple_params *p, const double *rays_host,
+                          int32_t *rgb_host, float *image_host, uint64_t *stats_host);
+
 /* ---- fused multi-GPU sinks for Algorithm B frames ---------------------------------------------
  * One process per GPU; a rank's path kernel stores its result where it is needed -- its own accumulators, the
  * final image on the collecting rank, or the accumulators of the rank that owns the pixel -- through NVLink peer

@@ -364,12 +364,64 @@ def gen_env(ref):
               np.bincount(reason.ravel(), minlength=6))
 
 
+# ----------------------------------------------------------------- output6 ("Algorithm C")
+def gen_simple(ref):
+    """FB/output6.py SimplifiedFBRenderer.render_original_style in traditional mode (fb_usage_prob = 0, no model).
+    ``fb_ray_tracing`` is absent from the reference, so ``__init__`` would raise: the instance is made with
+    ``object.__new__`` and given exactly the attributes ``__init__`` sets (output6.py:96-126); every method that runs
+    (render_original_style, trace_ray_simple, calculate_lighting_exact_original) is the reference's own."""
+    mod = _load("ref_output6", REF / "FB" / "output6.py")
+    spec = scenes.build_balls_in_space(ref.ns, as_rendered=False)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref_scene = mod.create_your_custom_scene()
+    assert_same_scene(spec.spheres, ref_scene, "output6 custom scene")
+    ctl = types.SimpleNamespace(pixel=-1, bounce=0, word=0)
+
+    class Hooked(mod.SimplifiedFBRenderer):
+        def trace_ray_simple(self, ray):
+            ctl.pixel += 1
+            ctl.bounce = -1
+            out = super().trace_ray_simple(ray)
+            colours.append([out.r, out.g, out.b])
+            return out
+
+        def calculate_lighting_exact_original(self, intersection):     # once per bounce, before any draw
+            ctl.bounce += 1
+            ctl.word = 0
+            return super().calculate_lighting_exact_original(intersection)
+
+    def fake_random():
+        w = ctl.word
+        ctl.word += 1
+        assert w < 2
+        return orc.rng_pair(seed, ctl.pixel, 0, ctl.bounce + 1)[w]
+
+    for tag, W, H, seed, depth in (("a", 64, 48, 21, 5), ("b", 40, 30, 22, 8)):
+        colours = []
+        ctl.pixel = -1
+        r = object.__new__(Hooked)
+        r.scene = ref_scene
+        r.sun_position, r.sun_radius, r.sun_color = ref.ns.Vector(-0.6, 0.2, 6), 0.1, ref.ns.Colour(255, 255, 204)
+        r.agent, r.fb_model_loaded = None, False
+        r.max_bounces, r.samples_per_pixel, r.fb_usage_prob = depth, 100, 0.0
+        r.stats = {}
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), \
+                mock.patch.object(np.random, "random", fake_random), mock.patch.object(mod, "tqdm", lambda it, **k: it), \
+                tempfile.TemporaryDirectory() as tmp:
+            img, _ = r.render_original_style(W, H, os.path.join(tmp, "x.png"))
+        rgb = np.array(colours, np.float64).reshape(H, W, 3)
+        stats = np.array([r.stats["total_rays"], r.stats["sun_hits"]], np.int64)
+        np.savez_compressed(OUT / f"simple_balls_{tag}_{W}x{H}.npz", image=img, rgb=rgb.astype(np.float32), stats=stats,
+                            W=W, H=H, seed=seed, max_bounces=depth, **flat_dict(rtb.flatten_scene(spec.spheres)))
+        print(f"simple_balls_{tag}", stats, "mean", rgb.mean(axis=(0, 1)))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     ref = load_reference()
-    which = sys.argv[1:] or ["kat", "whitted", "path", "env"]
+    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple"]
     for w in which:
-        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env}[w](ref)
+        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env, "simple": gen_simple}[w](ref)
 
 
 if __name__ == "__main__":

@@ -43,6 +43,11 @@ class _EnvCfg(C.Structure):
                 ("cam", C.c_double * 3), ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("sun_id", C.c_int32)]
 
 
+class _SimpleCfg(C.Structure):
+    _fields_ = [("cam", C.c_double * 3), ("fov", C.c_double), ("sun_pos", C.c_double * 3), ("sun_col", C.c_double * 3),
+                ("sun_id", C.c_int32), ("max_bounces", C.c_int32)]
+
+
 def build(force=False):
     """Compile oracle/rt_oracle.c with the committed Makefile (gcc, a second or two)."""
     src = os.path.join(_HERE, "rt_oracle.c")
@@ -73,6 +78,8 @@ def lib():
         _lib.orc_env_reset.argtypes = [C.POINTER(_Scene), C.POINTER(_EnvCfg), C.c_int, c_ip, C.c_void_p, c_fp]
         _lib.orc_env_step.argtypes = [C.POINTER(_Scene), C.POINTER(_EnvCfg), C.c_int, c_fp, C.c_void_p, c_fp, c_dp,
                                       c_u8p, c_u8p, c_ip]
+        _lib.orc_render_simple.argtypes = [C.POINTER(_Scene), C.POINTER(_SimpleCfg), C.c_int, C.c_int, C.c_uint64, c_dp, c_dp,
+                                           c_u64p, C.c_int]
         _lib.orc_sizeof_env.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -213,6 +220,27 @@ def render_path(fs, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=6
     stats = {"total_rays": int(st[0]), "total_intersections": int(st[1]), "light_hits": int(st[2]),
              "small_light_hits": int(st[3]), "queries": int(st[4])}
     return out, stats
+
+
+def render_simple(fs, W, H, cam=(0, 0, 1), fov=np.pi / 3, sun_pos=(-0.6, 0.2, 6), sun_col=(255, 255, 204), sun_id=7,
+                  max_bounces=5, seed=0, rays=None, nthreads=0):
+    """FB/output6.py ``render_original_style`` / ``trace_ray_simple`` (traditional mode).  Returns (rgb [H,W,3] f64
+    integer-valued colours, stats dict); with ``rays`` [m,6] the m explicit rays are traced instead (W = m, H = 1)."""
+    sc = _scene(fs)
+    cfg = _SimpleCfg()
+    cfg.cam[:] = [float(x) for x in cam]
+    cfg.fov = float(fov)
+    cfg.sun_pos[:] = [float(x) for x in sun_pos]
+    cfg.sun_col[:] = [float(x) for x in sun_col]
+    cfg.sun_id, cfg.max_bounces = int(sun_id), int(max_bounces)
+    rp = None
+    if rays is not None:
+        rays = _d(rays).reshape(-1, 6)
+        W, H, rp = rays.shape[0], 1, _p(rays, c_dp)
+    out = np.zeros((H, W, 3))
+    st = (C.c_uint64 * 2)()
+    lib().orc_render_simple(sc.ref, C.byref(cfg), int(W), int(H), int(seed), rp, _p(out, c_dp), st, int(nthreads))
+    return out, {"total_rays": int(st[0]), "sun_hits": int(st[1])}
 
 
 def resolve(sum_rgb, spp):

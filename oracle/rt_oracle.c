@@ -462,6 +462,124 @@ ORC_API void orc_render_path(const orc_scene *s, const double *cam, int W, int H
     if (stats5) { stats5[0] = R; stats5[1] = I; stats5[2] = Lh; stats5[3] = Sh; stats5[4] = Q; }
 }
 
+/* ------------------- "Algorithm C": FB/output6.py SimplifiedFBRenderer (fb_usage_prob = 0) */
+typedef struct {
+    double cam[3];                 /* render_original_style: Vector(0, 0, 1), output6.py:605 */
+    double fov;                    /* radians: np.pi / 3, output6.py:622 */
+    double sun_pos[3];             /* self.sun_position, output6.py:99 */
+    double sun_col[3];             /* self.sun_color, output6.py:101 */
+    int32_t sun_id;                /* 7, output6.py:204,478 */
+    int32_t max_bounces;           /* 5, output6.py:113 */
+} orc_simple_cfg;
+
+/* SimplifiedFBRenderer.calculate_lighting_exact_original: FB/output6.py:197-306 */
+static void simple_lighting(const orc_scene *s, const orc_simple_cfg *c, const isect *h, int64_t out[3], uint64_t *sun_hits) {
+    if (s->ids[h->idx] == c->sun_id) {                                        /* :204-206 */
+        (*sun_hits)++;
+        for (int k = 0; k < 3; ++k) out[k] = (int64_t)c->sun_col[k];
+        return;
+    }
+    v3 sun = V(c->sun_pos[0], c->sun_pos[1], c->sun_pos[2]);
+    v3 to_sun = vnorm(vsub(sun, h->p));                                       /* :244 */
+    v3 gdir = vnorm(V(3, 1, -0.75));                                          /* :247 */
+    double gcos = vdot(h->n, gdir); if (!(gcos > 0)) gcos = 0;                /* :248 max(0, .) */
+    const double gl[3] = {20, 20, 255};
+    int64_t g[3], su[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) g[k] = (int64_t)(gl[k] * gcos * 0.3);         /* :250-254 */
+    v3 so = vadd(h->p, vscale(h->n, 0.001)), sd = vnorm(to_sun);              /* :258-261, Ray() normalises */
+    double sun_distance = vdist(h->p, sun);                                   /* :264 */
+    int visible = 1;
+    for (int i = 0; i < s->n; ++i) {                                          /* :266-275 */
+        if (i == h->idx || s->ids[i] == c->sun_id) continue;
+        isect it = sphere_discriminant(so, sd, ld3(s->centre, i), s->radius[i], 0);
+        if (it.hit && vdist(it.p, h->p) < sun_distance) { visible = 0; break; }
+    }
+    if (visible) {                                                            /* :278-291 */
+        double distance = vdist(h->p, sun);
+        double att = distance > 0 ? 1.0 / (distance * distance) : 1.0;
+        att = att * 100 < 1.0 ? att * 100 : 1.0;
+        double ca = vdot(h->n, to_sun); if (!(ca > 0)) ca = 0;
+        for (int k = 0; k < 3; ++k) su[k] = (int64_t)(c->sun_col[k] * ca * att * 0.9);
+    }
+    const double *col = s->colour + 3 * h->idx;
+    for (int k = 0; k < 3; ++k) {                                             /* :293-304 */
+        int64_t comb = g[k] + su[k]; if (comb > 255) comb = 255;
+        out[k] = (int64_t)(col[k] * ((double)comb / 255.0));
+    }
+}
+
+/* SimplifiedFBRenderer.trace_ray_simple: FB/output6.py:434-577.  Philox slot bounce+1: glass draws word 0,
+   diffuse draws words 0,1 (the reference draws from np.random.random in that order). */
+static void trace_simple(const orc_scene *s, const orc_simple_cfg *c, v3 O, v3 D, uint64_t seed, uint32_t pixel,
+                         int64_t acc[3], uint64_t *rays, uint64_t *sun_hits) {
+    acc[0] = acc[1] = acc[2] = 0;
+    int bounce = 0;
+    while (bounce < c->max_bounces) {
+        (*rays)++;
+        isect best; memset(&best, 0, sizeof best); best.idx = -1; double nd = INFINITY;
+        for (int i = 0; i < s->n; ++i) {                                      /* :451-457 */
+            isect it = sphere_discriminant(O, D, ld3(s->centre, i), s->radius[i], 0);
+            if (it.hit) { double dist = vdist(it.p, O); if (dist < nd) { nd = dist; best = it; best.idx = i; } }
+        }
+        if (!best.hit) { if (bounce == 0) { acc[0] = 2; acc[1] = 2; acc[2] = 5; } break; }   /* :459-463 */
+        int64_t li[3];
+        simple_lighting(s, c, &best, li, sun_hits);
+        for (int k = 0; k < 3; ++k) { acc[k] += li[k]; if (acc[k] > 255) acc[k] = 255; }     /* :472-476 */
+        if (s->ids[best.idx] == c->sun_id) break;                             /* :479-480 */
+        const double *m = s->material + 4 * best.idx;
+        v3 nd_;
+        if (m[0] != 0) nd_ = vreflect(D, best.n);                             /* truthy reflective, :485-487 */
+        else if (m[1] != 0) {                                                 /* truthy transparent, :489-494 */
+            double u0, u1; rng_pair(seed, pixel, 0, (uint32_t)bounce + 1, &u0, &u1);
+            nd_ = u0 < 0.5 ? vreflect(D, best.n) : D;
+        } else {                                                              /* :540-564 */
+            double r1, r2; rng_pair(seed, pixel, 0, (uint32_t)bounce + 1, &r1, &r2);
+            double theta = acos(sqrt(r1)), phi = 2 * M_PI * r2;
+            v3 tg = fabs(best.n.z) > 0.9 ? V(1, 0, 0) : vcross(V(0, 0, 1), best.n);
+            tg = vnorm(tg);
+            v3 bt = vnorm(vcross(best.n, tg));
+            v3 ld = V(sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta));
+            nd_ = vnorm(V(ld.x * tg.x + ld.y * bt.x + ld.z * best.n.x, ld.x * tg.y + ld.y * bt.y + ld.z * best.n.y,
+                          ld.x * tg.z + ld.y * bt.z + ld.z * best.n.z));
+        }
+        O = vadd(best.p, vscale(best.n, 0.001));                              /* :567-570 */
+        D = vnorm(nd_);
+        bounce++;
+    }
+}
+
+/* render_original_style: FB/output6.py:579-635.  rgb_out [H,W,3] integer-valued colours (image = min(1, c/255));
+   rays != NULL: m explicit rays [m,6] (origin + raw direction) instead of the camera grid, W = m, H = 1.
+   stats2 = total_rays, sun_hits. */
+ORC_API void orc_render_simple(const orc_scene *s, const orc_simple_cfg *c, int W, int H, uint64_t seed,
+                               const double *rays, double *rgb_out, uint64_t *stats2, int nthreads) {
+    uint64_t R = 0, S = 0;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : R, S)
+#endif
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            v3 O, d;
+            size_t i = (size_t)y * W + x;
+            if (rays) { O = V(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]); d = V(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]); }
+            else {
+                double u = ((double)x / W - 0.5) * 2.0, v = ((double)y / H - 0.5) * -2.0;   /* :612-613 */
+                double aspect = (double)W / (double)H;
+                u *= aspect;                                                                 /* :616-617 */
+                double t = tan(c->fov / 2);
+                d = vnorm(V(u * t, v * t, -1));                                              /* :621 */
+                O = V(c->cam[0], c->cam[1], c->cam[2]);
+            }
+            int64_t acc[3];
+            uint64_t r = 0, sh = 0;
+            trace_simple(s, c, O, vnorm(d), seed, (uint32_t)i, acc, &r, &sh);
+            R += r; S += sh;
+            for (int k = 0; k < 3; ++k) rgb_out[3 * i + k] = (double)acc[k];
+        }
+    if (stats2) { stats2[0] = R; stats2[1] = S; }
+}
+
 /* -------------------------------------------------- RayTracerEnv (batched) */
 /* One record per env; mirrors the attributes of RayTracerEnv
    (RL/ray_tracer_env.py:79-86).                                              */

@@ -62,6 +62,12 @@ class PathParams(C.Structure):
                 ("schedule", C.c_int32), ("ksplit", C.c_int32), ("reserved_", C.c_int32)]
 
 
+class SimpleParams(C.Structure):
+    _fields_ = [("cam", C.c_double * 3), ("W", C.c_int32), ("H", C.c_int32), ("fov_rad", C.c_double),
+                ("sun_pos", C.c_double * 3), ("sun_col", C.c_double * 3), ("sun_id", C.c_int32), ("max_bounces", C.c_int32),
+                ("seed", C.c_uint64), ("m", C.c_int32), ("reserved_", C.c_int32), ("rays_dev", C.c_void_p)]
+
+
 RT_MAX_PEERS, IPC_HANDLE_BYTES = 16, 64
 SINK_ACCUM, SINK_IMAGE, SINK_SCATTER_ADD = 0, 1, 2
 
@@ -104,6 +110,8 @@ SIGNATURES = {
     "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
     "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "rt_render_simple": (C.c_int, [vp, C.c_int, C.POINTER(SimpleParams), vp, vp, vp, vp]),
+    "rt_render_simple_host": (C.c_int, [vp, C.c_int, C.POINTER(SimpleParams), vp, vp, vp, vp]),
     "rt_render_path_sink": (C.c_int, [vp, C.POINTER(PathParams), C.POINTER(PathSink), vp, vp]),
     "rt_resolve_clear": (C.c_int, [C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp]),
     "rt_peer_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(vp), C.c_char_p]),
@@ -419,6 +427,32 @@ class DeviceScene:
         check(lib().rt_render_path_host(self.handle, precision, C.byref(params), image.ctypes.data,
                                         None if accum is None else accum.ctypes.data, stats.ctypes.data))
         return image, accum, stats
+
+    def simple_params(self, W, H, cam=(0.0, 0.0, 1.0), fov=np.pi / 3, sun_pos=(-0.6, 0.2, 6.0), sun_col=(255, 255, 204),
+                      sun_id=7, max_bounces=5, seed=0):
+        p = SimpleParams()
+        p.cam[:] = [float(c) for c in cam]
+        p.W, p.H, p.fov_rad = int(W), int(H), float(fov)
+        p.sun_pos[:] = [float(c) for c in sun_pos]
+        p.sun_col[:] = [float(c) for c in sun_col]
+        p.sun_id, p.max_bounces, p.seed = int(sun_id), int(max_bounces), int(seed)
+        return p
+
+    def render_simple_host(self, params, precision=F32, rays=None, want_image=True):
+        """FB/output6.py ``render_original_style`` (or ``trace_ray_simple`` on explicit rays [m,6]) ->
+        (image [H,W,3] f32 | None, rgb [H,W,4] int32 = r, g, b, bounce_count, stats u64[8])."""
+        if rays is not None:
+            rays = _d(rays).reshape(-1, 6)
+            params.m = int(rays.shape[0])
+            shape = (1, params.m)
+        else:
+            shape = (params.H, params.W)
+        rgb = np.zeros(shape + (4,), np.int32)
+        image = np.zeros(shape + (3,), np.float32) if want_image else None
+        stats = np.zeros(8, np.uint64)
+        check(lib().rt_render_simple_host(self.handle, precision, C.byref(params), None if rays is None else rays.ctypes.data,
+                                          rgb.ctypes.data, None if image is None else image.ctypes.data, stats.ctypes.data))
+        return image, rgb, stats
 
     # ---- batched primitives ----------------------------------------------------------------------
     def trace_rays(self, rays, suppress=None, bounces0=None, through0=None, max_bounces=1, shadow_max_bounces=0,

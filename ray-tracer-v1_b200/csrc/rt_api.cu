@@ -716,6 +716,62 @@ RT_EXPORT int rt_render_path_host(rt_scene *scene, int precision, const rt_path_
     return render_host_common(scene, precision, false, p, image_host, accum_host, nullptr, stats_host);
 }
 
+// ------------------------------------------------------------------ "Algorithm C" frame (FB/output6.py)
+template <typename T>
+static int render_simple_t(const SceneDev<T> &view, const rt_simple_params *p, int32_t *rgb, float *image, uint64_t *stats,
+                           cudaStream_t st) {
+    SimpleDev<T> sp;
+    std::memset(&sp, 0, sizeof sp);
+    for (int k = 0; k < 3; ++k) { sp.cam[k] = (T)p->cam[k]; sp.sun_pos[k] = (T)p->sun_pos[k]; sp.sun_col[k] = (T)p->sun_col[k]; }
+    sp.tan_half = (T)std::tan(p->fov_rad / 2);                 // np.tan(fov/2), output6.py:623
+    sp.aspect = (T)((double)p->W / (double)(p->H > 0 ? p->H : 1));
+    sp.W = p->W; sp.H = p->H; sp.sun_id = p->sun_id; sp.max_bounces = p->max_bounces;
+    sp.k0 = (uint32_t)p->seed; sp.k1 = (uint32_t)(p->seed >> 32);
+    sp.rays = p->rays_dev;
+    sp.n = p->rays_dev ? p->m : p->W * p->H;
+    CU(launch_simple<T>(view, sp, reinterpret_cast<int4 *>(rgb), image, reinterpret_cast<unsigned long long *>(stats), st));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_render_simple(rt_scene *scene, int precision, const rt_simple_params *p, int32_t *rgb_dev, float *image_dev,
+                               uint64_t *stats_dev, void *stream) {
+    if (!scene || !p || !rgb_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (p->rays_dev ? p->m < 0 : (p->W <= 0 || p->H <= 0 || (long long)p->W * p->H > 0x7fffffffLL))
+        return fail(RT_ERR_INVALID, "bad frame size / ray count");
+    CU(cudaSetDevice(scene->device));
+    if (precision == RT_F64) return render_simple_t<double>(scene->d.view, p, rgb_dev, image_dev, stats_dev, S(stream));
+    if (precision == RT_F32) return render_simple_t<float>(scene->f.view, p, rgb_dev, image_dev, stats_dev, S(stream));
+    return fail(RT_ERR_INVALID, "unknown precision");
+}
+
+RT_EXPORT int rt_render_simple_host(rt_scene *scene, int precision, const rt_simple_params *p, const double *rays_host,
+                                    int32_t *rgb_host, float *image_host, uint64_t *stats_host) {
+    if (!scene || !p) return fail(RT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(scene->device));
+    rt_simple_params q = *p;
+    DevTmp rays, rgb, image, stats;
+    if (rays_host) {
+        if (q.m < 0) return fail(RT_ERR_INVALID, "negative ray count");
+        CU(cudaMalloc(&rays.p, sizeof(double) * 6 * (size_t)(q.m > 0 ? q.m : 1)));
+        CU(cudaMemcpyAsync(rays.p, rays_host, sizeof(double) * 6 * (size_t)q.m, cudaMemcpyHostToDevice, nullptr));
+        q.rays_dev = (const double *)rays.p;
+    }
+    const size_t n = q.rays_dev ? (size_t)q.m : (size_t)q.W * (size_t)q.H;
+    if (n == 0) return RT_OK;
+    CU(cudaMalloc(&rgb.p, n * 4 * sizeof(int32_t)));
+    CU(cudaMemsetAsync(rgb.p, 0, n * 4 * sizeof(int32_t), nullptr));
+    CU(cudaMalloc(&stats.p, 8 * sizeof(uint64_t)));
+    CU(cudaMemsetAsync(stats.p, 0, 8 * sizeof(uint64_t), nullptr));
+    if (image_host) CU(cudaMalloc(&image.p, n * 3 * sizeof(float)));
+    int rc = rt_render_simple(scene, precision, &q, (int32_t *)rgb.p, (float *)image.p, (uint64_t *)stats.p, nullptr);
+    if (rc) return rc;
+    if (rgb_host) CU(cudaMemcpyAsync(rgb_host, rgb.p, n * 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, nullptr));
+    if (image_host) CU(cudaMemcpyAsync(image_host, image.p, n * 3 * sizeof(float), cudaMemcpyDeviceToHost, nullptr));
+    if (stats_host) CU(cudaMemcpyAsync(stats_host, stats.p, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost, nullptr));
+    CU(cudaStreamSynchronize(nullptr));
+    return RT_OK;
+}
+
 // ------------------------------------------------------------------ batched RayTracerEnv
 template <typename T> static void bind_env(EnvDev<T> &e, const rt_env_desc &d, void *blob) {
     const size_t B = (size_t)d.B;

@@ -346,6 +346,134 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     }
 }
 
+// ------------------------------------------------------------------ "Algorithm C" frame (FB/output6.py)
+// SimplifiedFBRenderer.calculate_lighting_exact_original (output6.py:197-306).  The final int(colour * (combined /
+// 255.0)) is evaluated in double in both builds: for colour 255 the product is an exact integer and a float
+// reciprocal would truncate one level low.
+template <typename T>
+RT_DEV void simple_lighting(const Geo<T> &g, const SimpleDev<T> &sp, const Hit<T> &h, int out[3], unsigned &sun_hits,
+                            unsigned &tests) {
+    if (g.sv.ids[h.idx] == sp.sun_id) {                                          // :204-206
+        sun_hits++;
+        out[0] = (int)sp.sun_col[0]; out[1] = (int)sp.sun_col[1]; out[2] = (int)sp.sun_col[2];
+        return;
+    }
+    const V3<T> sun = mk<T>(sp.sun_pos[0], sp.sun_pos[1], sp.sun_pos[2]);
+    const V3<T> to_sun = normalise(sun - h.p);                                   // :244
+    const V3<T> gdir = normalise(mk<T>(T(3), T(1), T(-0.75)));                   // :247
+    T gcos = dot(h.n, gdir);
+    if (!(gcos > T(0))) gcos = T(0);
+    int gc[3], su[3] = {0, 0, 0};
+    gc[0] = (int)(T(20) * gcos * T(0.3)); gc[1] = gc[0]; gc[2] = (int)(T(255) * gcos * T(0.3));   // :250-254
+    const V3<T> so = h.p + h.n * T(0.001);                                        // :258-261
+    const V3<T> sd = M<T>::exact ? normalise(to_sun) : to_sun;
+    const V3<T> dv = h.p - sun;
+    const T sun_distance = M<T>::sqrt(dot(dv, dv));                               // :264
+    bool visible = true;
+    for (int i = 0; i < g.sv.n && visible; ++i) {                                 // :266-275
+        if (i == h.idx || g.sv.ids[i] == sp.sun_id) continue;
+        T t;
+        tests++;
+        if (!sphere_test<T>(so, sd, g.sv.sph[i], 0, t)) continue;
+        const V3<T> q = (so + sd * t) - h.p;
+        if (M<T>::sqrt(dot(q, q)) < sun_distance) visible = false;
+    }
+    if (visible) {                                                                // :278-291
+        T att = sun_distance > T(0) ? T(1) / (sun_distance * sun_distance) : T(1);
+        att = att * T(100) < T(1) ? att * T(100) : T(1);
+        T ca = dot(h.n, to_sun);
+        if (!(ca > T(0))) ca = T(0);
+        su[0] = (int)(sp.sun_col[0] * ca * att * T(0.9)); su[1] = (int)(sp.sun_col[1] * ca * att * T(0.9));
+        su[2] = (int)(sp.sun_col[2] * ca * att * T(0.9));
+    }
+    const typename M<T>::v4 col = g.sv.col[h.idx];
+    const double c3[3] = {(double)col.x, (double)col.y, (double)col.z};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                                                 // :293-304
+        const int comb = min(255, gc[k] + su[k]);
+        out[k] = (int)__dmul_rn(c3[k], __ddiv_rn((double)comb, 255.0));
+    }
+}
+
+// SimplifiedFBRenderer.trace_ray_simple + render_original_style (output6.py:434-577, :579-635): one thread per pixel
+// (8x4 warp tiles) or per explicit ray.
+template <typename T, int kMode>
+__global__ void __launch_bounds__(256) simple_kernel(SceneDev<T> sc, SimpleDev<T> sp, int4 *rgb, float *image,
+                                                     unsigned long long *stats) {
+    RT_MODE_DECL;
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    int x, y, i;
+    bool active;
+    if (sp.rays) {
+        i = blockIdx.x * blockDim.x + threadIdx.x; x = y = 0;
+        active = i < sp.n;
+    } else {
+        tile_pixel(x, y);
+        active = x < sp.W && y < sp.H;
+        i = y * sp.W + x;
+    }
+    unsigned n_rays = 0, n_sun = 0, n_query = 0, n_tests = 0, n_boxes = 0;
+    if (active) {
+        V3<T> O, D;
+        if (sp.rays) {
+            const double *r = sp.rays + 6 * (size_t)i;
+            O = mk<T>(T(r[0]), T(r[1]), T(r[2]));
+            D = normalise(mk<T>(T(r[3]), T(r[4]), T(r[5])));
+        } else {
+            T u = (T(x) / T(sp.W) - T(0.5)) * T(2), v = (T(y) / T(sp.H) - T(0.5)) * T(-2);       // :612-613
+            u *= sp.aspect;                                                                      // :616-617
+            D = normalise(mk<T>(u * sp.tan_half, v * sp.tan_half, T(-1)));                       // :621
+            if constexpr (M<T>::exact) D = normalise(D);                                         // Ray() normalises again
+            O = mk<T>(sp.cam[0], sp.cam[1], sp.cam[2]);
+        }
+        int acc[3] = {0, 0, 0};
+        int bounce = 0;
+        while (bounce < sp.max_bounces) {
+            n_rays++; n_query++;
+            T t;
+            const int hi = nearest<T, true, kBvh>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes);
+            if (hi < 0) { if (bounce == 0) { acc[0] = 2; acc[1] = 2; acc[2] = 5; } break; }      // :459-463
+            Hit<T> h;
+            finish_hit<T>(S.g, O, D, hi, t, h);
+            int li[3];
+            simple_lighting<T>(S.g, sp, h, li, n_sun, n_tests);
+            n_query++;
+            acc[0] = min(255, acc[0] + li[0]); acc[1] = min(255, acc[1] + li[1]); acc[2] = min(255, acc[2] + li[2]);
+            if (S.g.sv.ids[hi] == sp.sun_id) break;                                              // :479-480
+            const typename M<T>::v4 m = S.g.sv.mat[hi];
+            V3<T> nd;
+            if (m.x != T(0)) nd = reflect<T>(D, h.n);                                            // truthy reflective
+            else if (m.y != T(0)) {                                                              // glass: 50/50
+                const Philox4 o = philox4x32_10((uint32_t)i, 0u, ((uint32_t)bounce + 1u) >> 1, RT_PHILOX_TAG, sp.k0, sp.k1);
+                const uint32_t wa = ((bounce + 1) & 1) ? o.w[2] : o.w[0];
+                nd = u01<T>(wa) < T(0.5) ? reflect<T>(D, h.n) : D;
+            } else {
+                const Philox4 o = philox4x32_10((uint32_t)i, 0u, ((uint32_t)bounce + 1u) >> 1, RT_PHILOX_TAG, sp.k0, sp.k1);
+                const bool odd = (bounce + 1) & 1;
+                nd = bounce_direction<T>(D, h.n, false, u01<T>(odd ? o.w[2] : o.w[0]), u01<T>(odd ? o.w[3] : o.w[1]));
+            }
+            O = h.p + h.n * T(0.001);                                                            // :567-570
+            D = M<T>::exact ? normalise(nd) : nd;
+            bounce++;
+        }
+        rgb[i] = make_int4(acc[0], acc[1], acc[2], bounce);
+        if (image) {
+            float *px = image + 3 * (size_t)i;
+            px[0] = fminf(1.f, (float)((double)acc[0] / 255.0)); px[1] = fminf(1.f, (float)((double)acc[1] / 255.0));
+            px[2] = fminf(1.f, (float)((double)acc[2] / 255.0));
+        }
+    }
+    if (stats) {
+        flush_stats(stats, STAT_RAYS, n_rays);
+        flush_stats(stats, STAT_INTER, n_sun);
+        flush_stats(stats, STAT_QUERIES, n_query);
+        flush_stats(stats, STAT_SPHERE_TESTS, n_tests);
+        flush_stats(stats, STAT_AABB_TESTS, n_boxes);
+    }
+}
+
 // ------------------------------------------------------------------ resolve
 // pixel // spp then min(1, /255) (chandelier.py:540-549; output5.py:1500-1512)
 template <typename T>
@@ -701,6 +829,16 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
 }
 
 template <typename T>
+cudaError_t launch_simple(const SceneDev<T> &sc, const SimpleDev<T> &sp, int4 *rgb, float *image, unsigned long long *stats,
+                          cudaStream_t st) {
+    if (sp.n <= 0) return cudaSuccess;
+    dim3 block(256), grid = sp.rays ? dim3((sp.n + 255) / 256) : dim3((sp.W + 31) / 32, (sp.H + 7) / 8);
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, simple_kernel, grid, block, smem_for(sc), st, sc, sp, rgb, image, stats);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_resolve(const void *accum, int W, int y0, int y1, int spp, float *image, cudaStream_t st) {
     const size_t n = (size_t)(y1 - y0) * W;
     if (n == 0) return cudaSuccess;
@@ -767,6 +905,8 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
                                         cudaStream_t);                                                                  \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \
+    template cudaError_t launch_simple<T>(const SceneDev<T> &, const SimpleDev<T> &, int4 *, float *,                   \
+                                          unsigned long long *, cudaStream_t);                                         \
     template cudaError_t launch_sphere_disc<T>(int, const double *, const double *, int, double *, cudaStream_t);       \
     template cudaError_t launch_trace_rays<T>(const SceneDev<T> &, int, const double *, const int *, const int *,       \
                                               const int *, int, int, const double[3], double *, double *,              \

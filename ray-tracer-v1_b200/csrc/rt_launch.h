@@ -34,6 +34,14 @@ template <typename T> struct PathDev {
     int band_y[17];
 };
 
+// "Algorithm C" frame (rt_simple_params)
+template <typename T> struct SimpleDev {
+    T cam[3], tan_half, aspect, sun_pos[3], sun_col[3];
+    int W, H, n, sun_id, max_bounces;
+    uint32_t k0, k1;
+    const double *rays;
+};
+
 // batched RayTracerEnv state (SoA, [3][B] for vectors)
 template <typename T> struct EnvDev {
     int B, W, H, max_bounces, flavour, sun_id;
@@ -49,6 +57,9 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
                         cudaStream_t st);
+template <typename T>
+cudaError_t launch_simple(const SceneDev<T> &sc, const SimpleDev<T> &sp, int4 *rgb, float *image, unsigned long long *stats,
+                          cudaStream_t st);
 template <typename T>
 cudaError_t launch_resolve(const void *accum, int W, int y0, int y1, int spp, float *image, cudaStream_t st);
 // rt_f32.cu: resolve + clear, peer flags

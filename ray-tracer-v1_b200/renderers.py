@@ -7,6 +7,8 @@
                                  ``stats`` keys.
 * ``CustomSceneExperiment``      RL/output5.py:264 -- ``render_true_original(scene, path)`` (:416-533) and
                                  ``render_custom_scene(scene, 'traditional', path)`` (:1420-1525) (Algorithm A).
+* ``SimplifiedFBRenderer``       FB/output6.py:85-654 in traditional mode (``fb_usage_prob == 0``, the value the reference
+                                 ships): ``render_original_style(width, height, output_path)`` and ``trace_ray_simple(ray)``.
 * ``render_whitted`` / ``render_path``  the plain functions underneath (flat scene in, numpy image out).
 
 Every call re-flattens the scene (the reference's scenes are mutable lists) and uploads it; frames are rendered and
@@ -28,7 +30,7 @@ from .scenes import custom_scene_grid, notebook_grid
 from .vector import Vector
 
 __all__ = ["render_whitted", "render_path", "TraditionalRenderer", "ComplexTraditionalRenderer",
-           "CustomSceneExperiment", "save_png"]
+           "CustomSceneExperiment", "SimplifiedFBRenderer", "save_png"]
 
 _PREC = {"f32": nat.F32, "fp32": nat.F32, "float32": nat.F32, nat.F32: nat.F32,
          "f64": nat.F64, "fp64": nat.F64, "float64": nat.F64, "double": nat.F64}
@@ -204,3 +206,68 @@ class CustomSceneExperiment:
         if save_path is not None:
             save_png(image, save_path)
         return render_time, image
+
+
+class SimplifiedFBRenderer:
+    """Drop-in for FB/output6.py ``SimplifiedFBRenderer`` in its traditional mode.
+
+    The reference constructs the scene itself (``create_your_custom_scene()``, output6.py:45-83 = balls_in_space with
+    the sun as id 7) and ships ``fb_usage_prob = 0.0`` (:116), i.e. every diffuse bounce is the cosine-weighted
+    traditional one; the FB-guided branch needs a trained checkpoint the reference does not include and is out of the
+    hot path: a non-zero ``fb_usage_prob`` raises.  ``np.random.random`` draws (glass 50/50, diffuse
+    r1/r2) come from Philox keyed (pixel, bounce) with ``self.seed``."""
+
+    def __init__(self, model_path=None, device=0, precision="f32", seed=None):
+        from .scenes import build_balls_in_space
+        self.scene = build_balls_in_space(as_rendered=False).spheres
+        self.sun_position = Vector(-0.6, 0.2, 6)
+        self.sun_radius = 0.1
+        self.sun_color = Colour(255, 255, 204)
+        self.agent = None
+        self.fb_model_loaded = False
+        self.max_bounces = 5
+        self.samples_per_pixel = 100          # unused by render_original_style, as in the reference (:113)
+        self.fb_usage_prob = 0.0
+        self.stats = {'total_rays': 0, 'sun_hits': 0, 'fb_used': 0, 'fb_success': 0, 'render_time': 0}
+        self.device, self.precision, self.seed = device, precision, seed
+        self._renders = 0
+
+    def _scene_and_params(self, width, height):
+        if self.fb_usage_prob:
+            raise NotImplementedError("FB-guided sampling is outside the traditional hot path (fb_usage_prob must be 0)")
+        seed = self.seed if self.seed is not None else (time.time_ns() ^ (self._renders * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
+        self._renders += 1
+        sc = nat.DeviceScene(flatten_scene(self.scene), self.device)       # re-flattened: the scene list is mutable
+        p = sc.simple_params(width, height, cam=(0.0, 0.0, 1.0), sun_pos=_xyz(self.sun_position),
+                             sun_col=self.sun_color.getList(), sun_id=7, max_bounces=self.max_bounces, seed=seed)
+        return sc, p
+
+    def trace_ray_simple(self, ray):
+        """One ray -> accumulated ``Colour`` (output6.py:434-577); a batch of one through the same kernel."""
+        sc, p = self._scene_and_params(1, 1)
+        try:
+            o, d = _xyz(ray.origin), _xyz(ray.D)
+            _, rgb, st = sc.render_simple_host(p, _precision(self.precision), rays=np.array([[*o, *d]], np.float64),
+                                               want_image=False)
+        finally:
+            sc.close()
+        self.stats['total_rays'] += int(st[0])
+        self.stats['sun_hits'] += int(st[1])
+        return Colour(int(rgb[0, 0, 0]), int(rgb[0, 0, 1]), int(rgb[0, 0, 2]))
+
+    def render_original_style(self, width=400, height=300, output_path=None):
+        """-> (image [H,W,3] float32 in [0,1], output_path) (output6.py:579-654)."""
+        if output_path is None:
+            output_path = f"./fb_simple_render_{time.strftime('%Y%m%d_%H%M%S')}.png"
+        self.stats = {'total_rays': 0, 'sun_hits': 0, 'fb_used': 0, 'fb_success': 0, 'render_time': 0}
+        start = time.time()
+        sc, p = self._scene_and_params(width, height)
+        try:
+            image, _, st = sc.render_simple_host(p, _precision(self.precision))
+        finally:
+            sc.close()
+        self.stats['total_rays'], self.stats['sun_hits'] = int(st[0]), int(st[1])
+        self.stats['render_time'] = time.time() - start
+        if output_path:
+            save_png(image, output_path)
+        return image, output_path

@@ -365,3 +365,43 @@ def test_sample_split_gives_the_same_frame(nat):
     want = np.minimum(1.0, np.floor(ref[..., :3].astype(np.float64) / spp) / 255.0).astype(np.float32)
     assert np.array_equal(img.cpu().numpy(), want)
     sc.close()
+
+
+# ------------------------------------------------------------------ "Algorithm C": FB/output6.py traditional mode
+@pytest.mark.parametrize("name", ["simple_balls_a_64x48", "simple_balls_b_40x30"])
+def test_output6_frames_match_reference(nat, orc, name):
+    z, fs = load_golden(name)
+    W, H, seed, depth = int(z["W"]), int(z["H"]), int(z["seed"]), int(z["max_bounces"])
+    sc = nat.DeviceScene(fs)
+    p = sc.simple_params(W, H, max_bounces=depth, seed=seed)
+    img64, rgb64, st64 = sc.render_simple_host(p, nat.F64)
+    assert np.array_equal(rgb64[..., :3], z["rgb"].astype(np.int32))          # the reference's own render, exactly
+    assert np.array_equal(img64, z["image"])
+    assert [int(st64[0]), int(st64[1])] == list(z["stats"])
+    img32, rgb32, st32 = sc.render_simple_host(p, nat.F32)
+    d = np.abs(rgb32[..., :3].astype(np.int64) - z["rgb"].astype(np.int64)).max(axis=2)
+    assert (d > 1).mean() < 0.02, (d > 1).mean()          # same Philox stream: a few silhouette / int() flips
+    assert abs(int(st32[0]) - int(st64[0])) <= 0.01 * int(st64[0])
+    # a larger frame against the oracle (FP64 exact), and the explicit-ray entry against the frame
+    q = sc.simple_params(200, 150, max_bounces=depth, seed=seed + 1)
+    _, big64, stb = sc.render_simple_host(q, nat.F64)
+    ref, sto = orc.render_simple(fs, 200, 150, seed=seed + 1, max_bounces=depth)
+    assert np.array_equal(big64[..., :3], ref.astype(np.int32)) and int(stb[0]) == sto["total_rays"] and int(stb[1]) == sto["sun_hits"]
+    sc.close()
+
+
+def test_output6_dropin_class(rt, orc):
+    r = rt.SimplifiedFBRenderer(precision="f64", seed=5)
+    image, path = r.render_original_style(96, 72, output_path="")
+    fs = rt.flatten_scene(r.scene)
+    ref, st = orc.render_simple(fs, 96, 72, seed=5, max_bounces=5)
+    assert np.array_equal(image, np.minimum(1.0, ref / 255.0).astype(np.float32))
+    assert r.stats["total_rays"] == st["total_rays"] and r.stats["sun_hits"] == st["sun_hits"]
+    # scalar entry: a ray at the big blue sphere and one that bounces off the mirror towards the sun's side
+    r.max_bounces = 8
+    c = r.trace_ray_simple(rt.Ray(rt.Vector(0, 0, 1), rt.Vector(0.07, -0.07, -1)))
+    want, _ = orc.render_simple(fs, 1, 1, seed=5, max_bounces=8, rays=np.array([[0, 0, 1, 0.07, -0.07, -1.0]]))
+    assert (c.r, c.g, c.b) == tuple(int(v) for v in want[0, 0])
+    r.fb_usage_prob = 0.5
+    with pytest.raises(NotImplementedError):
+        r.render_original_style(8, 8, output_path="")

@@ -129,3 +129,23 @@ def test_env_rollouts(orc, name):
         assert np.array_equal(term, z["terminated"][t].astype(bool)), f"terminated step {t}"
         assert np.array_equal(trunc, z["truncated"][t].astype(bool)), f"truncated step {t}"
         assert np.array_equal(reason, z["reason"][t]), f"reason step {t}"
+
+
+@pytest.mark.parametrize("name", ["simple_balls_a_64x48", "simple_balls_b_40x30"])
+def test_output6_frames(orc, name):
+    """FB/output6.py render_original_style (traditional mode) rendered by the reference itself with the Philox stream
+    patched into np.random.random: per-pixel colours, float32 image and both counters, exactly."""
+    z, fs = load_golden(name)
+    rgb, st = orc.render_simple(fs, int(z["W"]), int(z["H"]), seed=int(z["seed"]), max_bounces=int(z["max_bounces"]))
+    assert np.array_equal(rgb, z["rgb"])
+    assert np.array_equal(np.minimum(1.0, rgb / 255.0).astype(np.float32), z["image"])
+    assert [st["total_rays"], st["sun_hits"]] == list(z["stats"])
+    # explicit rays = the scalar trace_ray_simple entry: the camera grid's own rays give the frame back
+    W, H = int(z["W"]), int(z["H"])
+    x, y = np.meshgrid(np.arange(W), np.arange(H))
+    t = np.tan(np.pi / 6)
+    d = np.stack([(x / W - 0.5) * 2.0 * (W / H) * t, (y / H - 0.5) * -2.0 * t, -np.ones_like(x, float)], axis=-1).reshape(-1, 3)
+    d = d / np.sqrt((d * d).sum(axis=1, keepdims=True))       # render_original_style normalises before Ray() does
+    rays = np.concatenate([np.tile([0.0, 0.0, 1.0], (W * H, 1)), d], axis=1)
+    rgb2, _ = orc.render_simple(fs, W, H, seed=int(z["seed"]), max_bounces=int(z["max_bounces"]), rays=rays)
+    assert (rgb2.reshape(H, W, 3) != rgb).any(axis=2).mean() < 0.002      # vnorm in numpy vs C: last-ulp flips only
