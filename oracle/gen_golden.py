@@ -416,12 +416,66 @@ def gen_simple(ref):
         print(f"simple_balls_{tag}", stats, "mean", rgb.mean(axis=(0, 1)))
 
 
+# ----------------------------------------------------------------- FB training trajectories (f-2)
+def gen_traj(ref):
+    """RayTracedComplexTrainer.generate_trajectory (FB/train_complex_only.py:254-334), the reference's own method, with
+    ``random.choice / uniform / random`` patched to the Philox stream.  ``fb_ray_tracing`` and
+    ``fb_multi_scene_trainer`` are absent from the reference: stub modules with empty classes stand in for the
+    imports, and the trainer is made with ``object.__new__`` (only ``self.max_bounces`` is read)."""
+    import random as pyrandom
+    for name, attrs in (("fb_ray_tracing", ("FBResearchAgent", "FBConfig")), ("fb_multi_scene_trainer", ("MultiSceneFBTrainer",))):
+        m = types.ModuleType(name)
+        for a in attrs:
+            setattr(m, a, type(a, (), {}))
+        sys.modules[name] = m
+    mod = _load("ref_train_complex", REF / "FB" / "train_complex_only.py")
+    spec = scenes.build_complex(ref.ns)
+    seed, n_traj, max_steps = 31, 256, 8
+    ctl = types.SimpleNamespace(j=-1, draws=0)
+
+    def nxt():
+        k = ctl.draws
+        ctl.draws += 1
+        # draw order: choice, theta | phi, - | then (r1, r2) pairs from slot 2
+        slot, word = (0, k) if k < 2 else (1, 0) if k == 2 else (2 + (k - 3) // 2, (k - 3) % 2)
+        return orc.rng_pair(seed, ctl.j, 0, slot)[word]
+
+    def fake_choice(seq):
+        return seq[min(len(seq) - 1, int(nxt() * len(seq)))]
+
+    def fake_uniform(a, b):
+        return a + (b - a) * nxt()
+
+    tr = object.__new__(mod.RayTracedComplexTrainer)
+    tr.max_bounces = 8
+    rows = {k: [] for k in ("obs", "action", "next_obs", "reward", "hit")}
+    length, hit_light = [], []
+    with contextlib.redirect_stdout(io.StringIO()), mock.patch.object(pyrandom, "choice", fake_choice), \
+            mock.patch.object(pyrandom, "uniform", fake_uniform), mock.patch.object(pyrandom, "random", nxt):
+        for j in range(n_traj):
+            ctl.j, ctl.draws = j, 0
+            transitions, hit = tr.generate_trajectory(spec.spheres, max_steps=max_steps)
+            length.append(len(transitions)); hit_light.append(int(hit))
+            pad = {"obs": np.zeros((max_steps, 22), np.float32), "action": np.zeros((max_steps, 2), np.float32),
+                   "next_obs": np.zeros((max_steps, 22), np.float32), "reward": np.zeros(max_steps, np.float32),
+                   "hit": np.zeros(max_steps, np.uint8)}
+            for t, (o, a, no, r, h) in enumerate(transitions):
+                pad["obs"][t], pad["action"][t], pad["next_obs"][t], pad["reward"][t], pad["hit"][t] = o, a, no, r, h
+            for k in rows:
+                rows[k].append(pad[k])
+    np.savez_compressed(OUT / "traj_complex_256.npz", seed=seed, max_steps=max_steps, max_bounces=8,
+                        length=np.array(length, np.int32), hit_light=np.array(hit_light, np.uint8),
+                        **{k: np.stack(v) for k, v in rows.items()}, **flat_dict(rtb.flatten_scene(spec.spheres)))
+    print("traj_complex", "transitions", int(np.sum(length)), "light hits", int(np.sum(hit_light)))
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     ref = load_reference()
-    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple"]
+    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple", "traj"]
     for w in which:
-        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env, "simple": gen_simple}[w](ref)
+        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env, "simple": gen_simple,
+         "traj": gen_traj}[w](ref)
 
 
 if __name__ == "__main__":

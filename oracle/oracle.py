@@ -80,6 +80,8 @@ def lib():
                                       c_u8p, c_u8p, c_ip]
         _lib.orc_render_simple.argtypes = [C.POINTER(_Scene), C.POINTER(_SimpleCfg), C.c_int, C.c_int, C.c_uint64, c_dp, c_dp,
                                            c_u64p, C.c_int]
+        _lib.orc_generate_trajectories.argtypes = [C.POINTER(_Scene), C.c_int, C.c_int, C.c_int, C.c_uint64, c_fp, c_fp, c_fp,
+                                                   c_fp, c_u8p, c_ip, c_u8p]
         _lib.orc_sizeof_env.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -241,6 +243,20 @@ def render_simple(fs, W, H, cam=(0, 0, 1), fov=np.pi / 3, sun_pos=(-0.6, 0.2, 6)
     st = (C.c_uint64 * 2)()
     lib().orc_render_simple(sc.ref, C.byref(cfg), int(W), int(H), int(seed), rp, _p(out, c_dp), st, int(nthreads))
     return out, {"total_rays": int(st[0]), "sun_hits": int(st[1])}
+
+
+def generate_trajectories(fs, n_traj, max_steps=8, max_bounces=8, seed=0):
+    """FB/train_complex_only.py ``generate_trajectory`` x n_traj -> dict of obs/action/next_obs/reward/hit (padded to
+    max_steps), length, hit_light."""
+    sc = _scene(fs)
+    n, m = int(n_traj), int(max_steps)
+    out = {"obs": np.zeros((n, m, 22), np.float32), "action": np.zeros((n, m, 2), np.float32),
+           "next_obs": np.zeros((n, m, 22), np.float32), "reward": np.zeros((n, m), np.float32),
+           "hit": np.zeros((n, m), np.uint8), "length": np.zeros(n, np.int32), "hit_light": np.zeros(n, np.uint8)}
+    lib().orc_generate_trajectories(sc.ref, n, m, int(max_bounces), int(seed), _p(out["obs"], c_fp), _p(out["action"], c_fp),
+                                    _p(out["next_obs"], c_fp), _p(out["reward"], c_fp), _p(out["hit"], c_u8p),
+                                    _p(out["length"], c_ip), _p(out["hit_light"], c_u8p))
+    return out
 
 
 def resolve(sum_rgb, spp):

@@ -580,6 +580,92 @@ ORC_API void orc_render_simple(const orc_scene *s, const orc_simple_cfg *c, int 
     if (stats2) { stats2[0] = R; stats2[1] = S; }
 }
 
+/* ---------------- FB training trajectories: FB/train_complex_only.py:54-162, :254-334 */
+/* sample_cosine_weighted_direction(normal), train_complex_only.py:69-96 (tangent rule |n.z| < 0.999, unlike the
+   renderers' |n.z| > 0.9) */
+static v3 traj_basis_dir(v3 n, double lx, double ly, double lz, v3 *tg_out, v3 *bt_out) {
+    v3 tg = fabs(n.z) < 0.999 ? vnorm(vcross(V(0, 0, 1), n)) : vnorm(vcross(V(1, 0, 0), n));
+    v3 bt = vnorm(vcross(n, tg));
+    if (tg_out) { *tg_out = tg; *bt_out = bt; }
+    return vnorm(V(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y, lx * tg.z + ly * bt.z + lz * n.z));
+}
+static v3 traj_cosine_dir(v3 n, double r1, double r2) {
+    double theta = acos(sqrt(r1)), phi = 2 * M_PI * r2;
+    return traj_basis_dir(n, sin(theta) * cos(phi), sin(theta) * sin(phi), cos(theta), NULL, NULL);
+}
+/* create_observation, train_complex_only.py:130-150 (22 x float32) */
+static void traj_obs(const orc_scene *s, v3 p, v3 n, v3 d, int bounce, const double col[3], int idx, int max_bounces, float *o) {
+    const double *m = s->material + 4 * idx;
+    o[0] = (float)p.x; o[1] = (float)p.y; o[2] = (float)p.z; o[3] = (float)d.x; o[4] = (float)d.y; o[5] = (float)d.z;
+    o[6] = (float)n.x; o[7] = (float)n.y; o[8] = (float)n.z;
+    o[9] = (float)m[0]; o[10] = (float)m[1]; o[11] = (float)m[2]; o[12] = (float)m[3];
+    o[13] = (float)(col[0] / 255.0); o[14] = (float)(col[1] / 255.0); o[15] = (float)(col[2] / 255.0);
+    o[16] = (float)((double)bounce / max_bounces); o[17] = 0.0f; o[18] = (float)((double)s->ids[idx] / 100.0);
+    o[19] = 0.5f; o[20] = 0.5f; o[21] = 0.5f;
+}
+/* RayTracedComplexTrainer.generate_trajectory, train_complex_only.py:254-334.  Draws (Philox, trajectory j, sample 0):
+   slot 0 = (sphere choice, theta), slot 1 word 0 = phi, slot 2 = incoming direction (r1, r2), slot 3+k = step k.
+   obs/next_obs [n,max_steps,22] f32, action [n,max_steps,2] f32, reward [n,max_steps] f32, hit [n,max_steps] u8,
+   length [n] (transitions recorded), hit_light [n]. */
+ORC_API void orc_generate_trajectories(const orc_scene *s, int n_traj, int max_steps, int max_bounces, uint64_t seed,
+                                       float *obs, float *action, float *next_obs, float *reward, uint8_t *hit,
+                                       int32_t *length, uint8_t *hit_light) {
+    int nl = 0;
+    for (int i = 0; i < s->n; ++i) if (s->material[4 * i + 2] == 0) nl++;
+    for (int j = 0; j < n_traj; ++j) {
+        length[j] = 0; hit_light[j] = 0;
+        if (nl == 0) continue;
+        double u0, u1, u2, u3;
+        rng_pair(seed, (uint32_t)j, 0, 0, &u0, &u1);
+        rng_pair(seed, (uint32_t)j, 0, 1, &u2, &u3);
+        int pick = (int)(u0 * nl); if (pick > nl - 1) pick = nl - 1;           /* random.choice(non_light) */
+        int idx = -1;
+        for (int i = 0; i < s->n; ++i) if (s->material[4 * i + 2] == 0 && pick-- == 0) { idx = i; break; }
+        double th = 0 + (2 * M_PI - 0) * u1, ph = 0 + (M_PI - 0) * u2;           /* random.uniform */
+        v3 unit = V(sin(ph) * cos(th), sin(ph) * sin(th), cos(ph));
+        v3 off = vscale(unit, s->radius[idx]);                                   /* scaleByLength */
+        v3 p = vadd(ld3(s->centre, idx), off), n = vnorm(off);
+        double r1, r2;
+        rng_pair(seed, (uint32_t)j, 0, 2, &r1, &r2);
+        v3 din = traj_cosine_dir(n, r1, r2);
+        const double black[3] = {0, 0, 0};
+        float cur[22];
+        traj_obs(s, p, n, din, 0, black, idx, max_bounces, cur);
+        int bounce = 0;
+        while (bounce < max_steps) {
+            rng_pair(seed, (uint32_t)j, 0, 3 + (uint32_t)bounce, &r1, &r2);
+            v3 nd = traj_cosine_dir(n, r1, r2);
+            /* direction_to_action, :99-127 */
+            v3 tg, bt;
+            traj_basis_dir(n, 0, 0, 1, &tg, &bt);
+            double lx = vdot(nd, tg), ly = vdot(nd, bt), lz = vdot(nd, n);
+            double cz = lz > 1 ? 1 : lz; if (cz < -1) cz = -1;
+            double theta = acos(cz); if (theta > M_PI / 2) theta = M_PI / 2;
+            double phi = atan2(ly, lx);
+            float a0 = (float)((theta / (M_PI / 2)) * 2 - 1), a1 = (float)(phi / M_PI);
+            v3 ro = vadd(p, vscale(n, 0.001)), rd = vnorm(nd);
+            isect best; memset(&best, 0, sizeof best); best.idx = -1; double bd = INFINITY;
+            for (int i = 0; i < s->n; ++i) {                                      /* nearest_intersection, :153-166 */
+                if (s->ids[i] == s->ids[idx]) continue;
+                isect it = sphere_discriminant(ro, rd, ld3(s->centre, i), s->radius[i], 0);
+                if (it.hit) { double dist = vdist(it.p, ro); if (dist < bd) { bd = dist; best = it; best.idx = i; } }
+            }
+            if (!best.hit) break;                                                /* ray escaped */
+            size_t t = (size_t)j * max_steps + length[j];
+            int lit = s->material[4 * best.idx + 2] != 0;
+            memcpy(obs + 22 * t, cur, sizeof cur);
+            action[2 * t] = a0; action[2 * t + 1] = a1;
+            traj_obs(s, best.p, best.n, rd, bounce + 1, lit ? s->colour + 3 * best.idx : black, best.idx, max_bounces, next_obs + 22 * t);
+            reward[t] = lit ? 1.0f : 0.0f; hit[t] = (uint8_t)lit;
+            length[j]++;
+            if (lit) { hit_light[j] = 1; break; }
+            p = best.p; n = best.n; idx = best.idx;
+            memcpy(cur, next_obs + 22 * t, sizeof cur);
+            bounce++;
+        }
+    }
+}
+
 /* -------------------------------------------------- RayTracerEnv (batched) */
 /* One record per env; mirrors the attributes of RayTracerEnv
    (RL/ray_tracer_env.py:79-86).                                              */

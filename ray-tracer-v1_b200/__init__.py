@@ -22,6 +22,7 @@ _LAZY = {
     "TraditionalRenderer": "renderers", "CustomSceneExperiment": "renderers", "SimplifiedFBRenderer": "renderers",
     "render_whitted": "renderers", "render_path": "renderers",
     "RayTracerEnv": "ray_tracer_env", "BatchedRayTracerEnv": "ray_tracer_env",
+    "generate_trajectories": "fb_trajectories", "generate_trajectory": "fb_trajectories", "TrajectoryBatch": "fb_trajectories",
     "NativeLibraryError": "_native", "DeviceScene": "_native",
 }
 

@@ -716,6 +716,27 @@ RT_EXPORT int rt_render_path_host(rt_scene *scene, int precision, const rt_path_
     return render_host_common(scene, precision, false, p, image_host, accum_host, nullptr, stats_host);
 }
 
+// ------------------------------------------------------------------ FB training trajectories
+RT_EXPORT int rt_generate_trajectories(rt_scene *scene, int precision, int32_t n_traj, int32_t max_steps, int32_t max_bounces,
+                                       uint64_t seed, float *obs_dev, float *action_dev, float *next_obs_dev,
+                                       float *reward_dev, uint8_t *hit_dev, int32_t *length_dev, uint8_t *hit_light_dev,
+                                       uint64_t *stats_dev, void *stream) {
+    if (!scene) return fail(RT_ERR_INVALID, "scene is NULL");
+    if (n_traj < 0 || max_steps <= 0 || max_bounces <= 0) return fail(RT_ERR_INVALID, "bad trajectory counts");
+    if (n_traj > 0 && (!obs_dev || !action_dev || !next_obs_dev || !reward_dev || !hit_dev || !length_dev || !hit_light_dev))
+        return fail(RT_ERR_INVALID, "NULL output");
+    CU(cudaSetDevice(scene->device));
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (precision == RT_F64)
+        CU(launch_trajectories<double>(scene->d.view, n_traj, max_steps, max_bounces, seed, obs_dev, action_dev, next_obs_dev,
+                                       reward_dev, hit_dev, length_dev, hit_light_dev, st, S(stream)));
+    else if (precision == RT_F32)
+        CU(launch_trajectories<float>(scene->f.view, n_traj, max_steps, max_bounces, seed, obs_dev, action_dev, next_obs_dev,
+                                      reward_dev, hit_dev, length_dev, hit_light_dev, st, S(stream)));
+    else return fail(RT_ERR_INVALID, "unknown precision");
+    return RT_OK;
+}
+
 // ------------------------------------------------------------------ "Algorithm C" frame (FB/output6.py)
 template <typename T>
 static int render_simple_t(const SceneDev<T> &view, const rt_simple_params *p, int32_t *rgb, float *image, uint64_t *stats,

@@ -474,6 +474,122 @@ __global__ void __launch_bounds__(256) simple_kernel(SceneDev<T> sc, SimpleDev<T
     }
 }
 
+// ------------------------------------------------------------------ FB training trajectories (train_complex_only.py)
+// sample_cosine_weighted_direction / direction_to_action basis (train_complex_only.py:84-89): |n.z| < 0.999 picks
+// (0,0,1) x n, unlike the renderers' |n.z| > 0.9 rule.
+template <typename T> RT_DEV void traj_basis(V3<T> n, V3<T> &tg, V3<T> &bt) {
+    tg = M<T>::fabs(n.z) < T(0.999) ? normalise(cross(mk<T>(0, 0, 1), n)) : normalise(cross(mk<T>(1, 0, 0), n));
+    bt = normalise(cross(n, tg));
+}
+template <typename T> RT_DEV V3<T> traj_cosine_dir(V3<T> n, T r1, T r2, V3<T> &tg, V3<T> &bt) {
+    T st, ct, sp, cp;
+    if constexpr (M<T>::exact) {
+        const T theta = ::acos(::sqrt(r1)), phi = 2 * 3.14159265358979323846 * r2;
+        st = ::sin(theta); ct = ::cos(theta); sp = ::sin(phi); cp = ::cos(phi);
+    } else {
+        ct = M<T>::sqrt(r1); st = M<T>::sqrt(1.f - r1);
+        sincospif(2.f * r2, &sp, &cp);
+    }
+    traj_basis<T>(n, tg, bt);
+    const T lx = st * cp, ly = st * sp, lz = ct;
+    return normalise(mk<T>(lx * tg.x + ly * bt.x + lz * n.x, lx * tg.y + ly * bt.y + lz * n.y, lx * tg.z + ly * bt.z + lz * n.z));
+}
+// create_observation (train_complex_only.py:130-150)
+template <typename T>
+RT_DEV void traj_obs(const Geo<T> &g, V3<T> p, V3<T> n, V3<T> d, int bounce, T c0, T c1, T c2, int idx, int max_bounces, float *o) {
+    const typename M<T>::v4 m = g.sv.mat[idx];
+    o[0] = (float)p.x; o[1] = (float)p.y; o[2] = (float)p.z; o[3] = (float)d.x; o[4] = (float)d.y; o[5] = (float)d.z;
+    o[6] = (float)n.x; o[7] = (float)n.y; o[8] = (float)n.z;
+    o[9] = (float)m.x; o[10] = (float)m.y; o[11] = (float)m.z; o[12] = (float)m.w;
+    o[13] = (float)(c0 / T(255)); o[14] = (float)(c1 / T(255)); o[15] = (float)(c2 / T(255));
+    o[16] = (float)(T(bounce) / T(max_bounces)); o[17] = 0.f; o[18] = (float)(T(g.sv.ids[idx]) / T(100));
+    o[19] = 0.5f; o[20] = 0.5f; o[21] = 0.5f;
+}
+// RayTracedComplexTrainer.generate_trajectory (train_complex_only.py:254-334): one thread per trajectory.
+template <typename T, int kMode>
+__global__ void __launch_bounds__(128) trajectory_kernel(SceneDev<T> sc, int n_traj, int max_steps, int max_bounces,
+                                                         uint32_t k0, uint32_t k1, float *obs, float *action,
+                                                         float *next_obs, float *reward, uint8_t *hit, int *length,
+                                                         uint8_t *hit_light, unsigned long long *stats) {
+    RT_MODE_DECL;
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned n_query = 0, n_tests = 0, n_boxes = 0;
+    if (j < n_traj) {
+        int len = 0, lit_any = 0;
+        int nl = 0;
+        for (int i = 0; i < S.g.sv.n; ++i) nl += S.g.sv.mat[i].z == T(0);
+        if (nl > 0) {
+            PathRng rng;
+            rng.begin((uint32_t)j, 0u, k0, k1);
+            uint32_t wa, wb, wc, wd;
+            rng.pair(0u, wa, wb);
+            rng.pair(1u, wc, wd);
+            int pick = min(nl - 1, (int)(u01<T>(wa) * T(nl)));                               // random.choice(non_light)
+            int idx = 0;
+            for (int i = 0; i < S.g.sv.n; ++i) if (S.g.sv.mat[i].z == T(0) && pick-- == 0) { idx = i; break; }
+            const T th = T(2 * 3.14159265358979323846) * u01<T>(wb), ph = T(3.14159265358979323846) * u01<T>(wc);
+            T sth, cth, sph_, cph;
+            M<T>::sincos(th, &sth, &cth); M<T>::sincos(ph, &sph_, &cph);
+            const typename M<T>::v4 s0 = S.g.sv.sph[idx];
+            const V3<T> off = mk<T>(sph_ * cth, sph_ * sth, cph) * s0.w;                      // scaleByLength(radius)
+            V3<T> p = centre_of<T>(s0) + off, n = normalise(off);
+            V3<T> tg, bt;
+            rng.pair(2u, wa, wb);
+            const V3<T> din = traj_cosine_dir<T>(n, u01<T>(wa), u01<T>(wb), tg, bt);
+            float cur[22];
+            traj_obs<T>(S.g, p, n, din, 0, T(0), T(0), T(0), idx, max_bounces, cur);
+            int bounce = 0;
+            while (bounce < max_steps) {
+                rng.pair(3u + (uint32_t)bounce, wa, wb);
+                const V3<T> nd = traj_cosine_dir<T>(n, u01<T>(wa), u01<T>(wb), tg, bt);
+                // direction_to_action (:99-127)
+                const T lx = dot(nd, tg), ly = dot(nd, bt), lz = dot(nd, n);
+                T cz = lz > T(1) ? T(1) : lz;
+                if (cz < T(-1)) cz = T(-1);
+                T theta, phi;
+                if constexpr (M<T>::exact) { theta = ::acos(cz); phi = ::atan2(ly, lx); }
+                else { theta = acosf(cz); phi = atan2f(ly, lx); }
+                const T half_pi = T(3.14159265358979323846 / 2);
+                if (theta > half_pi) theta = half_pi;
+                const float a0 = (float)((theta / half_pi) * T(2) - T(1)), a1 = (float)(phi / T(3.14159265358979323846));
+                const V3<T> ro = p + n * T(0.001);
+                const V3<T> rd = M<T>::exact ? normalise(nd) : nd;                            // Ray() normalises again
+                T t;
+                n_query++;
+                const int hi = nearest<T, true, kBvh>(S.g, ro, rd, S.g.sv.ids[idx], t, n_tests, n_boxes);
+                if (hi < 0) break;                                                           // ray escaped
+                Hit<T> h;
+                finish_hit<T>(S.g, ro, rd, hi, t, h);
+                const size_t tr = (size_t)j * max_steps + len;
+                const bool lit = S.g.sv.mat[hi].z != T(0);
+                float *po = obs + 22 * tr, *pn = next_obs + 22 * tr;
+#pragma unroll
+                for (int k = 0; k < 22; ++k) po[k] = cur[k];
+                action[2 * tr] = a0; action[2 * tr + 1] = a1;
+                const typename M<T>::v4 col = S.g.sv.col[hi];
+                traj_obs<T>(S.g, h.p, h.n, rd, bounce + 1, lit ? col.x : T(0), lit ? col.y : T(0), lit ? col.z : T(0), hi,
+                            max_bounces, cur);
+#pragma unroll
+                for (int k = 0; k < 22; ++k) pn[k] = cur[k];
+                reward[tr] = lit ? 1.f : 0.f; hit[tr] = (uint8_t)lit;
+                len++;
+                if (lit) { lit_any = 1; break; }
+                p = h.p; n = h.n; idx = hi;
+                bounce++;
+            }
+        }
+        length[j] = len; hit_light[j] = (uint8_t)lit_any;
+    }
+    if (stats) {
+        flush_stats(stats, STAT_QUERIES, n_query);
+        flush_stats(stats, STAT_SPHERE_TESTS, n_tests);
+        flush_stats(stats, STAT_AABB_TESTS, n_boxes);
+    }
+}
+
 // ------------------------------------------------------------------ resolve
 // pixel // spp then min(1, /255) (chandelier.py:540-549; output5.py:1500-1512)
 template <typename T>
@@ -829,6 +945,19 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
 }
 
 template <typename T>
+cudaError_t launch_trajectories(const SceneDev<T> &sc, int n_traj, int max_steps, int max_bounces, uint64_t seed, float *obs,
+                                float *action, float *next_obs, float *reward, uint8_t *hit, int *length,
+                                uint8_t *hit_light, unsigned long long *stats, cudaStream_t st) {
+    if (n_traj <= 0) return cudaSuccess;
+    const int block = 128, grid = (n_traj + block - 1) / block;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, trajectory_kernel, grid, block, smem_for(sc), st, sc, n_traj, max_steps, max_bounces, k0, k1, obs,
+                     action, next_obs, reward, hit, length, hit_light, stats);
+    return cudaGetLastError();
+}
+
+template <typename T>
 cudaError_t launch_simple(const SceneDev<T> &sc, const SimpleDev<T> &sp, int4 *rgb, float *image, unsigned long long *stats,
                           cudaStream_t st) {
     if (sp.n <= 0) return cudaSuccess;
@@ -905,6 +1034,8 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
                                         cudaStream_t);                                                                  \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \
+    template cudaError_t launch_trajectories<T>(const SceneDev<T> &, int, int, int, uint64_t, float *, float *, float *,  \
+                                                float *, uint8_t *, int *, uint8_t *, unsigned long long *, cudaStream_t); \
     template cudaError_t launch_simple<T>(const SceneDev<T> &, const SimpleDev<T> &, int4 *, float *,                   \
                                           unsigned long long *, cudaStream_t);                                         \
     template cudaError_t launch_sphere_disc<T>(int, const double *, const double *, int, double *, cudaStream_t);       \

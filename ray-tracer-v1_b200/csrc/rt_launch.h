@@ -58,6 +58,10 @@ template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
                         cudaStream_t st);
 template <typename T>
+cudaError_t launch_trajectories(const SceneDev<T> &sc, int n_traj, int max_steps, int max_bounces, uint64_t seed, float *obs,
+                                float *action, float *next_obs, float *reward, uint8_t *hit, int *length,
+                                uint8_t *hit_light, unsigned long long *stats, cudaStream_t st);
+template <typename T>
 cudaError_t launch_simple(const SceneDev<T> &sc, const SimpleDev<T> &sp, int4 *rgb, float *image, unsigned long long *stats,
                           cudaStream_t st);
 template <typename T>

@@ -196,3 +196,36 @@ def test_render_entry_points(rt, orc):
     c.small_lights = [s for s in c.light_sources if s.radius < 0.5]
     im = c.render(96, 54, samples_per_pixel=2, max_bounces=5)
     assert im.shape == (54, 96, 3) and im.dtype == np.float32 and 5.0 < c.stats["total_rays"] / (96 * 54 * 2) <= 6.0
+
+
+def test_fb_trajectories_match_reference(rt, orc):
+    """rt_generate_trajectories vs the reference-generated golden walks (FP64: same path, observations to float32
+    rounding of a 1-ulp libm difference) and vs the oracle at a larger batch; FP32: same walk for most trajectories."""
+    from conftest import load_golden
+    from ray_tracer_v1_b200 import fb_trajectories as fbt
+    z, fs = load_golden("traj_complex_256")
+    S, mb, seed = int(z["max_steps"]), int(z["max_bounces"]), int(z["seed"])
+    b = fbt.generate_trajectories(fs, 256, S, mb, seed, precision="f64")
+    assert np.array_equal(b.length.cpu().numpy(), z["length"]) and np.array_equal(b.hit_light.cpu().numpy(), z["hit_light"].astype(bool))
+    assert np.array_equal(b.hit.cpu().numpy(), z["hit"].astype(bool)) and np.array_equal(b.reward.cpu().numpy(), z["reward"])
+    for k, t in (("obs", b.obs), ("action", b.action), ("next_obs", b.next_obs)):
+        np.testing.assert_allclose(t.cpu().numpy(), z[k], rtol=2e-6, atol=2e-6, err_msg=k)
+    j = int(np.argmax(z["length"]))
+    tr = b.transitions(j)
+    assert len(tr) == int(z["length"][j]) > 0 and tr[0][0].shape == (22,) and tr[0][1].shape == (2,)
+    big = fbt.generate_trajectories(fs, 20000, S, mb, seed + 1, precision="f64")
+    ref = orc.generate_trajectories(fs, 20000, S, mb, seed + 1)
+    assert np.array_equal(big.length.cpu().numpy(), ref["length"]) and np.array_equal(big.hit_light.cpu().numpy(), ref["hit_light"].astype(bool))
+    np.testing.assert_allclose(big.next_obs.cpu().numpy(), ref["next_obs"], rtol=2e-6, atol=2e-6)
+    f32 = fbt.generate_trajectories(fs, 20000, S, mb, seed + 1, precision="f32")
+    same = f32.length.cpu().numpy() == ref["length"]
+    assert same.mean() > 0.97
+    # FP32 rounding is amplified at every bounce off a curved surface: the first transition is tight, the whole
+    # walk (up to 8 bounces) stays close for most trajectories
+    d = np.abs(f32.next_obs.cpu().numpy()[same] - ref["next_obs"][same])
+    assert (d[:, 0].max(axis=1) < 2e-3).mean() > 0.97
+    assert (d.max(axis=(1, 2)) < 5e-2).mean() > 0.9
+    o, a, no, r, h = f32.flat()
+    assert o.shape[0] == int(f32.length.sum()) and f32.queries >= o.shape[0]
+    one, lit = fbt.generate_trajectory(fs, S, mb, seed=seed + 1)
+    assert isinstance(lit, bool) and len(one) == int(f32.length[0])

@@ -149,3 +149,13 @@ def test_output6_frames(orc, name):
     rays = np.concatenate([np.tile([0.0, 0.0, 1.0], (W * H, 1)), d], axis=1)
     rgb2, _ = orc.render_simple(fs, W, H, seed=int(z["seed"]), max_bounces=int(z["max_bounces"]), rays=rays)
     assert (rgb2.reshape(H, W, 3) != rgb).any(axis=2).mean() < 0.002      # vnorm in numpy vs C: last-ulp flips only
+
+
+def test_fb_trajectories(orc):
+    """FB/train_complex_only.py generate_trajectory run by the reference itself (random.* patched to the Philox
+    stream): 256 random walks on the complex scene, every transition bit for bit."""
+    z, fs = load_golden("traj_complex_256")
+    o = orc.generate_trajectories(fs, 256, int(z["max_steps"]), int(z["max_bounces"]), int(z["seed"]))
+    assert int(o["length"].sum()) > 1000 and int(o["hit_light"].sum()) > 5
+    for k in ("length", "hit_light", "obs", "action", "next_obs", "reward", "hit"):
+        assert np.array_equal(o[k], z[k]), k
