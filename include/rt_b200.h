@@ -278,6 +278,9 @@ typedef struct rt_env_desc {
     int32_t max_bounces;
     int32_t flavour;        /* RT_ENV_RL | RT_ENV_FB */
     int32_t sun_id;         /* FB flavour: 7 (FB/ray_tracer_env.py:256) */
+    int32_t reward_mode;    /* RL flavour: 0 = RayTracerEnv._calculate_reward, 1 = AdaptiveRewardRayTracerEnv
+                               (RL/train_raytracer_optimized.py:25-61: light / mirror bonuses, short-path penalty) */
+    int32_t light_ids[2];   /* reward_mode 1: self.light_ids = [99, 100] (:21) */
 } rt_env_desc;
 int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out);
 int rt_env_destroy(rt_env *env);

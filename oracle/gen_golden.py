@@ -92,6 +92,8 @@ def load_reference():
     sys.modules["complex_scene"] = cs
     ref.complex = _load("ref_complex", REF / "FB" / "fb_vs_traditional_complex.py")
     ref.improved = _load("ref_improved", REF / "RL" / "train_raytracer_improved.py")
+    sys.modules["ray_tracer_env"] = ref.env_rl          # train_raytracer_optimized.py: `from ray_tracer_env import RayTracerEnv`
+    ref.optimized = _load("ref_optimized", REF / "RL" / "train_raytracer_optimized.py")
     return ref
 
 
@@ -328,9 +330,14 @@ def gen_env(ref):
     balls.camera = (0.0, 0.0, 1.0)
     cases.append(("fb_balls", "fb", balls, (0, 0, 0)))
     cases.append(("rl_balls_rotated", "rl", balls, (0.1, -0.05, 0.02)))
+    cases.append(("rl_adaptive", "rl", opt, (0, 0, 0)))            # AdaptiveRewardRayTracerEnv on its own training scene
     B = 96
+    only = os.environ.get("GEN_ENV_ONLY")
     for name, flavour, spec, angle in cases:
+        if only and name != only:
+            continue
         mod = ref.env_fb if flavour == "fb" else ref.env_rl
+        cls = ref.optimized.AdaptiveRewardRayTracerEnv if name == "rl_adaptive" else mod.RayTracerEnv
         rs = np.random.RandomState(abs(hash(name)) % 2 ** 31 if False else sum(map(ord, name)))
         pixels = np.stack([rs.randint(0, spec.width, B), rs.randint(0, spec.height, B)], 1).astype(np.int32)
         pixels[0] = (spec.width // 2, spec.height // 2)
@@ -346,10 +353,10 @@ def gen_env(ref):
         total = np.zeros((T, B))
         for b in range(B):
             with contextlib.redirect_stdout(io.StringIO()):
-                env = mod.RayTracerEnv(spheres=spec.spheres, image_width=spec.width, image_height=spec.height,
-                                       camera_position=V(*spec.camera), camera_angle=A(*angle), fov=spec.fov,
-                                       max_bounces=spec.max_bounces, background_colour=spec.background,
-                                       global_light_sources=spec.global_lights, point_light_sources=spec.point_lights)
+                env = cls(spheres=spec.spheres, image_width=spec.width, image_height=spec.height,
+                          camera_position=V(*spec.camera), camera_angle=A(*angle), fov=spec.fov,
+                          max_bounces=spec.max_bounces, background_colour=spec.background,
+                          global_light_sources=spec.global_lights, point_light_sources=spec.point_lights)
                 obs0[b], _ = env.reset(options={"pixel": (int(pixels[b, 0]), int(pixels[b, 1]))})
                 for t in range(T):      # keeps stepping after termination, like a careless caller would
                     o, r, te, tr, info = env.step(actions[t, b])

@@ -40,7 +40,8 @@ class _Scene(C.Structure):
 
 class _EnvCfg(C.Structure):
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("max_bounces", C.c_int32), ("flavour", C.c_int32),
-                ("cam", C.c_double * 3), ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("sun_id", C.c_int32)]
+                ("cam", C.c_double * 3), ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("sun_id", C.c_int32),
+                ("adaptive", C.c_int32), ("light_ids", C.c_int32 * 2)]
 
 
 class _SimpleCfg(C.Structure):
@@ -270,7 +271,7 @@ class OracleEnv:
     """Batched RayTracerEnv (flavour 'rl' = RL/ray_tracer_env.py, 'fb' = FB/ray_tracer_env.py)."""
 
     def __init__(self, fs, B, width, height, camera=(0, 0, 0), camera_angle=(0, 0, 0), fov=90, max_bounces=5,
-                 flavour="rl", sun_id=7):
+                 flavour="rl", sun_id=7, adaptive=False, light_ids=(99, 100)):
         self.sc = _scene(fs)
         self.B = int(B)
         cfg = self.cfg = _EnvCfg()
@@ -278,6 +279,8 @@ class OracleEnv:
         cfg.cam[:] = [float(x) for x in camera]
         cfg.cam_angle[:] = [float(x) for x in camera_angle]
         cfg.fov, cfg.sun_id = float(fov), int(sun_id)
+        cfg.adaptive = int(bool(adaptive))
+        cfg.light_ids[:] = [int(light_ids[0]), int(light_ids[1])]
         self.state = np.zeros(self.B * lib().orc_sizeof_env(), np.uint8)
 
     def reset(self, pixels):

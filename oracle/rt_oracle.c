@@ -674,12 +674,15 @@ typedef struct {
     double p[3], n[3], d[3];      /* current_intersection.point/.normal, current_ray.D */
     double acc[3];                /* accumulated_color */
     double total_reward;
+    int32_t consec, total_hits;   /* AdaptiveRewardRayTracerEnv.consecutive_light_hits / total_light_hits */
 } orc_env;
 
 typedef struct {
     int32_t W, H, max_bounces, flavour;   /* flavour 0 = RL/ray_tracer_env.py, 1 = FB/ray_tracer_env.py */
     double cam[3], cam_angle[3], fov;
     int32_t sun_id;                        /* FB flavour: hard-coded 7 (FB/ray_tracer_env.py:256,419,460) */
+    int32_t adaptive;                      /* 1: AdaptiveRewardRayTracerEnv (RL/train_raytracer_optimized.py:16-67) */
+    int32_t light_ids[2];                  /* self.light_ids = [99, 100] (:21) */
 } orc_env_cfg;
 
 enum { R_NONE = 0, R_RAY_MISSED = 1, R_RAY_ESCAPED = 2, R_MAX_BOUNCES = 3, R_HIT_SUN = 4, R_ALREADY_ON_SUN = 5 };
@@ -711,6 +714,24 @@ static double env_reward(const orc_scene *s, const orc_env_cfg *cfg, const isect
     return brightness + pen;
 }
 
+/* AdaptiveRewardRayTracerEnv._calculate_reward: RL/train_raytracer_optimized.py:25-61 */
+static double env_reward_adaptive(const orc_scene *s, const orc_env_cfg *cfg, orc_env *e, const isect *h, int bounce_count) {
+    if (!h->hit) return -0.5;
+    double base = env_reward(s, cfg, h, bounce_count);
+    double light_bonus = 0, reflective_bonus = 0, path_length_penalty = 0;
+    int id = s->ids[h->idx];
+    if (id == cfg->light_ids[0] || id == cfg->light_ids[1]) {
+        light_bonus = 2.0; e->consec += 1; e->total_hits += 1;
+        if (e->consec > 1) light_bonus += 0.5 * e->consec;
+    } else e->consec = 0;
+    if (s->material[4 * h->idx] > 0.5) reflective_bonus = 0.3;
+    if (bounce_count < 2 && base > 0) path_length_penalty = -0.1;
+    return base + light_bonus + reflective_bonus + path_length_penalty;
+}
+static double env_reward_rl(const orc_scene *s, const orc_env_cfg *cfg, orc_env *e, const isect *h, int bounce_count) {
+    return cfg->adaptive ? env_reward_adaptive(s, cfg, e, h, bounce_count) : env_reward(s, cfg, h, bounce_count);
+}
+
 /* FB/ray_tracer_env.py:280-336 */
 static double env_lighting_reward(const orc_scene *s, const orc_env_cfg *cfg, const isect *h) {
     if (!h->hit) return 0.0;
@@ -736,7 +757,10 @@ static double env_lighting_reward(const orc_scene *s, const orc_env_cfg *cfg, co
 ORC_API void orc_env_reset(const orc_scene *s, const orc_env_cfg *cfg, int B, const int32_t *pixels /*[B,2]*/,
                            orc_env *env, float *obs /*[B,18]*/) {
     for (int b = 0; b < B; ++b) {
-        orc_env *e = env + b; memset(e, 0, sizeof *e);
+        orc_env *e = env + b;
+        int32_t keep = e->total_hits;                /* total_light_hits survives reset (train_raytracer_optimized.py:63-66) */
+        memset(e, 0, sizeof *e);
+        e->total_hits = keep;
         double aspect = (double)cfg->W / (double)cfg->H;
         double fr = cfg->fov * M_PI / 180;
         double px = (2 * (pixels[2 * b] + 0.5) / cfg->W - 1) * aspect * tan(fr / 2);
@@ -766,7 +790,7 @@ ORC_API void orc_env_step(const orc_scene *s, const orc_env_cfg *cfg, int B, con
             env_obs(s, e, obs + 18 * b); continue;
         }
         if (e->bounce_count >= cfg->max_bounces) {                   /* :325-337 */
-            double fr = cfg->flavour == 1 ? env_lighting_reward(s, cfg, &cur) : env_reward(s, cfg, &cur, e->bounce_count);
+            double fr = cfg->flavour == 1 ? env_lighting_reward(s, cfg, &cur) : env_reward_rl(s, cfg, e, &cur, e->bounce_count);
             e->total_reward += fr; reason[b] = R_MAX_BOUNCES; reward[b] = fr; terminated[b] = 1; truncated[b] = 1;
             env_obs(s, e, obs + 18 * b); continue;
         }
@@ -788,7 +812,7 @@ ORC_API void orc_env_step(const orc_scene *s, const orc_env_cfg *cfg, int B, con
         e->bounce_count += 1;
         isect nx = trace_terminal(s, cur.p, D, s->ids[e->idx], e->bounce_count, cfg->max_bounces, e->through_count);
         double rw; int term = 0;
-        if (cfg->flavour == 0) rw = env_reward(s, cfg, &cur, e->bounce_count);   /* reward at the PRE-update hit, :362 */
+        if (cfg->flavour == 0) rw = env_reward_rl(s, cfg, e, &cur, e->bounce_count);   /* reward at the PRE-update hit, :362 */
         else if (nx.hit) {
             if (s->ids[nx.idx] == cfg->sun_id) { rw = 10.0; reason[b] = R_HIT_SUN; term = 1; }
             else rw = env_lighting_reward(s, cfg, &nx);

@@ -811,6 +811,9 @@ template <typename T> static void bind_env(EnvDev<T> &e, const rt_env_desc &d, v
     e.bounce = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.through = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.episode = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.consec = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.total_hits = reinterpret_cast<int *>(p); p += B * sizeof(int);
+    e.adaptive = d.reward_mode == 1; e.light0 = d.light_ids[0]; e.light1 = d.light_ids[1];
 }
 
 RT_EXPORT int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out) {
@@ -824,7 +827,7 @@ RT_EXPORT int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *d
     if (!env) return fail(RT_ERR_NOMEM, "host allocation failed");
     env->scene = scene; env->precision = precision; env->desc = *desc;
     const size_t B = (size_t)desc->B, el = precision == RT_F64 ? sizeof(double) : sizeof(float);
-    const size_t bytes = B * sizeof(double) + 12 * B * el + 5 * B * sizeof(int);
+    const size_t bytes = B * sizeof(double) + 12 * B * el + 7 * B * sizeof(int);
     cudaError_t e = cudaMalloc(&env->blob, bytes);
     if (e != cudaSuccess) { delete env; cudaGetLastError(); return e == cudaErrorMemoryAllocation ? fail(RT_ERR_NOMEM, "out of device memory") : cuda_fail(e, "cudaMalloc"); }
     e = cudaMemset(env->blob, 0, bytes);

@@ -713,8 +713,8 @@ template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, i
 
 // RL _calculate_reward (RL/ray_tracer_env.py:224-252); FB _calculate_reward (FB/ray_tracer_env.py:241-278)
 template <typename T, bool kBvh>
-RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, const Hit<T> &h, int bounce_count,
-                         Counters &ct) {
+RT_DEV double env_reward_base(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, const Hit<T> &h, int bounce_count,
+                              Counters &ct) {
     if (h.idx < 0) return -0.1;
     if (e.flavour == 1 && g.sv.ids[h.idx] == e.sun_id) return 10.0;
     T c[3];
@@ -726,6 +726,25 @@ RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> 
     } else {
         return (double)((c[0] + c[1] + c[2]) * (1.f / 765.f) - 0.01f * (float)bounce_count);
     }
+}
+// + AdaptiveRewardRayTracerEnv._calculate_reward (RL/train_raytracer_optimized.py:25-61) when e.adaptive
+template <typename T, bool kBvh>
+RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, int b, const Hit<T> &h, int bounce_count,
+                         Counters &ct) {
+    if (!e.adaptive) return env_reward_base<T, kBvh>(g, la, e, h, bounce_count, ct);
+    if (h.idx < 0) return -0.5;
+    const double base = env_reward_base<T, kBvh>(g, la, e, h, bounce_count, ct);
+    double light_bonus = 0.0, reflective_bonus = 0.0, path_length_penalty = 0.0;
+    const int id = g.sv.ids[h.idx];
+    if (id == e.light0 || id == e.light1) {
+        light_bonus = 2.0;
+        const int c = e.consec[b] + 1;
+        e.consec[b] = c; e.total_hits[b] += 1;
+        if (c > 1) light_bonus += 0.5 * c;
+    } else e.consec[b] = 0;
+    if (g.sv.mat[h.idx].x > T(0.5)) reflective_bonus = 0.3;
+    if (bounce_count < 2 && base > 0.0) path_length_penalty = -0.1;
+    return base + light_bonus + reflective_bonus + path_length_penalty;
 }
 
 // FB _calculate_lighting_reward (FB/ray_tracer_env.py:280-336)
@@ -785,7 +804,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         d = normalise(d);
         Hit<T> h = trace_terminal<T, kBvh>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
         env_store_hit<T>(e, b, h, d);
-        e.bounce[b] = 0; e.through[b] = 0;
+        e.bounce[b] = 0; e.through[b] = 0; e.consec[b] = 0;
         e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
         e.total[b] = 0.0;
         env_obs<T>(S.g, e, b, obs);
@@ -816,7 +835,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
         if (cur.idx < 0) {                                                   // ray already missed, :313-323
             rsn = 1; rw = -1.0; term = 1; info_total = e.total[b];
         } else if (bc >= e.max_bounces) {                                    // :325-337
-            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T, kBvh>(S.g, S.la, e, cur, bc, ct);
+            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T, kBvh>(S.g, S.la, e, b, cur, bc, ct);
             e.total[b] += rw; info_total = e.total[b];
             rsn = 3; term = 1; trunc = 1;
         } else if (e.flavour == 1 && S.g.sv.ids[cur.idx] == e.sun_id) {      // FB :417-431 (total_reward not updated)
@@ -840,7 +859,7 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
             if constexpr (M<T>::exact) D = normalise(D);                      // Ray() normalises again
             bc += 1;
             Hit<T> nx = trace_terminal<T, kBvh>(S.g, cur.p, D, S.g.sv.ids[cur.idx], bc, e.max_bounces, through, ct);
-            if (e.flavour == 0) rw = env_reward<T, kBvh>(S.g, S.la, e, cur, bc, ct);    // reward at the PRE-update hit, :362
+            if (e.flavour == 0) rw = env_reward<T, kBvh>(S.g, S.la, e, b, cur, bc, ct);    // reward at the PRE-update hit, :362
             else if (nx.idx >= 0) {
                 if (S.g.sv.ids[nx.idx] == e.sun_id) { rw = 10.0; rsn = 4; term = 1; info_sun = 1.0; }
                 else { rw = env_lighting_reward<T>(S.g, e, nx); info_sun = 0.0; }

@@ -46,7 +46,8 @@ template <typename T> struct SimpleDev {
 template <typename T> struct EnvDev {
     int B, W, H, max_bounces, flavour, sun_id;
     T cam[3], cam_angle[3], tan_half;
-    int *has_hit, *idx, *bounce, *through, *episode;
+    int adaptive, light0, light1;                    // AdaptiveRewardRayTracerEnv (rt_env_desc::reward_mode)
+    int *has_hit, *idx, *bounce, *through, *episode, *consec, *total_hits;
     T *p, *n, *d, *acc;
     double *total;
 };

@@ -24,7 +24,7 @@ from .colour import Colour
 from .scene import flatten_scene
 from .vector import Angle, Vector
 
-__all__ = ["BatchedRayTracerEnv", "RayTracerEnv", "FBRayTracerEnv", "Box"]
+__all__ = ["AdaptiveRewardRayTracerEnv", "RayTracerVecEnv", "BatchedRayTracerEnv", "RayTracerEnv", "FBRayTracerEnv", "Box"]
 
 OBS_DIM = 18
 
@@ -82,7 +82,7 @@ class BatchedRayTracerEnv:
     def __init__(self, spheres, n_envs, image_width=800, image_height=600, camera_position=Vector(0, 0, 0),
                  camera_angle=Angle(0, 0, 0), fov=90, max_bounces=5, background_colour=Colour(0, 0, 0),
                  global_light_sources=None, point_light_sources=None, flavour="rl", sun_id=7, precision="f32",
-                 device=0, seed=0):
+                 device=0, seed=0, reward_mode="default", light_ids=(99, 100)):
         import torch
         self.torch = torch
         self.spheres = spheres
@@ -96,6 +96,11 @@ class BatchedRayTracerEnv:
         if flavour not in ("rl", "fb"):
             raise ValueError("flavour must be 'rl' or 'fb'")
         self.flavour, self.sun_id = flavour, int(sun_id)
+        if reward_mode not in ("default", "adaptive"):
+            raise ValueError("reward_mode must be 'default' or 'adaptive'")
+        if reward_mode == "adaptive" and flavour != "rl":
+            raise ValueError("the adaptive reward (RL/train_raytracer_optimized.py) shapes the RL flavour's reward")
+        self.reward_mode, self.light_ids = reward_mode, (int(light_ids[0]), int(light_ids[1]))
         self.precision = nat.F64 if precision in ("f64", "fp64", "float64", "double", nat.F64) and precision != nat.F32 else nat.F32
         self.device = int(device)
         self.seed = int(seed)
@@ -149,6 +154,8 @@ class BatchedRayTracerEnv:
             d.cam_angle[:] = _xyz(self.camera_angle)
             d.fov, d.max_bounces = float(self.fov), self.max_bounces
             d.flavour, d.sun_id = (nat.ENV_FB if self.flavour == "fb" else nat.ENV_RL), self.sun_id
+            d.reward_mode = 1 if self.reward_mode == "adaptive" else 0
+            d.light_ids[:] = self.light_ids
             h = C.c_void_p()
             nat.check(nat.lib().rt_env_create(self.scene.handle, self.precision, C.byref(d), C.byref(h)))
             self.handle = h.value
@@ -236,6 +243,7 @@ class RayTracerEnv(_EnvBase):
 
     metadata = {"render_modes": ["rgb_array"], "render_fps": 30}
     flavour = "rl"
+    reward_mode = "default"
 
     def __init__(self, spheres=None, image_width=800, image_height=600, camera_position=Vector(0, 0, 0),
                  camera_angle=Angle(0, 0, 0), fov=90, max_bounces=5, background_colour=Colour(0, 0, 0),
@@ -262,7 +270,8 @@ class RayTracerEnv(_EnvBase):
         self._batch = BatchedRayTracerEnv(self.spheres, 1, image_width, image_height, camera_position, camera_angle, fov,
                                           max_bounces, background_colour, self.global_light_sources,
                                           self.point_light_sources, flavour=self.flavour, precision=precision,
-                                          device=device)
+                                          device=device, reward_mode=self.reward_mode,
+                                          light_ids=getattr(self, "light_ids", (99, 100)))
 
     # pinhole camera of the reference (RL/ray_tracer_env.py:121-142), host-side copy for info['initial_ray'] only
     def _get_initial_ray(self, pixel_x, pixel_y):
@@ -348,6 +357,105 @@ class RayTracerEnv(_EnvBase):
         self._batch.close()
 
 
+class AdaptiveRewardRayTracerEnv(RayTracerEnv):
+    """Drop-in for ``AdaptiveRewardRayTracerEnv`` (RL/train_raytracer_optimized.py:16-67): the RL reward plus a bonus for
+    standing on a light (growing with consecutive hits), a bonus for mirrors and a short-path penalty."""
+    reward_mode = "adaptive"
+
+    def __init__(self, *args, **kwargs):
+        self.light_ids = [99, 100]
+        self.consecutive_light_hits = 0
+        self.total_light_hits = 0
+        super().__init__(*args, **kwargs)
+
+
 class FBRayTracerEnv(RayTracerEnv):
     """Scalar drop-in for ``FB/ray_tracer_env.RayTracerEnv``: actions in [-1,1]^2, sun id 7, lighting reward."""
     flavour = "fb"
+
+
+# ---- vectorised adapter (SURVEY.md 8f-3) -----------------------------------------------------------------------------
+try:                                    # subclass SB3's VecEnv when stable_baselines3 is installed (it is optional)
+    from stable_baselines3.common.vec_env import VecEnv as _VecEnvBase
+except Exception:                       # pragma: no cover - depends on the image
+    _VecEnvBase = object
+
+
+class RayTracerVecEnv(_VecEnvBase):
+    """``n_envs`` ray-tracer environments behind the Stable-Baselines3 ``VecEnv`` protocol, stepped by ONE kernel launch.
+
+    The reference trains PPO/SAC through ``DummyVecEnv([lambda: RayTracerEnv(...)])`` (RL/train_raytracer.py:128-147),
+    i.e. one Python env; this adapter gives the same agents 65,536 of them.  Protocol kept from SB3: ``reset()`` -> obs
+    [n,18]; ``step(actions)`` (or ``step_async`` + ``step_wait``) -> ``(obs, rewards, dones, infos)`` where finished
+    episodes are reset automatically -- the returned observation is the first one of the new episode and
+    ``infos[i]['terminal_observation']`` holds the last one of the old, ``infos[i]['TimeLimit.truncated']`` its
+    truncation flag.  ``as_torch=True`` returns CUDA tensors and a dict of tensors instead of numpy arrays and a list
+    of dicts (no device->host copy on the rollout path)."""
+
+    def __init__(self, spheres, n_envs, as_torch=False, **env_kwargs):
+        self.env = BatchedRayTracerEnv(spheres, n_envs, **env_kwargs)
+        self.num_envs = int(n_envs)
+        self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
+        self.as_torch = bool(as_torch)
+        self.render_mode = None
+        self._actions = None
+        self._seed = env_kwargs.get("seed", 0)
+        self.episode_returns = None
+
+    def seed(self, seed=None):
+        self._seed = 0 if seed is None else int(seed)
+        return [self._seed + i for i in range(self.num_envs)]
+
+    def reset(self):
+        obs, _ = self.env.reset(seed=self._seed)
+        self._seed += 1
+        return obs.clone() if self.as_torch else obs.cpu().numpy().copy()
+
+    def step_async(self, actions):
+        self._actions = actions
+
+    def step_wait(self):
+        torch = self.env.torch
+        obs, rew, term, trunc, binfo = self.env.step(self._actions)
+        dones = term | trunc
+        rew = rew.clone()
+        last_obs = obs.clone()
+        trunc_now = trunc.clone()
+        reason = binfo["reason"].clone()
+        total = binfo["total_reward"].clone()
+        if bool(dones.any()):
+            obs, _ = self.env.reset(mask=dones.to(torch.uint8))            # only the finished episodes restart
+        if self.as_torch:
+            infos = {"terminal_observation": last_obs, "TimeLimit.truncated": trunc_now, "reason": reason,
+                     "total_reward": total, "done": dones}
+            return obs.clone(), rew.to(torch.float32), dones, infos
+        d = dones.cpu().numpy()
+        lo, tn, rs, tt = last_obs.cpu().numpy(), trunc_now.cpu().numpy(), reason.cpu().numpy(), total.cpu().numpy()
+        infos = [{} for _ in range(self.num_envs)]
+        for i in np.nonzero(d)[0]:
+            infos[i] = {"terminal_observation": lo[i].copy(), "TimeLimit.truncated": bool(tn[i]),
+                        "reason": nat.REASONS[int(rs[i])], "episode": {"r": float(tt[i])}}
+        return obs.cpu().numpy().copy(), rew.cpu().numpy().astype(np.float32), d, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self):
+        self.env.close()
+
+    # the rest of the VecEnv protocol, for wrappers that probe it
+    def get_attr(self, attr_name, indices=None):
+        return [getattr(self.env, attr_name)] * self.num_envs
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self.env, attr_name, value)
+
+    def env_method(self, method_name, *method_args, indices=None, **method_kwargs):
+        return [getattr(self.env, method_name)(*method_args, **method_kwargs)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False] * self.num_envs
+
+    def get_images(self):
+        return []

@@ -8,20 +8,22 @@ from conftest import load_golden
 
 pytestmark = pytest.mark.gpu
 
-ENVS = ["env_rl_optimized", "env_rl_demo", "env_fb_demo", "env_fb_balls", "env_rl_balls_rotated"]
+ENVS = ["env_rl_optimized", "env_rl_demo", "env_fb_demo", "env_fb_balls", "env_rl_balls_rotated", "env_rl_adaptive"]
 
 
 def make_env(rt, z, fs, B, precision):
     from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
     return BatchedRayTracerEnv(fs, B, int(z["width"]), int(z["height"]), camera_position=tuple(z["cam"]),
                                camera_angle=tuple(z["cam_angle"]), fov=float(z["fov"]), max_bounces=int(z["max_bounces"]),
-                               flavour=str(z["flavour"]), precision=precision)
+                               flavour=str(z["flavour"]), precision=precision,
+                               reward_mode="adaptive" if "adaptive" in str(z.get("name", "")) else "default")
 
 
 @pytest.mark.parametrize("name", ENVS)
 def test_batched_env_matches_reference_rollouts(rt, name):
     """Rollouts recorded from the UNMODIFIED reference env (96 episodes x T steps, stepping on past termination)."""
     z, fs = load_golden(name)
+    z["name"] = name
     B = z["pixels"].shape[0]
     env = make_env(rt, z, fs, B, "f64")
     obs0, _ = env.reset(options={"pixels": z["pixels"]})
@@ -41,9 +43,11 @@ def test_batched_env_matches_reference_rollouts(rt, name):
 @pytest.mark.parametrize("name", ENVS)
 def test_batched_env_fp64_equals_oracle_and_fp32_is_close(rt, orc, name):
     z, fs = load_golden(name)
+    z["name"] = name
     B = z["pixels"].shape[0]
     ref = orc.OracleEnv(fs, B, int(z["width"]), int(z["height"]), camera=z["cam"], camera_angle=z["cam_angle"],
-                        fov=float(z["fov"]), max_bounces=int(z["max_bounces"]), flavour=str(z["flavour"]))
+                        fov=float(z["fov"]), max_bounces=int(z["max_bounces"]), flavour=str(z["flavour"]),
+                        adaptive="adaptive" in name)
     e64, e32 = make_env(rt, z, fs, B, "f64"), make_env(rt, z, fs, B, "f32")
     o_ref = ref.reset(z["pixels"])
     o64, _ = e64.reset(options={"pixels": z["pixels"]})
@@ -229,3 +233,44 @@ def test_fb_trajectories_match_reference(rt, orc):
     assert o.shape[0] == int(f32.length.sum()) and f32.queries >= o.shape[0]
     one, lit = fbt.generate_trajectory(fs, S, mb, seed=seed + 1)
     assert isinstance(lit, bool) and len(one) == int(f32.length[0])
+
+
+def test_vec_env_adapter(rt):
+    """RayTracerVecEnv: the SB3 VecEnv protocol over the batched env -- auto-reset of finished episodes with
+    terminal_observation / TimeLimit.truncated, numpy and torch modes stepping the same episodes."""
+    import torch
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.ray_tracer_env import RayTracerVecEnv, AdaptiveRewardRayTracerEnv
+    spec = scenes.build_optimized_env_scene()
+    kw = dict(image_width=spec.width, image_height=spec.height, fov=spec.fov, max_bounces=spec.max_bounces,
+              background_colour=spec.background, point_light_sources=spec.point_lights, reward_mode="adaptive", seed=3)
+    n = 512
+    ve, vt = RayTracerVecEnv(spec.spheres, n, **kw), RayTracerVecEnv(spec.spheres, n, as_torch=True, **kw)
+    assert ve.num_envs == n and ve.observation_space.shape == (18,) and ve.action_space.shape == (2,)
+    o1, o2 = ve.reset(), vt.reset()
+    assert o1.shape == (n, 18) and o1.dtype == np.float32 and np.array_equal(o1, o2.cpu().numpy())
+    rs = np.random.RandomState(0)
+    finished = 0
+    for t in range(12):
+        a = rs.uniform((0, 0), (np.pi / 2, 2 * np.pi), (n, 2)).astype(np.float32)
+        obs, rew, dones, infos = ve.step(a)
+        tobs, trew, tdones, tinfos = vt.step(torch.as_tensor(a, device="cuda"))
+        assert obs.shape == (n, 18) and rew.shape == (n,) and rew.dtype == np.float32 and dones.dtype == bool and len(infos) == n
+        assert np.array_equal(obs, tobs.cpu().numpy()) and np.array_equal(dones, tdones.cpu().numpy())
+        np.testing.assert_allclose(rew, trew.cpu().numpy(), rtol=1e-6)
+        for i in np.nonzero(dones)[0][:8]:
+            assert infos[i]["terminal_observation"].shape == (18,) and "TimeLimit.truncated" in infos[i]
+            assert infos[i]["reason"] in ("ray_missed", "ray_escaped", "max_bounces")
+            assert np.array_equal(infos[i]["terminal_observation"], tinfos["terminal_observation"][i].cpu().numpy())
+        assert all(not infos[i] for i in np.nonzero(~dones)[0][:8])
+        finished += int(dones.sum())
+    assert finished > n                      # every env finished at least once and kept going: auto-reset works
+    ve.close(); vt.close()
+    # the scalar drop-in of the adaptive env shares the kernel: one episode, rewards as the batched env gives them
+    env = AdaptiveRewardRayTracerEnv(spheres=spec.spheres, image_width=spec.width, image_height=spec.height, fov=spec.fov,
+                                     max_bounces=spec.max_bounces, point_light_sources=spec.point_lights)
+    assert env.light_ids == [99, 100]
+    obs, info = env.reset(options={"pixel": (160, 140)})
+    o, r, term, trunc, info = env.step(np.array([0.3, 1.0], np.float32))
+    assert o.shape == (18,) and isinstance(r, float) and "total_reward" in info
+    env.close()

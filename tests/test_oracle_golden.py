@@ -107,7 +107,7 @@ def test_path_frames(orc, name):
     assert np.array_equal(parts, sums)
 
 
-ENVS = ["env_rl_optimized", "env_rl_demo", "env_fb_demo", "env_fb_balls", "env_rl_balls_rotated"]
+ENVS = ["env_rl_optimized", "env_rl_demo", "env_fb_demo", "env_fb_balls", "env_rl_balls_rotated", "env_rl_adaptive"]
 
 
 @pytest.mark.parametrize("name", ENVS)
@@ -115,7 +115,8 @@ def test_env_rollouts(orc, name):
     z, fs = load_golden(name)
     B = z["pixels"].shape[0]
     env = orc.OracleEnv(fs, B, int(z["width"]), int(z["height"]), camera=z["cam"], camera_angle=z["cam_angle"],
-                        fov=float(z["fov"]), max_bounces=int(z["max_bounces"]), flavour=str(z["flavour"]))
+                        fov=float(z["fov"]), max_bounces=int(z["max_bounces"]), flavour=str(z["flavour"]),
+                        adaptive=name.endswith("adaptive"))      # RL/train_raytracer_optimized.py AdaptiveRewardRayTracerEnv
     # The reference env hands the agent's float32 action straight into numpy trig (RL/ray_tracer_env.py:155-163),
     # so under NumPy>=2 promotion rules part of ITS arithmetic runs in float32; the double oracle therefore agrees
     # with it to float32 rounding (amplified by the trace), not to 1e-9.  Observations are float32 anyway.
