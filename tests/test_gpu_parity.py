@@ -405,3 +405,65 @@ def test_output6_dropin_class(rt, orc):
     r.fb_usage_prob = 0.5
     with pytest.raises(NotImplementedError):
         r.render_original_style(8, 8, output_path="")
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_cases_match_the_oracle(nat, orc):
+    """Empty scene, a scene without lights, one sphere, frames that are not tile multiples, depth 0 / 1, a sample
+    range longer than the integer accumulators allow, and the error codes of bad arguments."""
+    import ctypes as C
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    V, Col, M, S = pkg.Vector, pkg.Colour, pkg.Material, pkg.Sphere
+    cam = (0.0, 0.0, 5.0)
+
+    def both(fs, W, H, spp, depth, thr=0.0, seed=1):
+        sc = nat.DeviceScene(fs)
+        p = sc.path_params(cam, W, H, spp, depth, thr, seed=seed)
+        ref, st = orc.render_path(fs, cam, W, H, spp, depth, thr, seed=seed)
+        for prec in (nat.F64, nat.F32):
+            img, sums, stats = sc.render_path_host(p, prec)
+            if prec == nat.F64:
+                assert np.array_equal(sums[..., :3], ref), "FP64 path differs"
+                assert int(stats[0]) == st["total_rays"] and int(stats[1]) == st["total_intersections"]
+            else:
+                assert (np.abs(sums[..., :3] - ref).max(axis=2) > spp).mean() < 0.03
+            assert np.array_equal(sums[..., 3], np.full((H, W), spp))
+        sc.close()
+        return ref
+
+    empty = pkg.flatten_scene([], background_colour=Col(2, 2, 5))
+    r = both(empty, 33, 9, 3, 4)
+    assert np.array_equal(r, np.broadcast_to(np.array([2.0, 2.0, 5.0]) * 3, r.shape))       # every ray misses
+    matte = M(reflective=0, transparent=0, emitive=0, refractive_index=1)
+    lamp = M(reflective=0, transparent=0, emitive=1, refractive_index=1)
+    no_lights = pkg.flatten_scene([S(V(0, 0, 0), 1.0, matte, Col(200, 100, 50), id=1),
+                                   S(V(0, -101, 0), 100.0, matte, Col(90, 90, 90), id=2)], background_colour=Col(2, 2, 5))
+    both(no_lights, 37, 21, 2, 3)
+    one = pkg.flatten_scene([S(V(0, 0, 0), 1.5, lamp, Col(255, 240, 200), id=9)], background_colour=Col(2, 2, 5))
+    r = both(one, 31, 17, 1, 2)
+    assert r.max() == 255 and r.min() == 2
+    spec = scenes.build_chandelier()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    both(fs, 45, 13, 2, 0)          # max_bounces 0: every call returns at the depth check
+    both(fs, 45, 13, 2, 1)
+    # 9 spheres: the padded selection loop reads a second, mostly empty group
+    nine = pkg.flatten_scene(spec.spheres[:9], background_colour=spec.background)
+    both(nine, 40, 24, 2, 4)
+    # argument errors come back as status codes with a message, not as crashes
+    sc = nat.DeviceScene(fs)
+    p = sc.path_params(cam, 16, 16, 1, 40, 0.0)             # depth above RT_PATH_MAX_DEPTH
+    with pytest.raises(nat.NativeLibraryError, match="max_bounces"):
+        sc.render_path_host(p, nat.F32)
+    p = sc.path_params(cam, 16, 16, 1, 4, 0.0, rows=(8, 40))
+    with pytest.raises(nat.NativeLibraryError, match="row band"):
+        sc.render_path_host(p, nat.F32)
+    p = sc.path_params(cam, 16, 16, 1, 4, 0.0)
+    with pytest.raises(nat.NativeLibraryError):
+        sc.render_path_host(p, 7)                            # unknown precision
+    sink = nat.PathSink()
+    sink.mode = nat.SINK_IMAGE                               # no image pointer
+    with pytest.raises(nat.NativeLibraryError, match="image sink"):
+        sc.render_path_sink(p, sink)
+    assert nat.lib().rt_render_path(None, nat.F32, C.byref(p), None, None, None) != 0
+    sc.close()
