@@ -201,7 +201,8 @@ class BatchedRayTracerEnv:
                                         self.info.data_ptr(), self.stats.data_ptr(), None))
         info = {"bounce_count": self.info[:, 0], "through_count": self.info[:, 1], "total_reward": self.info[:, 2],
                 "hit_sun": self.info[:, 3], "reason": self.reason}
-        return self.obs, self.reward, self.terminated.bool(), self.truncated.bool(), info
+        # uint8 0/1 flags reinterpreted as bool: no conversion kernels on the rollout path
+        return self.obs, self.reward, self.terminated.view(torch.bool), self.truncated.view(torch.bool), info
 
     def close(self):
         if self.handle is not None:
