@@ -22,6 +22,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries ONE JSON line.  Libraries write banners to fd 1 behind Python's back (NCCL prints "NCCL version ..."
+# there whenever NCCL_DEBUG >= VERSION), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 
 import numpy as np  # noqa: E402
 
@@ -147,7 +152,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "rays_ref_compatible_per_s": r_tot / t_tot / 1e6, "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=JSON_OUT, flush=True)
     return 0
 
 
@@ -319,7 +324,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(fs, spec)
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
