@@ -210,6 +210,27 @@ int rt_generate_trajectories(rt_scene *scene, int precision, int32_t n_traj, int
                              uint8_t *hit_dev, int32_t *length_dev, uint8_t *hit_light_dev, uint64_t *stats_dev,
                              void *stream);
 
+/* ---- Algorithm B as a wavefront, for learned direction sampling: WorkingFBRenderer.trace_ray_fb / render
+ *      (FB/fb_vs_traditional_complex.py:487-640).  The reference calls fb_agent.choose_direction(obs22) per hit; here
+ *      the kernels stop at exactly that point, the caller's policy (a torch module) maps the observations of the paths
+ *      that ask to actions on the same stream, and the next kernel consumes them.  One frame (or a row band / sample
+ *      range of it, P = W * (y1-y0) * (s1-s0) <= max_paths path slots):
+ *          rt_wf_begin;  repeat max_bounces times { rt_wf_trace; actions[need] = policy(obs[need]); rt_wf_bounce };
+ *          rt_wf_finish (adds the folded path colours and sample counts into accum [H,W,4]).
+ *      fb_usage_prob = 0 reproduces rt_render_path bit for bit (FP64) with the same Philox streams. */
+typedef struct rt_wavefront rt_wavefront;
+int rt_wf_create(rt_scene *scene, int precision, int32_t max_paths, int32_t max_depth, rt_wavefront **out);
+int rt_wf_destroy(rt_wavefront *wf);
+int rt_wf_begin(rt_wavefront *wf, const rt_path_params *p, double fb_usage_prob, uint64_t *stats_dev, void *stream);
+/* obs_dev [P,22] float32 (rows of asking paths are written), need_dev [P] uint8 (1 = wants an action).
+ * stats_dev (optional) uint64[8] as rt_render_path plus [7] = fb_used. */
+int rt_wf_trace(rt_wavefront *wf, float *obs_dev, uint8_t *need_dev, uint64_t *stats_dev, void *stream);
+/* actions_dev [P,2] float32 in [-1,1]^2, read where need_dev is 1; live_dev (int32, zeroed by the caller) receives the
+ * number of paths still alive. */
+int rt_wf_bounce(rt_wavefront *wf, const uint8_t *need_dev, const float *actions_dev, uint64_t *stats_dev, int32_t *live_dev,
+                 void *stream);
+int rt_wf_finish(rt_wavefront *wf, void *accum_dev, void *stream);
+
 /* ---- fused multi-GPU sinks for Algorithm B frames ---------------------------------------------
  * One process per GPU; a rank's path kernel stores its result where it is needed -- its own accumulators, the
  * final image on the collecting rank, or the accumulators of the rank that owns the pixel -- through NVLink peer

@@ -423,6 +423,68 @@ def gen_simple(ref):
         print(f"simple_balls_{tag}", stats, "mean", rgb.mean(axis=(0, 1)))
 
 
+# ----------------------------------------------------------------- FB-guided Algorithm B (f-4)
+def test_policy(obs):
+    """The stand-in for ``fb_agent.choose_direction``: IEEE basic operations only (products with powers of two, adds,
+    clip), so numpy on the CPU and torch on the GPU give the same float32 bits.  Returned as float64 -- see
+    trace_path_fb in rt_oracle.c for why."""
+    o = np.asarray(obs, np.float32)
+    a0 = np.clip(o[6] * np.float32(0.5) + o[7] * np.float32(0.25) - np.float32(0.125), np.float32(-1), np.float32(1))
+    a1 = np.clip(o[8] * np.float32(0.5) + o[3] * np.float32(0.25) + o[16] * np.float32(0.5), np.float32(-1), np.float32(1))
+    return np.array([a0, a1], dtype=np.float64)
+
+
+def gen_fb(ref):
+    """WorkingFBRenderer.render (FB/fb_vs_traditional_complex.py:425-640), the reference's own class, with a stand-in
+    agent (the trained checkpoints are not in the reference) and np.random.random patched to the Philox streams."""
+    V = ref.ns.Vector
+    mod = ref.complex
+    spec = scenes.build_complex(ref.ns)
+    W, H, spp, depth, seed, prob = 40, 24, 3, 5, 41, 0.6
+    ctl = types.SimpleNamespace(n=0, phase=0, bounce=0, draws=0)
+
+    class Hooked(mod.WorkingFBRenderer):
+        def trace_ray_fb(self, ray, bounce_count=0, accumulated_color=ref.ns.Colour(0, 0, 0)):
+            if bounce_count == 0:
+                ctl.phase = 1
+            ctl.bounce, ctl.draws = bounce_count, 0
+            out = super().trace_ray_fb(ray, bounce_count, accumulated_color)
+            if bounce_count == 0:
+                sums[ctl.n // spp] += [out.r, out.g, out.b]
+                ctl.n += 1
+                ctl.phase, ctl.draws = 0, 0
+            return out
+
+    def fake_random():
+        pix, sm = ctl.n // spp, ctl.n % spp
+        k = ctl.draws
+        ctl.draws += 1
+        if ctl.phase == 0:                         # jitter x, y
+            assert k < 2
+            return orc.rng_pair(seed, pix, sm, 0)[k]
+        if k == 0:                                 # the use-FB decision
+            return (orc.philox([pix, sm, ctl.bounce, 0x52544642], [seed & 0xffffffff, seed >> 32])[0] >> 8) / 16777216.0
+        assert k < 3
+        return orc.rng_pair(seed, pix, sm, ctl.bounce + 1)[k - 1]
+
+    sums = np.zeros((W * H, 3))
+    r = Hooked(model_path=None, scene_small_lights=[s for s in spec.spheres if s.material.emitive and s.radius < 0.5],
+               camera_position=V(*spec.camera))
+    r.scene = spec.spheres
+    r.light_sources = [s for s in spec.spheres if s.material.emitive]
+    r.fb_agent = types.SimpleNamespace(choose_direction=test_policy)
+    r.fb_loaded, r.fb_usage_prob = True, prob
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), \
+            mock.patch.object(np.random, "random", fake_random), mock.patch.object(mod, "tqdm", lambda it, **k: it):
+        img = r.render(W, H, spp, depth)
+    stats = np.array([r.stats[k] for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits", "fb_used")],
+                     np.int64)
+    np.savez_compressed(OUT / "path_fb_complex_40x24.npz", image=img, sums=sums.reshape(H, W, 3).astype(np.float32), stats=stats,
+                        W=W, H=H, spp=spp, max_bounces=depth, seed=seed, mirror_threshold=0.9, fb_usage_prob=prob,
+                        cam=np.array(spec.camera), **flat_dict(flat(spec)))
+    print("path_fb_complex", stats)
+
+
 # ----------------------------------------------------------------- FB training trajectories (f-2)
 def gen_traj(ref):
     """RayTracedComplexTrainer.generate_trajectory (FB/train_complex_only.py:254-334), the reference's own method, with
@@ -479,10 +541,10 @@ def gen_traj(ref):
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     ref = load_reference()
-    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple", "traj"]
+    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple", "traj", "fb"]
     for w in which:
         {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env, "simple": gen_simple,
-         "traj": gen_traj}[w](ref)
+         "traj": gen_traj, "fb": gen_fb}[w](ref)
 
 
 if __name__ == "__main__":

@@ -49,6 +49,9 @@ class _SimpleCfg(C.Structure):
                 ("sun_id", C.c_int32), ("max_bounces", C.c_int32)]
 
 
+POLICY_FN = C.CFUNCTYPE(None, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p)
+
+
 def build(force=False):
     """Compile oracle/rt_oracle.c with the committed Makefile (gcc, a second or two)."""
     src = os.path.join(_HERE, "rt_oracle.c")
@@ -83,6 +86,8 @@ def lib():
                                            c_u64p, C.c_int]
         _lib.orc_generate_trajectories.argtypes = [C.POINTER(_Scene), C.c_int, C.c_int, C.c_int, C.c_uint64, c_fp, c_fp, c_fp,
                                                    c_fp, c_u8p, c_ip, c_u8p]
+        _lib.orc_render_path_fb.argtypes = [C.POINTER(_Scene), c_dp, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int,
+                                            C.c_double, C.c_double, C.c_uint64, POLICY_FN, C.c_void_p, c_dp, c_u64p]
         _lib.orc_sizeof_env.restype = C.c_int
         _lib.orc_max_threads.restype = C.c_int
     return _lib
@@ -258,6 +263,27 @@ def generate_trajectories(fs, n_traj, max_steps=8, max_bounces=8, seed=0):
                                     _p(out["next_obs"], c_fp), _p(out["reward"], c_fp), _p(out["hit"], c_u8p),
                                     _p(out["length"], c_ip), _p(out["hit_light"], c_u8p))
     return out
+
+
+def render_path_fb(fs, cam, W, H, spp, max_bounces, mirror_threshold, policy, fb_usage_prob=1.0, seed=0, fov=60.0,
+                   samples=None):
+    """WorkingFBRenderer.render (FB/fb_vs_traditional_complex.py:487-640): Algorithm B with ``policy(obs22 float32
+    array) -> action (2,)`` choosing the diffuse direction with probability ``fb_usage_prob`` (policy None = the
+    traditional renderer).  Returns (sum [H,W,3], stats dict incl. fb_used)."""
+    sc = _scene(fs)
+    s0, s1 = samples if samples is not None else (0, spp)
+    out = np.zeros((H, W, 3))
+    st = (C.c_uint64 * 6)()
+
+    def cb(obs, act, _user):
+        a = policy(np.ctypeslib.as_array(obs, shape=(22,)).copy())
+        act[0], act[1] = float(a[0]), float(a[1])
+
+    fn = POLICY_FN(cb) if policy is not None else C.cast(None, POLICY_FN)
+    lib().orc_render_path_fb(sc.ref, _p(_d(cam), c_dp), int(W), int(H), float(fov), int(s0), int(s1), int(max_bounces),
+                             float(mirror_threshold), float(fb_usage_prob), int(seed), fn, None, _p(out, c_dp), st)
+    return out, {"total_rays": int(st[0]), "total_intersections": int(st[1]), "light_hits": int(st[2]),
+                 "small_light_hits": int(st[3]), "queries": int(st[4]), "fb_used": int(st[5])}
 
 
 def resolve(sum_rgb, spp):

@@ -423,6 +423,123 @@ static void trace_path(const bctx *c, v3 O, v3 D, int bounce, double out[3]) {
     }
 }
 
+/* WorkingFBRenderer.trace_ray_fb: FB/fb_vs_traditional_complex.py:487-601 -- trace_ray_traditional with the diffuse
+   direction taken from a policy (fb_agent.choose_direction(obs22) -> action in [-1,1]^2) with probability
+   fb_usage_prob.  Draws: the use-FB decision is word 0 of the Philox block (pixel, sample, bounce, tag "RTFB"); r1, r2
+   stay on slot bounce+1 of the path stream. */
+typedef void (*orc_policy_fn)(const float *obs22, float *action2, void *user);
+typedef struct {
+    const orc_scene *s; int max_bounces; double thr, fb_prob; uint64_t seed; uint32_t pixel, sample; bstats *st;
+    uint64_t *fb_used; orc_policy_fn policy; void *user;
+} fctx;
+static void trace_path_fb(const fctx *c, v3 O, v3 D, int bounce, double out[3]) {
+    const orc_scene *s = c->s;
+    c->st->rays++;
+    if (bounce >= c->max_bounces) { out[0] = 2; out[1] = 2; out[2] = 5; return; }
+    c->st->queries++;
+    isect best; memset(&best, 0, sizeof best); best.idx = -1; double nd = INFINITY;
+    for (int i = 0; i < s->n; ++i) {
+        isect it = sphere_discriminant(O, D, ld3(s->centre, i), s->radius[i], 0);
+        if (it.hit) { double dist = vdist(it.p, O); if (dist < nd) { nd = dist; best = it; best.idx = i; } }
+    }
+    if (!best.hit) { out[0] = 2; out[1] = 2; out[2] = 5; return; }
+    c->st->inter++;
+    const double *m = s->material + 4 * best.idx, *col = s->colour + 3 * best.idx;
+    if (m[2] != 0) {
+        c->st->light++; if (s->small && s->small[best.idx]) c->st->small++;
+        out[0] = col[0]; out[1] = col[1]; out[2] = col[2]; return;
+    }
+    double direct[3] = {0, 0, 0};
+    for (int l = 0; l < s->nL; ++l) {
+        if (s->l_index[l] == best.idx) continue;
+        v3 tl = vsub(ld3(s->l_centre, l), best.p), tln = vnorm(tl);
+        double ca = vdot(best.n, tln); if (!(ca > 0)) ca = 0;
+        if (ca > 0) {
+            double dist = vmag(tl), att = 1.0 / (dist * dist);
+            for (int k = 0; k < 3; ++k) direct[k] += (double)(int64_t)(s->l_colour[3 * l + k] * ca * att * 0.3);
+        }
+    }
+    double ind[3];
+    v3 o2 = vadd(best.p, vscale(best.n, 0.001));
+    if (m[0] > c->thr) {
+        trace_path_fb(c, o2, vnorm(vreflect(D, best.n)), bounce + 1, ind);
+    } else {
+        int use_fb = 0;
+        if (c->policy) {                                     /* self.fb_loaded and np.random.random() < fb_usage_prob, :537 */
+            uint32_t ctr[4] = {c->pixel, c->sample, (uint32_t)bounce, 0x52544642u /* "RTFB" */};
+            uint32_t key[2] = {(uint32_t)c->seed, (uint32_t)(c->seed >> 32)}, o[4];
+            philox4x32_10(ctr, key, o);
+            use_fb = (double)(o[0] >> 8) * (1.0 / 16777216.0) < c->fb_prob;
+        }
+        double st_, ct_, sp_, cp_;
+        if (use_fb) {
+            (*c->fb_used)++;
+            float obs[22], act[2];                           /* create_observation, :469-485 (accumulated_color is always 0) */
+            obs[0] = (float)best.p.x; obs[1] = (float)best.p.y; obs[2] = (float)best.p.z;
+            obs[3] = (float)D.x; obs[4] = (float)D.y; obs[5] = (float)D.z;
+            obs[6] = (float)best.n.x; obs[7] = (float)best.n.y; obs[8] = (float)best.n.z;
+            obs[9] = (float)m[0]; obs[10] = (float)m[1]; obs[11] = (float)m[2]; obs[12] = (float)m[3];
+            obs[13] = obs[14] = obs[15] = 0.0f;
+            obs[16] = (float)((double)bounce / c->max_bounces); obs[17] = 0.0f;
+            obs[18] = (float)((double)s->ids[best.idx] / 100.0); obs[19] = obs[20] = obs[21] = 0.5f;
+            c->policy(obs, act, c->user);
+            /* :545-546 in double (the action's float32 values promoted): what the reference computes when the agent
+               returns float64, and under NumPy < 2 for float32 too; with NumPy >= 2 a float32 action would drag the
+               rest of the branch into float32 */
+            double theta = ((double)act[0] + 1) * M_PI / 4, phi = (double)act[1] * M_PI;
+            st_ = sin(theta); ct_ = cos(theta); sp_ = sin(phi); cp_ = cos(phi);
+        } else {
+            double r1, r2; rng_pair(c->seed, c->pixel, c->sample, (uint32_t)bounce + 1, &r1, &r2);
+            double theta = acos(sqrt(r1)), phi = 2 * M_PI * r2;
+            st_ = sin(theta); ct_ = cos(theta); sp_ = sin(phi); cp_ = cos(phi);
+        }
+        v3 tg = fabs(best.n.z) > 0.9 ? V(1, 0, 0) : vcross(V(0, 0, 1), best.n);
+        tg = vnorm(tg);
+        v3 bt = vnorm(vcross(best.n, tg));
+        v3 ld = V(st_ * cp_, st_ * sp_, ct_);
+        v3 bd = vnorm(V(ld.x * tg.x + ld.y * bt.x + ld.z * best.n.x, ld.x * tg.y + ld.y * bt.y + ld.z * best.n.y,
+                        ld.x * tg.z + ld.y * bt.z + ld.z * best.n.z));
+        trace_path_fb(c, o2, vnorm(bd), bounce + 1, ind);
+    }
+    for (int k = 0; k < 3; ++k) {
+        double tot = direct[k] + ind[k]; if (!(tot < 255)) tot = 255;
+        out[k] = (double)(int64_t)(col[k] * (tot / 255.0));
+    }
+}
+
+/* WorkingFBRenderer.render: FB/fb_vs_traditional_complex.py:603-640 (same camera and resolve as TraditionalRenderer).
+   stats6 = total_rays, total_intersections, light_hits, small_light_hits, queries, fb_used.  Single-threaded: the
+   policy is a Python callback. */
+ORC_API void orc_render_path_fb(const orc_scene *s, const double *cam, int W, int H, double fov_deg, int s0, int s1,
+                                int max_bounces, double mirror_threshold, double fb_prob, uint64_t seed,
+                                orc_policy_fn policy, void *user, double *sum_out, uint64_t *stats6) {
+    v3 O = V(cam[0], cam[1], cam[2]);
+    double aspect = (double)W / (double)H;
+    double half_h = tan((fov_deg * (M_PI / 180.0)) / 2), half_w = half_h * aspect;
+    bstats st = {0, 0, 0, 0, 0};
+    uint64_t fb_used = 0;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            double acc[3] = {0, 0, 0};
+            for (int sm = s0; sm < s1; ++sm) {
+                uint32_t pix = (uint32_t)(y * W + x);
+                double u0, u1; rng_pair(seed, pix, (uint32_t)sm, 0, &u0, &u1);
+                double sx = 0.5 + (u0 - 0.5), sy = 0.5 + (u1 - 0.5);
+                double ndc_x = (x + sx) / W, ndc_y = (y + sy) / H;
+                double scx = 2.0 * ndc_x - 1.0, scy = 1.0 - 2.0 * ndc_y;
+                scx *= aspect; scx *= half_w; scy *= half_h;
+                v3 d = vnorm(V(scx, scy, -1));
+                fctx c = {s, max_bounces, mirror_threshold, fb_prob, seed, pix, (uint32_t)sm, &st, &fb_used, policy, user};
+                double col[3];
+                trace_path_fb(&c, O, vnorm(d), 0, col);
+                acc[0] += col[0]; acc[1] += col[1]; acc[2] += col[2];
+            }
+            double *o = sum_out + 3 * ((size_t)y * W + x);
+            o[0] = acc[0]; o[1] = acc[1]; o[2] = acc[2];
+        }
+    if (stats6) { stats6[0] = st.rays; stats6[1] = st.inter; stats6[2] = st.light; stats6[3] = st.small; stats6[4] = st.queries; stats6[5] = fb_used; }
+}
+
 /* TraditionalRenderer.generate_camera_ray + render:
    FB/fb_vs_traditional_chandelier.py:417-429, :523-554.  sum_out [H,W,3] =
    sum over samples [s0,s1) of the per-sample colour for rows [y0,y1).       */

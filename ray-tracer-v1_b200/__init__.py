@@ -20,6 +20,7 @@ __version__ = "0.1.0"
 _LAZY = {
     "Ray": "ray", "Intersection": "ray",
     "TraditionalRenderer": "renderers", "CustomSceneExperiment": "renderers", "SimplifiedFBRenderer": "renderers",
+    "WorkingFBRenderer": "renderers", "render_path_wavefront": "renderers",
     "render_whitted": "renderers", "render_path": "renderers",
     "RayTracerEnv": "ray_tracer_env", "BatchedRayTracerEnv": "ray_tracer_env",
     "generate_trajectories": "fb_trajectories", "generate_trajectory": "fb_trajectories", "TrajectoryBatch": "fb_trajectories",

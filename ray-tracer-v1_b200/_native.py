@@ -110,6 +110,12 @@ SIGNATURES = {
     "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
     "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
+    "rt_wf_create": (C.c_int, [vp, C.c_int, C.c_int32, C.c_int32, C.POINTER(vp)]),
+    "rt_wf_destroy": (C.c_int, [vp]),
+    "rt_wf_begin": (C.c_int, [vp, C.POINTER(PathParams), C.c_double, vp, vp]),
+    "rt_wf_trace": (C.c_int, [vp, vp, vp, vp, vp]),
+    "rt_wf_bounce": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+    "rt_wf_finish": (C.c_int, [vp, vp, vp]),
     "rt_generate_trajectories": (C.c_int, [vp, C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, vp, vp, vp, vp, vp, vp, vp,
                                             vp, vp]),
     "rt_render_simple": (C.c_int, [vp, C.c_int, C.POINTER(SimpleParams), vp, vp, vp, vp]),

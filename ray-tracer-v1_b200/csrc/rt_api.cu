@@ -716,6 +716,123 @@ RT_EXPORT int rt_render_path_host(rt_scene *scene, int precision, const rt_path_
     return render_host_common(scene, precision, false, p, image_host, accum_host, nullptr, stats_host);
 }
 
+// ------------------------------------------------------------------ wavefront Algorithm B (learned direction sampling)
+struct rt_wavefront {
+    rt_scene *scene = nullptr;
+    int precision = RT_F32, max_paths = 0, max_depth = 0;
+    void *blob = nullptr;
+    WaveDev<float> f;
+    WaveDev<double> d;
+    PathDev<float> pf;
+    PathDev<double> pd;
+    bool begun = false;
+};
+
+template <typename T> static size_t wave_bytes(size_t P, size_t depth) {
+    return 12 * P * sizeof(T) + 2 * P * sizeof(int) + P + 2 * depth * P * sizeof(uint32_t) + 3 * P * sizeof(double) + 256;
+}
+template <typename T> static void bind_wave(WaveDev<T> &w, void *blob, size_t P, size_t depth) {
+    unsigned char *p = reinterpret_cast<unsigned char *>(blob);
+    w.leaf = reinterpret_cast<double *>(p); p += 3 * P * sizeof(double);
+    w.O = reinterpret_cast<T *>(p); p += 3 * P * sizeof(T);
+    w.D = reinterpret_cast<T *>(p); p += 3 * P * sizeof(T);
+    w.hp = reinterpret_cast<T *>(p); p += 3 * P * sizeof(T);
+    w.hn = reinterpret_cast<T *>(p); p += 3 * P * sizeof(T);
+    w.state = reinterpret_cast<int *>(p); p += P * sizeof(int);
+    w.depth = reinterpret_cast<int *>(p); p += P * sizeof(int);
+    w.st_idx = reinterpret_cast<uint32_t *>(p); p += depth * P * sizeof(uint32_t);
+    w.st_direct = reinterpret_cast<uint32_t *>(p); p += depth * P * sizeof(uint32_t);
+    w.mirror = p;
+}
+
+RT_EXPORT int rt_wf_create(rt_scene *scene, int precision, int32_t max_paths, int32_t max_depth, rt_wavefront **out) {
+    if (!scene || !out) return fail(RT_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (precision != RT_F32 && precision != RT_F64) return fail(RT_ERR_INVALID, "unknown precision");
+    if (max_paths <= 0 || max_depth <= 0 || max_depth > RT_PATH_MAX_DEPTH) return fail(RT_ERR_INVALID, "bad wavefront size");
+    CU(cudaSetDevice(scene->device));
+    rt_wavefront *wf = new (std::nothrow) rt_wavefront();
+    if (!wf) return fail(RT_ERR_NOMEM, "host allocation failed");
+    wf->scene = scene; wf->precision = precision; wf->max_paths = max_paths; wf->max_depth = max_depth;
+    const size_t P = (size_t)max_paths, D = (size_t)max_depth;
+    const size_t bytes = precision == RT_F64 ? wave_bytes<double>(P, D) : wave_bytes<float>(P, D);
+    cudaError_t e = cudaMalloc(&wf->blob, bytes);
+    if (e != cudaSuccess) { delete wf; cudaGetLastError(); return e == cudaErrorMemoryAllocation ? fail(RT_ERR_NOMEM, "out of device memory") : cuda_fail(e, "cudaMalloc"); }
+    *out = wf;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_wf_destroy(rt_wavefront *wf) {
+    if (!wf) return RT_OK;
+    if (wf->blob) cudaFree(wf->blob);
+    delete wf;
+    return RT_OK;
+}
+
+template <typename T>
+static int wf_begin_t(rt_wavefront *wf, WaveDev<T> &w, PathDev<T> &pp, const rt_path_params *p, double fb_prob, uint64_t *stats,
+                      cudaStream_t st) {
+    const long long P = (long long)p->W * (p->y1 - p->y0) * (p->s1 - p->s0);
+    if (P > wf->max_paths) return fail(RT_ERR_INVALID, "more paths than the wavefront was created for");
+    std::memset(&w, 0, sizeof w);
+    std::memset(&pp, 0, sizeof pp);
+    bind_wave<T>(w, wf->blob, (size_t)P, (size_t)wf->max_depth);
+    w.P = (int)P; w.max_depth = wf->max_depth;
+    w.W = p->W; w.H = p->H; w.y0 = p->y0; w.y1 = p->y1; w.s0 = p->s0; w.s1 = p->s1; w.max_bounces = p->max_bounces;
+    const double aspect = (double)p->W / (double)p->H;
+    const double half_h = std::tan((p->fov_deg * (M_PI / 180.0)) / 2), half_w = half_h * aspect;
+    for (int k = 0; k < 3; ++k) { w.cam[k] = (T)p->cam[k]; pp.cam[k] = (T)p->cam[k]; }
+    w.aspect = pp.aspect = (T)aspect; w.half_w = pp.half_w = (T)half_w; w.half_h = pp.half_h = (T)half_h;
+    pp.W = p->W; pp.H = p->H;
+    w.mirror_threshold = (T)p->mirror_threshold; w.fb_prob = (T)fb_prob;
+    w.k0 = (uint32_t)p->seed; w.k1 = (uint32_t)(p->seed >> 32);
+    CU(launch_wf_begin<T>(w, pp, reinterpret_cast<unsigned long long *>(stats), st));
+    wf->begun = true;
+    return RT_OK;
+}
+
+RT_EXPORT int rt_wf_begin(rt_wavefront *wf, const rt_path_params *p, double fb_usage_prob, uint64_t *stats_dev, void *stream) {
+    if (!wf || !p) return fail(RT_ERR_INVALID, "NULL argument");
+    int rc = check_band(p->W, p->H, p->y0, p->y1, p->s0, p->s1);
+    if (rc) return rc;
+    if (p->max_bounces > wf->max_depth) return fail(RT_ERR_INVALID, "max_bounces above the wavefront's stack depth");
+    if (!(fb_usage_prob >= 0.0 && fb_usage_prob <= 1.0)) return fail(RT_ERR_INVALID, "fb_usage_prob outside [0, 1]");
+    CU(cudaSetDevice(wf->scene->device));
+    if (wf->precision == RT_F64) return wf_begin_t<double>(wf, wf->d, wf->pd, p, fb_usage_prob, stats_dev, S(stream));
+    return wf_begin_t<float>(wf, wf->f, wf->pf, p, fb_usage_prob, stats_dev, S(stream));
+}
+
+RT_EXPORT int rt_wf_trace(rt_wavefront *wf, float *obs_dev, uint8_t *need_dev, uint64_t *stats_dev, void *stream) {
+    if (!wf || !obs_dev || !need_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (!wf->begun) return fail(RT_ERR_INVALID, "rt_wf_begin has not been called");
+    CU(cudaSetDevice(wf->scene->device));
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (wf->precision == RT_F64) CU(launch_wf_trace<double>(wf->scene->d.view, wf->d, obs_dev, need_dev, st, S(stream)));
+    else CU(launch_wf_trace<float>(wf->scene->f.view, wf->f, obs_dev, need_dev, st, S(stream)));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_wf_bounce(rt_wavefront *wf, const uint8_t *need_dev, const float *actions_dev, uint64_t *stats_dev,
+                           int32_t *live_dev, void *stream) {
+    if (!wf || !need_dev || !actions_dev || !live_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (!wf->begun) return fail(RT_ERR_INVALID, "rt_wf_begin has not been called");
+    CU(cudaSetDevice(wf->scene->device));
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (wf->precision == RT_F64) CU(launch_wf_bounce<double>(wf->d, need_dev, actions_dev, st, live_dev, S(stream)));
+    else CU(launch_wf_bounce<float>(wf->f, need_dev, actions_dev, st, live_dev, S(stream)));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_wf_finish(rt_wavefront *wf, void *accum_dev, void *stream) {
+    if (!wf || !accum_dev) return fail(RT_ERR_INVALID, "NULL argument");
+    if (!wf->begun) return fail(RT_ERR_INVALID, "rt_wf_begin has not been called");
+    CU(cudaSetDevice(wf->scene->device));
+    if (wf->precision == RT_F64) CU(launch_wf_finish<double>(wf->scene->d.view, wf->d, accum_dev, S(stream)));
+    else CU(launch_wf_finish<float>(wf->scene->f.view, wf->f, accum_dev, S(stream)));
+    wf->begun = false;
+    return RT_OK;
+}
+
 // ------------------------------------------------------------------ FB training trajectories
 RT_EXPORT int rt_generate_trajectories(rt_scene *scene, int precision, int32_t n_traj, int32_t max_steps, int32_t max_bounces,
                                        uint64_t seed, float *obs_dev, float *action_dev, float *next_obs_dev,

@@ -1,8 +1,10 @@
 // rt_f32.cu -- the FP32 product build of every kernel, plus the FFMA micro-benchmark that measures the FP32
 // roofline denominator on the box (MEASURED_PEAKS.json has no FP32 figure).
 #include "rt_kernels.cuh"
+#include "rt_wavefront.cuh"
 namespace rt {
 RT_INSTANTIATE_LAUNCHERS(float)
+RT_INSTANTIATE_WAVEFRONT(float)
 
 // 16 independent accumulator chains per thread: enough ILP to cover the 4-cycle FFMA latency at any occupancy.
 __global__ void __launch_bounds__(1024) fp32_peak_kernel(int iters, float *sink) {

@@ -42,6 +42,19 @@ template <typename T> struct SimpleDev {
     const double *rays;
 };
 
+// wavefront form of Algorithm B (rt_wavefront.cuh): SoA path state, one slot per (pixel, sample)
+template <typename T> struct WaveDev {
+    int P, max_depth;                     // path slots, stack depth
+    int W, H, y0, y1, s0, s1, max_bounces;
+    T cam[3], aspect, half_w, half_h, mirror_threshold, fb_prob;
+    uint32_t k0, k1;
+    T *O, *D, *hp, *hn;                   // [3][P] origin, direction, pending hit point / normal
+    int *state, *depth;                   // [P]
+    uint8_t *mirror;                      // [P] pending hit is a mirror
+    uint32_t *st_idx, *st_direct;         // [max_depth][P] per-level (sphere, clamped direct light)
+    double *leaf;                         // [3][P] colour at the end of the path
+};
+
 // batched RayTracerEnv state (SoA, [3][B] for vectors)
 template <typename T> struct EnvDev {
     int B, W, H, max_bounces, flavour, sun_id;
@@ -89,6 +102,17 @@ template <typename T>
 cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, double *reward,
                             uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
                             unsigned long long *stats, cudaStream_t st);
+
+template <typename T>
+cudaError_t launch_wf_begin(const WaveDev<T> &w, const PathDev<T> &pp, unsigned long long *stats, cudaStream_t st);
+template <typename T>
+cudaError_t launch_wf_trace(const SceneDev<T> &sc, const WaveDev<T> &w, float *obs, uint8_t *need, unsigned long long *stats,
+                            cudaStream_t st);
+template <typename T>
+cudaError_t launch_wf_bounce(const WaveDev<T> &w, const uint8_t *need, const float *actions, unsigned long long *stats,
+                             int *live_count, cudaStream_t st);
+template <typename T>
+cudaError_t launch_wf_finish(const SceneDev<T> &sc, const WaveDev<T> &w, void *accum, cudaStream_t st);
 
 // FFMA issue-rate micro-benchmark (rt_f32.cu): `iters` trips of 16 independent FFMA per thread
 cudaError_t launch_fp32_peak(int blocks, int threads, int iters, float *sink, cudaStream_t st);

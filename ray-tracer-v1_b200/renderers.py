@@ -30,7 +30,7 @@ from .scenes import custom_scene_grid, notebook_grid
 from .vector import Vector
 
 __all__ = ["render_whitted", "render_path", "TraditionalRenderer", "ComplexTraditionalRenderer",
-           "CustomSceneExperiment", "SimplifiedFBRenderer", "save_png"]
+           "CustomSceneExperiment", "SimplifiedFBRenderer", "WorkingFBRenderer", "render_path_wavefront", "save_png"]
 
 _PREC = {"f32": nat.F32, "fp32": nat.F32, "float32": nat.F32, nat.F32: nat.F32,
          "f64": nat.F64, "fp64": nat.F64, "float64": nat.F64, "double": nat.F64}
@@ -271,3 +271,131 @@ class SimplifiedFBRenderer:
         if output_path:
             save_png(image, output_path)
         return image, output_path
+
+
+# ---- Algorithm B with learned direction sampling -----------------------------------------------------
+def _batched_policy(agent):
+    """``agent.choose_directions(obs [m,22] CUDA tensor) -> [m,2]`` if the agent has it (a torch module evaluated once
+    per bounce), else the reference's per-observation ``choose_direction(obs numpy) -> (2,)`` looped on the host."""
+    import torch
+    if hasattr(agent, "choose_directions"):
+        return agent.choose_directions
+
+    def looped(obs):
+        rows = obs.cpu().numpy()
+        out = np.stack([np.asarray(agent.choose_direction(r), np.float32).reshape(2) for r in rows]) if len(rows) else \
+            np.zeros((0, 2), np.float32)
+        return torch.as_tensor(out, device=obs.device)
+    return looped
+
+
+def render_path_wavefront(fs, camera, width, height, spp, max_bounces, mirror_threshold, policy=None, fb_usage_prob=1.0,
+                          seed=0, fov=60.0, precision="f32", device=0, max_paths=1 << 22, scene=None):
+    """Algorithm B frame with ``policy(obs [m,22] float32 CUDA tensor) -> actions [m,2]`` choosing the diffuse bounce
+    direction with probability ``fb_usage_prob`` (``WorkingFBRenderer.trace_ray_fb``,
+    FB/fb_vs_traditional_complex.py:487-601).  Wavefront on the GPU: per bounce one trace kernel, the policy on the
+    asking paths, one bounce kernel; sample ranges are processed ``max_paths`` paths at a time.
+    -> (image [H,W,3] float32 numpy, sums [H,W,4] numpy, stats dict)."""
+    import ctypes as C
+    import torch
+    prec = _precision(precision)
+    own = scene is None
+    sc = nat.DeviceScene(fs, device) if own else scene
+    wf = C.c_void_p()
+    try:
+        dev = torch.device("cuda", sc.device)
+        per_sample = width * height
+        chunk = max(1, min(spp, max_paths // per_sample)) if per_sample <= max_paths else 0
+        if chunk == 0:
+            raise ValueError("max_paths is smaller than one sample of the frame")
+        P = per_sample * chunk
+        nat.check(nat.lib().rt_wf_create(sc.handle, prec, P, max(1, int(max_bounces)), C.byref(wf)))
+        ft = torch.float64 if prec == nat.F64 else torch.float32
+        accum = torch.zeros((height, width, 4), dtype=ft, device=dev)
+        obs = torch.zeros((P, 22), dtype=torch.float32, device=dev)
+        need = torch.zeros(P, dtype=torch.uint8, device=dev)
+        actions = torch.zeros((P, 2), dtype=torch.float32, device=dev)
+        live = torch.zeros(1, dtype=torch.int32, device=dev)
+        stats = torch.zeros(8, dtype=torch.int64, device=dev)
+        prob = float(fb_usage_prob) if policy is not None else 0.0
+        for s0 in range(0, spp, chunk):
+            s1 = min(spp, s0 + chunk)
+            n = per_sample * (s1 - s0)
+            p = sc.path_params(camera, width, height, spp, max_bounces, mirror_threshold, seed=seed, fov=fov, samples=(s0, s1))
+            nat.check(nat.lib().rt_wf_begin(wf, C.byref(p), prob, stats.data_ptr(), None))
+            for _ in range(int(max_bounces)):
+                nat.check(nat.lib().rt_wf_trace(wf, obs.data_ptr(), need.data_ptr(), stats.data_ptr(), None))
+                if prob > 0.0:
+                    idx = need[:n].nonzero(as_tuple=True)[0]
+                    if idx.numel():
+                        actions[idx] = policy(obs[idx]).to(device=dev, dtype=torch.float32).reshape(-1, 2)
+                live.zero_()
+                nat.check(nat.lib().rt_wf_bounce(wf, need.data_ptr(), actions.data_ptr(), stats.data_ptr(), live.data_ptr(), None))
+                if int(live.item()) == 0:
+                    break
+            nat.check(nat.lib().rt_wf_finish(wf, accum.data_ptr(), None))
+        image = torch.zeros((height, width, 3), dtype=torch.float32, device=dev)
+        sc.resolve(accum, width, height, spp, image, prec)
+        torch.cuda.synchronize(dev)
+        st = stats.cpu().numpy()
+        out = {"total_rays": int(st[0]), "total_intersections": int(st[1]), "light_hits": int(st[2]), "small_light_hits": int(st[3]),
+               "queries": int(st[4]), "sphere_tests": int(st[5]), "fb_used": int(st[7])}
+        return image.cpu().numpy(), accum.cpu().numpy(), out
+    finally:
+        if wf.value:
+            nat.load_symbols().rt_wf_destroy(wf)
+        if own:
+            sc.close()
+
+
+class WorkingFBRenderer:
+    """Drop-in for ``WorkingFBRenderer`` (FB/fb_vs_traditional_complex.py:425-640; the chandelier file's copy differs
+    only in the mirror threshold): Algorithm B whose diffuse bounces are steered by ``self.fb_agent`` with probability
+    ``self.fb_usage_prob``.  The reference builds the agent from a checkpoint (``TrainedFBAgent(model_path, ...)``);
+    the checkpoints and ``fb_ray_tracing`` are not part of the reference, so here the agent is whatever object the
+    caller assigns to ``fb_agent``: ``choose_directions(obs [m,22] CUDA tensor) -> [m,2]`` (preferred, one call per
+    bounce) or the reference's ``choose_direction(obs) -> (2,)``.  Without an agent it renders like
+    ``TraditionalRenderer`` (``fb_usage_prob = 0``, as the reference does when no model is given)."""
+
+    mirror_threshold = 0.9
+
+    def __init__(self, model_path=None, scene_small_lights=None, camera_position=None, device=0, precision="f32", seed=None):
+        if model_path is not None:
+            raise NotImplementedError("trained FB checkpoints are not part of the reference: assign an agent to .fb_agent")
+        self.scene = []
+        self.camera_position = camera_position if camera_position is not None else Vector(0, 2, 0)
+        self.camera_angle = None
+        self.global_lights, self.point_lights, self.light_sources = [], [], []
+        self.small_lights = scene_small_lights if scene_small_lights is not None else []
+        self.fb_agent, self.fb_loaded, self.fb_usage_prob = None, False, 0.0
+        self.stats = {'total_rays': 0, 'total_intersections': 0, 'light_hits': 0, 'small_light_hits': 0, 'fb_used': 0,
+                      'fb_success': 0, 'render_time': 0, 'rays_per_second': 0}
+        self.device, self.precision, self.seed = device, precision, seed
+        self._renders = 0
+
+    def set_render_settings(self, width=200, height=150, max_bounces=3, samples_per_pixel=4):
+        self.image_width, self.image_height = width, height
+        self.max_bounces, self.samples_per_pixel = max_bounces, samples_per_pixel
+        self.aspect_ratio = width / height
+        self.fov = 60
+
+    def render(self, width=200, height=150, samples_per_pixel=4, max_bounces=3):
+        self.set_render_settings(width, height, max_bounces, samples_per_pixel)
+        self.stats = {k: 0 for k in self.stats}
+        start = time.time()
+        seed = self.seed if self.seed is not None else (time.time_ns() ^ (self._renders * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
+        self._renders += 1
+        fs = flatten_scene(self.scene, background_colour=Colour(2, 2, 5), light_sources=self.light_sources,
+                           small_lights=self.small_lights)
+        use = self.fb_loaded and self.fb_agent is not None
+        image, _, st = render_path_wavefront(fs, _xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
+                                             self.mirror_threshold, policy=_batched_policy(self.fb_agent) if use else None,
+                                             fb_usage_prob=self.fb_usage_prob if use else 0.0, seed=seed, fov=self.fov,
+                                             precision=self.precision, device=self.device)
+        for k in ('total_rays', 'total_intersections', 'light_hits', 'small_light_hits', 'fb_used'):
+            self.stats[k] = st[k]
+        self.stats['fb_success'] = st['fb_used']                     # the reference counts both at the same place (:539-544)
+        self.stats['render_time'] = time.time() - start
+        if self.stats['render_time'] > 0:
+            self.stats['rays_per_second'] = self.stats['total_rays'] / self.stats['render_time']
+        return image

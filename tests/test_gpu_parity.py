@@ -467,3 +467,58 @@ def test_edge_cases_match_the_oracle(nat, orc):
         sc.render_path_sink(p, sink)
     assert nat.lib().rt_render_path(None, nat.F32, C.byref(p), None, None, None) != 0
     sc.close()
+
+
+# ------------------------------------------------------------------ wavefront Algorithm B with a policy (f-4)
+def test_wavefront_fb_renderer(rt, nat, orc):
+    """rt_wf_*: (1) without a policy the wavefront equals rt_render_path bit for bit (FP64 and FP32: same device
+    functions, same Philox streams), also when the frame is cut into sample chunks; (2) with the stand-in policy the
+    FP64 build reproduces the reference's own WorkingFBRenderer.render (golden) and the oracle; (3) the drop-in class."""
+    import torch
+    from test_oracle_golden import fb_test_policy
+    from ray_tracer_v1_b200 import renderers
+    z, fs = load_golden("path_fb_complex_40x24")
+    W, H, spp, depth, thr = int(z["W"]), int(z["H"]), int(z["spp"]), int(z["max_bounces"]), float(z["mirror_threshold"])
+    seed, prob = int(z["seed"]), float(z["fb_usage_prob"])
+    sc = nat.DeviceScene(fs)
+    p = sc.path_params(z["cam"], W, H, spp, depth, thr, seed=seed)
+    for prec, name in ((nat.F64, "f64"), (nat.F32, "f32")):
+        _, ref, st = sc.render_path_host(p, prec)
+        for max_paths in (1 << 22, W * H):                     # one chunk / one sample per chunk
+            _, sums, out = renderers.render_path_wavefront(fs, z["cam"], W, H, spp, depth, thr, seed=seed, precision=name,
+                                                            max_paths=max_paths, scene=sc)
+            assert np.array_equal(sums, ref), (name, max_paths)
+            assert [out["total_rays"], out["total_intersections"], out["light_hits"], out["small_light_hits"]] == [int(v) for v in st[:4]]
+            assert out["fb_used"] == 0
+
+    def policy(obs):                                            # torch twin of fb_test_policy: same float32 bits
+        a0 = (obs[:, 6] * 0.5 + obs[:, 7] * 0.25 - 0.125).clamp(-1, 1)
+        a1 = (obs[:, 8] * 0.5 + obs[:, 3] * 0.25 + obs[:, 16] * 0.5).clamp(-1, 1)
+        return torch.stack([a0, a1], dim=1)
+
+    _, sums64, out = renderers.render_path_wavefront(fs, z["cam"], W, H, spp, depth, thr, policy, prob, seed=seed,
+                                                     precision="f64", scene=sc)
+    assert np.array_equal(sums64[..., :3], z["sums"])          # the reference's own FB render
+    assert [out[k] for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits", "fb_used")] == list(z["stats"])
+    _, sums32, out32 = renderers.render_path_wavefront(fs, z["cam"], W, H, spp, depth, thr, policy, prob, seed=seed,
+                                                       precision="f32", scene=sc)
+    assert (np.abs(sums32[..., :3] - z["sums"]).max(axis=2) > spp).mean() < 0.03
+    assert abs(out32["fb_used"] - out["fb_used"]) < 0.01 * out["fb_used"]
+    # a bigger frame against the oracle, the policy through the reference's per-observation protocol
+    ref, sto = orc.render_path_fb(fs, z["cam"], 64, 36, 2, depth, thr, fb_test_policy, 1.0, seed + 1)
+    agent = type("Agent", (), {"choose_direction": staticmethod(fb_test_policy)})()
+    _, s2, o2 = renderers.render_path_wavefront(fs, z["cam"], 64, 36, 2, depth, thr, renderers._batched_policy(agent), 1.0,
+                                                seed=seed + 1, precision="f64", scene=sc)
+    assert np.array_equal(s2[..., :3], ref) and o2["fb_used"] == sto["fb_used"] and o2["total_rays"] == sto["total_rays"]
+    sc.close()
+    # drop-in class
+    from ray_tracer_v1_b200 import scenes
+    spec = scenes.build_complex()
+    r = rt.WorkingFBRenderer(camera_position=rt.Vector(*spec.camera), precision="f64", seed=seed)
+    r.scene = spec.spheres
+    r.light_sources = [s for s in spec.spheres if s.material.emitive]
+    r.small_lights = [s for s in r.light_sources if s.radius < 0.5]
+    r.fb_agent = type("Agent", (), {"choose_directions": staticmethod(policy)})()
+    r.fb_loaded, r.fb_usage_prob = True, prob
+    img = r.render(W, H, spp, depth)
+    assert np.array_equal(img, z["image"]) and r.stats["fb_used"] == int(z["stats"][4]) and r.stats["fb_success"] == r.stats["fb_used"]

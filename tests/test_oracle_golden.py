@@ -160,3 +160,25 @@ def test_fb_trajectories(orc):
     assert int(o["length"].sum()) > 1000 and int(o["hit_light"].sum()) > 5
     for k in ("length", "hit_light", "obs", "action", "next_obs", "reward", "hit"):
         assert np.array_equal(o[k], z[k]), k
+
+
+def fb_test_policy(obs):
+    """Stand-in for fb_agent.choose_direction (the one oracle/gen_golden.py used): IEEE basic ops only, float32."""
+    o = np.asarray(obs, np.float32)
+    a0 = np.clip(o[6] * np.float32(0.5) + o[7] * np.float32(0.25) - np.float32(0.125), np.float32(-1), np.float32(1))
+    a1 = np.clip(o[8] * np.float32(0.5) + o[3] * np.float32(0.25) + o[16] * np.float32(0.5), np.float32(-1), np.float32(1))
+    return np.array([a0, a1], dtype=np.float64)
+
+
+def test_fb_guided_path_frame(orc):
+    """WorkingFBRenderer.render of the reference itself (stand-in agent, np.random.random patched to the Philox
+    streams): sums and all five counters exactly; and with no policy the FB renderer IS the traditional one."""
+    z, fs = load_golden("path_fb_complex_40x24")
+    args = (z["cam"], int(z["W"]), int(z["H"]), int(z["spp"]), int(z["max_bounces"]), float(z["mirror_threshold"]))
+    sums, st = orc.render_path_fb(fs, *args, fb_test_policy, float(z["fb_usage_prob"]), int(z["seed"]))
+    assert np.array_equal(sums, z["sums"])
+    assert [st[k] for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits", "fb_used")] == list(z["stats"])
+    assert st["fb_used"] > 1000
+    plain, st0 = orc.render_path_fb(fs, *args, None, 0.0, int(z["seed"]))
+    trad, st1 = orc.render_path(fs, *args, seed=int(z["seed"]))
+    assert np.array_equal(plain, trad) and st0["total_rays"] == st1["total_rays"] and st0["fb_used"] == 0
