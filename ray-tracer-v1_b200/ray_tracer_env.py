@@ -120,6 +120,7 @@ class BatchedRayTracerEnv:
         self.scene = None
         self.handle = None
         self._resets = 0
+        self._step_args = None
 
     # ---- sharding ------------------------------------------------------------------------------------------------
     @classmethod
@@ -174,7 +175,8 @@ class BatchedRayTracerEnv:
         pixels, otherwise they are drawn on the device with Philox(seed).  -> (obs [B,18] CUDA tensor, info dict)."""
         if seed is not None:
             self.seed = int(seed)
-        self._ensure()
+        if mask is None or self.handle is None:
+            self._ensure()            # full reset: the scene list may have been mutated since (re-flatten + upload)
         torch = self.torch
         pix = None
         if options is not None and "pixels" in options:
@@ -196,13 +198,17 @@ class BatchedRayTracerEnv:
         else:
             a = self._dev_tensor(actions, torch.float32, (self.n_envs, 2))
         self._last_actions = a
-        nat.check(nat.lib().rt_env_step(self.handle, a.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(),
-                                        self.terminated.data_ptr(), self.truncated.data_ptr(), self.reason.data_ptr(),
-                                        self.info.data_ptr(), self.stats.data_ptr(), None))
-        info = {"bounce_count": self.info[:, 0], "through_count": self.info[:, 1], "total_reward": self.info[:, 2],
-                "hit_sun": self.info[:, 3], "reason": self.reason}
-        # uint8 0/1 flags reinterpreted as bool: no conversion kernels on the rollout path
-        return self.obs, self.reward, self.terminated.view(torch.bool), self.truncated.view(torch.bool), info
+        if self._step_args is None:     # the output buffers never move: resolve their pointers and views once
+            self._step_args = (self.obs.data_ptr(), self.reward.data_ptr(), self.terminated.data_ptr(),
+                               self.truncated.data_ptr(), self.reason.data_ptr(), self.info.data_ptr(), self.stats.data_ptr())
+            self._info = {"bounce_count": self.info[:, 0], "through_count": self.info[:, 1], "total_reward": self.info[:, 2],
+                          "hit_sun": self.info[:, 3], "reason": self.reason}
+            self._flags = (self.terminated.view(torch.bool), self.truncated.view(torch.bool))
+            self._step_fn = nat.lib().rt_env_step
+        rc = self._step_fn(self.handle, a.data_ptr(), *self._step_args, None)
+        if rc:
+            nat.check(rc)
+        return self.obs, self.reward, self._flags[0], self._flags[1], dict(self._info)
 
     def close(self):
         if self.handle is not None:

@@ -146,6 +146,22 @@ def bench_env(name, spec, flavour, B, W, H, fov, depth, cam, reps, cpu_B):
     steps = B * len(acts)
     out = {"envs": B, "flavour": flavour, "steps_per_rollout": len(acts), "ms_per_rollout": ms,
            "env_steps_per_s": steps / (ms * 1e-3), "Mrays_per_s": q / ms / 1e3, "launches_per_rollout": 1 + len(acts)}
+    # steady state of a vectorised trainer: every step is followed by a masked reset of the finished episodes, so all
+    # B environments stay busy (2 launches per step)
+    def busy(n):
+        for k in range(n):
+            _, _, te, tr, _ = env.step(acts[k % len(acts)])
+            env.reset(mask=(te | tr).to(torch.uint8))
+    env.reset(seed=1)
+    busy(20)
+    torch.cuda.synchronize()
+    env.stats.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(); busy(200); b.record()
+    torch.cuda.synchronize()
+    t = a.elapsed_time(b)
+    out["steady_state"] = {"us_per_step_with_auto_reset": 1e3 * t / 200, "env_steps_per_s": B * 200 / (t * 1e-3),
+                           "Mrays_per_s": int(env.stats.cpu()[4]) / t / 1e3}
     env.close()
     if cpu_B:
         from oracle import oracle as orc
@@ -206,10 +222,10 @@ def main():
     if want("C5"):
         balls = scenes.build_balls_in_space(as_rendered=False)
         bench_env("C5 FB env 65536 envs balls_in_space", balls, "fb", 65536, 800, 600, 90, 5, (0.0, 0.0, 1.0), R,
-                  4096 if cpu else 0)
+                  65536 if cpu else 0)
         opt = scenes.build_optimized_env_scene()
         bench_env("C5 RL env 65536 envs optimized scene", opt, "rl", 65536, 320, 240, 80, 6, (0.0, 0.0, 0.0), R,
-                  4096 if cpu else 0)
+                  65536 if cpu else 0)
 
 
 if __name__ == "__main__":
