@@ -20,7 +20,7 @@ __all__ = ["NativeLibraryError", "lib", "build", "DeviceBuffer", "PinnedArray", 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(CSRC, "librt_b200.so")      # override: kernel A/B builds
 
 F32, F64 = 0, 1
 NO_ID = -(2 ** 31)

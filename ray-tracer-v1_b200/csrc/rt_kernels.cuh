@@ -104,6 +104,9 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 
 // Kernel variants: kMode 0 = scene staged in shared memory, brute force (no hierarchy code in the kernel at all);
 //                  kMode 1 = staged in shared memory + LBVH traversal; kMode 2 = scene read from global + LBVH.
+#ifndef RT_PATH_MIN_BLOCKS
+#define RT_PATH_MIN_BLOCKS 3   /* 3 x 256 threads per SM at <= 85 registers: measured 2.7 % faster than 4 at <= 64 */
+#endif
 #define RT_MODE_DECL constexpr bool kShared = kMode < 2; constexpr bool kBvh = kMode > 0
 
 // ------------------------------------------------------------------ Algorithm A frame
@@ -180,7 +183,7 @@ template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, 
 //                   trip.  Pays off only when early termination is common and the per-sample code is short.
 // kIntFold: integer fold through the div255 table (all leaf colours integer-valued), else the double-division fold.
 template <typename T, int kMode, bool kIntFold, bool kRegen>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? 4 : 1))
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_PATH_MIN_BLOCKS : 1))
 path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned long long *stats) {
     RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
