@@ -204,6 +204,15 @@ def main():
         torch.cuda.synchronize()
 
     fused = world > 1 and args.collective == "fused"
+    fused_note = None
+    if fused:
+        # peer mappings are set up collectively; if any rank cannot (no IPC / no peer access) every rank raises and
+        # the whole job uses the NCCL collective instead
+        try:
+            r._ensure_fabric(W, H)
+        except Exception as e:      # noqa: BLE001
+            fused, fused_note = False, f"fused collective unavailable, NCCL used: {e}"
+            print(fused_note, file=sys.stderr, flush=True)
 
     def step(i, **kw):
         if fused:
@@ -301,7 +310,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "width": W, "height": H, "spp": spp, "max_bounces": DEPTH,
-                       "sharding": args.mode if world == 1 else f"{args.mode}, {args.collective} collective "
+                       "sharding": args.mode if world == 1 else f"{args.mode}, {'fused' if fused else 'nccl'} collective "
                        + ("(path-kernel epilogue stores/reductions over NVLink peer memory, epoch flags)" if fused else "(NCCL)"),
                        "l2": "flushed between steps (256 MiB memset, untimed); inputs are a 3 KB scene",
                        "ray_definition": "one nearest-hit query over the scene (SURVEY 8d)"},
@@ -322,6 +331,10 @@ def main():
                          "hbm_algorithmic_bytes_per_launch": W * H * 16 // world},
             "clocks": clocks,
         }
+        if fused:
+            line["config"]["fused_wait_timed_out"] = bool(r.fused_timed_out())
+        if fused_note:
+            line["config"]["note"] = fused_note
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(fs, spec)
         print(json.dumps(line), file=JSON_OUT, flush=True)

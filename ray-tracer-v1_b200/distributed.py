@@ -128,23 +128,44 @@ class PeerFabric:
         self.ptrs, self._own, self._opened = {}, [], []
 
     def alloc(self, name, nbytes):
+        """Collective.  A failure on ANY rank (allocation, IPC export, peer mapping) raises on EVERY rank after the
+        exchange, so callers can fall back together instead of leaving peers blocked in a collective."""
         import ctypes as C
         nat, dist = self.nat, _dist()
         own, handle = C.c_void_p(), C.create_string_buffer(nat.IPC_HANDLE_BYTES)
-        nat.check(nat.lib().rt_peer_alloc(self.device, int(nbytes), C.byref(own), handle))
-        self._own.append(own.value)
+        err = None
+        try:
+            nat.check(nat.lib().rt_peer_alloc(self.device, int(nbytes), C.byref(own), handle))
+            self._own.append(own.value)
+        except Exception as e:                      # noqa: BLE001 - reported to every rank below
+            err = f"rank {self.rank}: {e}"
         handles = [None] * self.world
         if self.world > 1:
-            dist.all_gather_object(handles, handle.raw, group=self.group)
+            dist.all_gather_object(handles, None if err else handle.raw, group=self.group)
         ptrs = []
-        for r in range(self.world):
-            if r == self.rank:
-                ptrs.append(own.value)
-            else:
+        if err is None and all(h is not None for h in handles if self.world > 1):
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(own.value)
+                    continue
                 q = C.c_void_p()
-                nat.check(nat.lib().rt_peer_open(self.device, handles[r], C.byref(q)))
+                try:
+                    nat.check(nat.lib().rt_peer_open(self.device, handles[r], C.byref(q)))
+                except Exception as e:              # noqa: BLE001
+                    err = f"rank {self.rank} mapping rank {r}: {e}"
+                    break
                 self._opened.append(q.value)
                 ptrs.append(q.value)
+        elif err is None:
+            err = f"rank {self.rank}: a peer could not allocate"
+        if self.world > 1:
+            errs = [None] * self.world
+            dist.all_gather_object(errs, err, group=self.group)
+            bad = [e for e in errs if e]
+            if bad:
+                raise nat.NativeLibraryError("peer memory unavailable: " + "; ".join(bad))
+        elif err:
+            raise nat.NativeLibraryError("peer memory unavailable: " + err)
         self.ptrs[name] = ptrs
         return ptrs
 
@@ -156,7 +177,7 @@ class PeerFabric:
         tab = (C.c_void_p * len(targets))(*[self.ptrs[name][t] + 4 * int(word) for t in targets])
         nat.check(nat.lib().rt_peer_signal(self.device, tab, len(targets), int(epoch) & 0xFFFFFFFF, stream))
 
-    def wait(self, name, first_word, n, epoch, timed_out=None, timeout_ms=4000, stream=None):
+    def wait(self, name, first_word, n, epoch, timed_out=None, timeout_ms=20000, stream=None):
         """Block the stream until the ``n`` local flag words from ``first_word`` have reached ``epoch``."""
         nat = self.nat
         nat.check(nat.lib().rt_peer_wait(self.device, self.ptrs[name][self.rank] + 4 * int(first_word), int(n),
