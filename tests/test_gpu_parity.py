@@ -522,3 +522,58 @@ def test_wavefront_fb_renderer(rt, nat, orc):
     r.fb_loaded, r.fb_usage_prob = True, prob
     img = r.render(W, H, spp, depth)
     assert np.array_equal(img, z["image"]) and r.stats["fb_used"] == int(z["stats"][4]) and r.stats["fb_success"] == r.stats["fb_used"]
+
+
+# ------------------------------------------------------------------ full-size properties of C2 and C4
+def test_c2_full_size_properties(nat):
+    """Marbles scene 1280x720, 16 spp, depth 4 (BASELINE config 2): row bands x sample ranges accumulate to the whole
+    frame bit for bit, the deterministic centre-of-pixel frame is reproducible, and jitter only moves edge pixels."""
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    spec = scenes.build_marbles4()
+    fs = flatten_scene(spec.spheres, spec.global_lights, spec.point_lights, spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp = 1280, 720, 16
+    k = 640 * spec.ray_step
+    X, Y = np.linspace(-k * 16 / 9, k * 16 / 9, W), np.linspace(k, -k, H)
+    miss = [spec.miss.r, spec.miss.g, spec.miss.b]
+    whole = nat.DeviceBuffer((H, W, 4), np.float32)
+    st = nat.DeviceBuffer(8, np.uint64)
+    sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=3), whole, nat.F32, stats=st)
+    parts = nat.DeviceBuffer((H, W, 4), np.float32)
+    for rows in ((0, 250), (250, 720)):
+        for i, smp in enumerate(((0, 5), (5, 16))):
+            sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=3, rows=rows,
+                                                samples=smp, accumulate=i > 0), parts, nat.F32)
+    a = whole.download()
+    assert np.array_equal(a, parts.download())
+    assert np.all(a[..., 3] == spp) and int(st.download()[0]) == W * H * spp
+    one = nat.DeviceBuffer((H, W, 4), np.float32)
+    sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=1, max_bounces=4, miss=miss), one, nat.F32)
+    d = np.abs(a[..., :3] / spp - one.download()[..., :3]).max(axis=2)
+    assert (d > 2).mean() < 0.02              # supersampling changes silhouettes and shadow edges only
+    sc.close()
+
+
+def test_c4_full_size_properties(nat):
+    """Chandelier 1920x1080 (BASELINE config 4): sample ranges summed == the whole frame, LBVH == brute force up to
+    near-tie pixels, rays per sample in the band the reference measures (8.14 at depth 8)."""
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    spec = scenes.build_chandelier()
+    fs = flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp = 1920, 1080, 8
+    whole = nat.DeviceBuffer((H, W, 4), np.float32)
+    st = nat.DeviceBuffer(8, np.uint64)
+    sc.render_path(sc.path_params(spec.camera, W, H, spp, 8, 0.0, seed=1), whole, nat.F32, stats=st)
+    parts = nat.DeviceBuffer((H, W, 4), np.float32)
+    for i, smp in enumerate(((0, 3), (3, 4), (4, 8))):
+        sc.render_path(sc.path_params(spec.camera, W, H, spp, 8, 0.0, seed=1, samples=smp, accumulate=i > 0), parts, nat.F32)
+    a = whole.download()
+    assert np.array_equal(a, parts.download())
+    rays_per_sample = st.download()[0] / (W * H * spp)
+    assert 7.5 < rays_per_sample < 8.6, rays_per_sample
+    sc.build_lbvh(50.0)
+    bvh = nat.DeviceBuffer((H, W, 4), np.float32)
+    sc.render_path(sc.path_params(spec.camera, W, H, spp, 8, 0.0, seed=1), bvh, nat.F32)
+    assert (bvh.download() != a).any(axis=2).mean() < 0.01
+    sc.close()
