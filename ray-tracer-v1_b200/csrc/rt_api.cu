@@ -2,6 +2,7 @@
 // and stream-ordered launches of the kernels in rt_f32.cu / rt_f64.cu / rt_lbvh.cu.  No compute happens on the host.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -48,6 +49,8 @@ struct rt_scene {
     size_t scratch_bytes = 0;
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
+    PkConst pkc;                  // host copy of the FP32 sphere pairs of a small scene (path kernel parameter block)
+    bool pkc_ok = false;
 };
 
 struct rt_env {
@@ -169,7 +172,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     v.p_func = q; q += nP;
     v.l_index = q; q += nL;
     v.small = small_dev;
-    v.key_mask = 0x7ffffff8;
+    v.key_mask = 0x7ffffff8; v.key_mask6 = 0x7fffffc0;
     v.bg[0] = (T)s->bg[0]; v.bg[1] = (T)s->bg[1]; v.bg[2] = (T)s->bg[2];
     std::memset(&v.bvh, 0, sizeof v.bvh);
 }
@@ -218,6 +221,19 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
     if (s->small) std::memcpy(small.data(), s->small, (size_t)s->n);
     CU(cudaMemcpyAsync(sc->small_dev, small.data(), small.size(), cudaMemcpyHostToDevice, st));
     CU(cudaStreamSynchronize(st));          // the staging vectors die at return
+    {   // small scenes: the path kernel takes the FP32 pair array through its parameter block (kMode 3)
+        const int n_pad = (s->n + 7) & ~7;
+        static const bool off = std::getenv("RT_B200_NO_PKC") != nullptr;      // A/B switch for measurements
+        sc->pkc_ok = !off && n_pad > 0 && n_pad <= RT_PKC_MAX && s->nL <= RT_LPKC_MAX;
+        std::memset(&sc->pkc, 0, sizeof sc->pkc);
+        if (sc->pkc_ok) {
+            // blob layout (pack_scene): sph[n_pad] pk[n_pad] mat[n] col[n] g_vec g_col [nG] p_pos p_col [nP] l_pos l_col [nL] lpk
+            const float4 *v = reinterpret_cast<const float4 *>(hf.data());
+            std::memcpy(sc->pkc.q, v + n_pad, (size_t)n_pad * sizeof(float4));
+            const size_t lpk_at = 2 * (size_t)n_pad + 2 * (size_t)s->n + 2 * (size_t)s->nG + 2 * (size_t)s->nP + 2 * (size_t)s->nL;
+            std::memcpy(sc->pkc.l, v + lpk_at, 3 * (size_t)((s->nL + 1) / 2) * sizeof(float4));
+        }
+    }
     bind_view<float>(sc->f, s, sc->small_dev);
     bind_view<double>(sc->d, s, sc->small_dev);
     lbvh_drop(sc->bvh);                     // geometry changed: any hierarchy is stale
@@ -503,6 +519,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     pp.aspect = (T)aspect; pp.half_w = (T)half_w; pp.half_h = (T)half_h;
     pp.mirror_threshold = (T)p->mirror_threshold;
     pp.k0 = (uint32_t)p->seed; pp.k1 = (uint32_t)(p->seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) { pp.rk[2 * r] = pp.k0 + r * 0x9E3779B9u; pp.rk[2 * r + 1] = pp.k1 + r * 0xBB67AE85u; }
     pp.accumulate = p->accumulate;
     pp.int_fold = sc->int_colours && (p->s1 - p->s0) <= 65536;
     pp.regenerate = p->schedule == 1;
@@ -545,7 +562,8 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         else { while (lk < 5 && (pixels << lk) / 256 < want && (ns >> (lk + 1)) >= 2) ++lk; }
         pp.ksplit_log2 = lk;
     }
-    CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st));
+    CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
+                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 ? &sc->pkc : nullptr));
     return RT_OK;
 }
 

@@ -121,6 +121,18 @@ RT_DEV Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
     return o;
 }
+// the same rounds with the ten round keys precomputed (kernel parameter block: they become constant-bank operands)
+RT_DEV Philox4 philox4x32_10_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const uint32_t (&rk)[20]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = h1 ^ c1 ^ rk[2 * r], n2 = h0 ^ c3 ^ rk[2 * r + 1];
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+    }
+    Philox4 o; o.w[0] = c0; o.w[1] = c1; o.w[2] = c2; o.w[3] = c3;
+    return o;
+}
 #define RT_PHILOX_TAG 0x52544232u /* "RTB2" */
 template <typename T> RT_DEV T u01(uint32_t w) { return T(w >> 8) * T(1.0 / 16777216.0); }   // 24-bit, exact in f32
 
@@ -136,6 +148,13 @@ struct PathRng {
         uint32_t pr = slot >> 1;
         if ((slot & 1u) && cached_pair == pr) { a = c2; b = c3; return; }
         Philox4 o = philox4x32_10(pixel, sample, pr, RT_PHILOX_TAG, k0, k1);
+        if (slot & 1u) { a = o.w[2]; b = o.w[3]; }
+        else { a = o.w[0]; b = o.w[1]; c2 = o.w[2]; c3 = o.w[3]; cached_pair = pr; }
+    }
+    RT_DEV void pair_rk(uint32_t slot, uint32_t &a, uint32_t &b, const uint32_t (&rk)[20]) {
+        uint32_t pr = slot >> 1;
+        if ((slot & 1u) && cached_pair == pr) { a = c2; b = c3; return; }
+        Philox4 o = philox4x32_10_rk(pixel, sample, pr, RT_PHILOX_TAG, rk);
         if (slot & 1u) { a = o.w[2]; b = o.w[3]; }
         else { a = o.w[0]; b = o.w[1]; c2 = o.w[2]; c3 = o.w[3]; cached_pair = pr; }
     }
@@ -158,16 +177,26 @@ template <typename T> struct SceneDev {
     const v4 *l_pos, *l_col, *lpk; const int *l_index;
     const uint8_t *small;
     int key_mask;             // 0x7ffffff8, passed as DATA so that the selection loop's (t & mask) | k stays ONE LOP3
+    int key_mask6;            // 0x7fffffc0: the same for brute_select_pkc (6 index bits)
     T bg[3];
     BvhView bvh;              // optional LBVH, see rt_lbvh.cuh
 };
+
+// Sphere pairs and light pairs (the FP32 `pk` / `lpk` arrays) of a small scene carried IN THE KERNEL PARAMETER BLOCK:
+// the selection loop and the direct-light loop then read them through the constant bank into uniform registers
+// (LDCU.128) and FFMA2 takes them as uniform operands, so no vector register, no register-file read port and no
+// shared-memory load is spent on warp-uniform scene data.
+#define RT_PKC_MAX 64                    /* spheres */
+#define RT_LPKC_MAX 32                   /* Algorithm-B light spheres (the `lpk` light-pair array, 3 vectors per pair) */
+struct PkConst { ulonglong2 q[RT_PKC_MAX]; ulonglong2 l[3 * RT_LPKC_MAX / 2]; };
+struct PkNone {};
 
 // sphere arrays as the tracing functions see them (shared-memory staged or global)
 template <typename T> struct SphereView {
     using v4 = typename M<T>::v4;
     int n;
     int n_padded;            // sph[] readable up to here: n rounded up to 8 with NaN-radius spheres (never hit)
-    int key_mask;            // SceneDev::key_mask
+    int key_mask, key_mask6; // SceneDev::key_mask, key_mask6
     const v4 *sph, *pk, *mat, *col;
     const int *ids;
 };

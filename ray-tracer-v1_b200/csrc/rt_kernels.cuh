@@ -45,7 +45,7 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
     using v4 = typename M<T>::v4;
     S.g.sv.n = sc.n;
     S.g.sv.n_padded = (sc.n + 7) & ~7;      // both the staged copy and the HBM blob are padded
-    S.g.sv.key_mask = sc.key_mask;
+    S.g.sv.key_mask = sc.key_mask; S.g.sv.key_mask6 = sc.key_mask6;
     S.g.bvh = sc.bvh;
     S.la.nG = sc.nG; S.la.nP = sc.nP; S.lb.nL = sc.nL;
     S.la.bg[0] = sc.bg[0]; S.la.bg[1] = sc.bg[1]; S.la.bg[2] = sc.bg[2];
@@ -103,11 +103,22 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 }
 
 // Kernel variants: kMode 0 = scene staged in shared memory, brute force (no hierarchy code in the kernel at all);
-//                  kMode 1 = staged in shared memory + LBVH traversal; kMode 2 = scene read from global + LBVH.
+//                  kMode 1 = staged in shared memory + LBVH traversal; kMode 2 = scene read from global + LBVH;
+//                  kMode 3 (path_kernel, FP32 only) = kMode 0 with the sphere pairs of a <= RT_PKC_MAX-sphere scene in
+//                  the kernel parameter block (constant bank -> uniform registers), see brute_select_pkc.
 #ifndef RT_PATH_MIN_BLOCKS
 #define RT_PATH_MIN_BLOCKS 3   /* 3 x 256 threads per SM at <= 85 registers: measured 2.7 % faster than 4 at <= 64 */
 #endif
-#define RT_MODE_DECL constexpr bool kShared = kMode < 2; constexpr bool kBvh = kMode > 0
+#ifndef RT_DEFER_FOLD
+#define RT_DEFER_FOLD 1        /* lock-step schedule: fold once per sample and warp (A/B: see DESIGN.md) */
+#endif
+#ifndef RT_PHILOX_RK
+#define RT_PHILOX_RK 1         /* Philox round keys from the parameter block instead of two IADD per round */
+#endif
+#ifndef RT_SKIP_LAST_BOUNCE
+#define RT_SKIP_LAST_BOUNCE 1  /* no bounce direction for the ray that is never traced */
+#endif
+#define RT_MODE_DECL constexpr bool kShared = kMode != 2; constexpr bool kBvh = kMode == 1 || kMode == 2
 
 // ------------------------------------------------------------------ Algorithm A frame
 template <typename T, int kMode>
@@ -184,8 +195,10 @@ template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, 
 // kIntFold: integer fold through the div255 table (all leaf colours integer-valued), else the double-division fold.
 template <typename T, int kMode, bool kIntFold, bool kRegen>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_PATH_MIN_BLOCKS : 1))
-path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned long long *stats) {
+path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned long long *stats,
+            const __grid_constant__ typename std::conditional<kMode == 3, PkConst, PkNone>::type pkc) {
     RT_MODE_DECL;
+    using PK = typename std::conditional<kMode == 3, PkConst, PkNone>::type;
     extern __shared__ __align__(32) unsigned char smem[];
     double *div255 = reinterpret_cast<double *>(smem);                 // [256] k / 255.0, correctly rounded
     for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
@@ -230,11 +243,14 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             depth = 0; O = cam;
             rng.begin(pixel, (uint32_t)smp, pp.k0, pp.k1);
             uint32_t wa, wb;
-            rng.pair(0u, wa, wb);
+            if (RT_PHILOX_RK) rng.pair_rk(0u, wa, wb, pp.rk); else rng.pair(0u, wa, wb);
             D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
             n_rays++;                                 // trace_ray_traditional call count, chandelier.py:432
         };
         if (alive) start_sample(s);
+        bool pend = false;                            // lock-step: path ended, fold deferred to the end of the sample
+        int pl0 = 2, pl1 = 2, pl2 = 5;
+        double pf0 = 2.0, pf1 = 2.0, pf2 = 5.0;
         for (;;) {
             bool ended = false;
             int leaf0 = 2, leaf1 = 2, leaf2 = 5;      // miss / depth limit: Colour(2,2,5)
@@ -243,7 +259,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
                 T t;
                 n_query++;
-                const int i = nearest<T, true, kBvh>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes);
+                const int i = nearest<T, true, kBvh, PK>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes, pkc);
                 if (i < 0) ended = true;
                 else {
                     n_inter++;
@@ -260,21 +276,52 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                         finish_hit<T>(S.g, O, D, i, t, h);
                         st.idx[depth] = (uint32_t)i;
                         if constexpr (M<T>::exact) st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
+                        else if constexpr (kMode == 3) st.direct[depth] = direct_light_pkc(pkc, (S.lb.nL + 1) >> 1, h.p, h.n);
                         else st.direct[depth] = direct_light_pk(S.lb.lpk, (S.lb.nL + 1) >> 1, h.p, h.n);
-                        const bool mirror = m.x > pp.mirror_threshold;
-                        T r1 = T(0), r2 = T(0);
-                        if (!mirror) {
-                            uint32_t wa, wb;
-                            rng.pair((uint32_t)depth + 1u, wa, wb);
-                            r1 = u01<T>(wa); r2 = u01<T>(wb);
-                        }
-                        D = bounce_direction<T>(D, h.n, mirror, r1, r2);
-                        O = h.p + h.n * T(0.001);
                         depth++;
                         n_rays++;                                                    // the recursive call ...
                         ended = depth >= pp.max_bounces;                             // ... returns (2,2,5) at once
+                        // the bounce ray of the deepest level is never traced (counter-based RNG: skipping its
+                        // draw changes nothing), so its direction is not computed either
+                        if (!RT_SKIP_LAST_BOUNCE || !ended) {
+                            const bool mirror = m.x > pp.mirror_threshold;
+                            T r1 = T(0), r2 = T(0);
+                            if (!mirror) {
+                                uint32_t wa, wb;
+                                if (RT_PHILOX_RK) rng.pair_rk((uint32_t)depth, wa, wb, pp.rk); else rng.pair((uint32_t)depth, wa, wb);
+                                r1 = u01<T>(wa); r2 = u01<T>(wb);
+                            }
+                            D = bounce_direction<T>(D, h.n, mirror, r1, r2);
+                            O = h.p + h.n * T(0.001);
+                        }
                     }
                 }
+            }
+            if (RT_DEFER_FOLD && !kRegen) {
+                // lock-step: a lane whose path ends early only parks its leaf; the whole warp folds together once
+                // the sample's longest path has ended (one full-occupancy fold instead of several sparse ones)
+                if (alive && ended) {
+                    alive = false; pend = true;
+                    if constexpr (kIntFold) { pl0 = leaf0; pl1 = leaf1; pl2 = leaf2; }
+                    else { pf0 = lf0; pf1 = lf1; pf2 = lf2; }
+                }
+                if (__any_sync(0xffffffffu, alive)) continue;
+                if (pend) {
+                    pend = false;
+                    if constexpr (kIntFold) {
+                        int c[3] = {pl0, pl1, pl2};
+                        fold_path_int<T>(S.g, st, depth, div255, c);
+                        a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
+                    } else {
+                        double c[3] = {pf0, pf1, pf2};
+                        fold_path<T>(S.g, st, depth, c);
+                        a0 += c[0]; a1 += c[1]; a2 += c[2];
+                    }
+                }
+                s += kk;
+                if (s - sub >= pp.s1) break;
+                if (has_pixel && s < pp.s1) { alive = true; start_sample(s); }
+                continue;
             }
             if (alive && ended) {
                 alive = false;
@@ -935,7 +982,7 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
 
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
-                        cudaStream_t st) {
+                        cudaStream_t st, const PkConst *pkc) {
     const int rows = pp.y1 - pp.y0;
     if (rows <= 0 || pp.W <= 0) return cudaSuccess;
     const int tiles = (rows + 7) / 8, step = pp.tile_step > 1 ? pp.tile_step : 1;
@@ -947,12 +994,25 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     dim3 grid((pp.W + ctw - 1) / ctw, gy), block(256);
     using v4 = typename M<T>::v4;
     const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold
-    const int mode = mode_for(sc, extra);
-    const size_t sm = (mode < 2 ? smem_for(sc) : 0) + extra;
+    int mode = mode_for(sc, extra);
+    // small brute-force FP32 scenes: sphere pairs through the parameter block (kMode 3)
+    if (mode == 0 && sizeof(T) == 4 && pkc && ((sc.n + 7) & ~7) <= RT_PKC_MAX && sc.nL <= RT_LPKC_MAX) mode = 3;
+    const size_t sm = (mode != 2 ? smem_for(sc) : 0) + extra;
     cudaError_t e = cudaSuccess;
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \
-      path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats); }
+      path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats, PkNone()); }
+    if (mode == 3) {
+        if constexpr (sizeof(T) == 4) {
+#define RT_PATH_CASE3(F_, R_)                                                                                      \
+    { e = allow_smem(path_kernel<T, 3, F_, R_>, sm); if (e != cudaSuccess) return e;                               \
+      path_kernel<T, 3, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats, *pkc); }
+            if (pp.int_fold) { if (pp.regenerate) RT_PATH_CASE3(true, true) else RT_PATH_CASE3(true, false) }
+            else { if (pp.regenerate) RT_PATH_CASE3(false, true) else RT_PATH_CASE3(false, false) }
+#undef RT_PATH_CASE3
+        }
+        return cudaGetLastError();
+    }
     const int variant = mode * 4 + (pp.int_fold ? 2 : 0) + (pp.regenerate ? 1 : 0);
     switch (variant) {
         case 0: RT_PATH_CASE(0, false, false) break;   case 1: RT_PATH_CASE(0, false, true) break;
@@ -1054,7 +1114,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_whitted<T>(const SceneDev<T> &, const WhittedDev<T> &, void *, int *,                   \
                                            unsigned long long *, cudaStream_t);                                         \
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
-                                        cudaStream_t);                                                                  \
+                                        cudaStream_t, const PkConst *);                                                 \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \
     template cudaError_t launch_trajectories<T>(const SceneDev<T> &, int, int, int, uint64_t, float *, float *, float *,  \
                                                 float *, uint8_t *, int *, uint8_t *, unsigned long long *, cudaStream_t); \

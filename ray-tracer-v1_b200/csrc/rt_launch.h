@@ -23,6 +23,7 @@ template <typename T> struct PathDev {
     T aspect, half_w, half_h;    // W/H, tan(fov/2)*aspect, tan(fov/2)   (chandelier.py:412-415)
     T mirror_threshold;
     uint32_t k0, k1;
+    uint32_t rk[20];                     // Philox round keys k0 + r*W0, k1 + r*W1 (constant-bank operands of the rounds)
     int accumulate;
     int int_fold;                // every leaf colour is an integer in [0, 65535]: integer fold + uint32 accumulators
     int regenerate;              // 1: path-regeneration schedule, 0: lock-step schedule (rt_kernels.cuh)
@@ -70,7 +71,7 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
                            unsigned long long *stats, cudaStream_t st);
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
-                        cudaStream_t st);
+                        cudaStream_t st, const PkConst *pkc = nullptr);   // pkc: host copy of the FP32 pair array or NULL
 template <typename T>
 cudaError_t launch_trajectories(const SceneDev<T> &sc, int n_traj, int max_steps, int max_bounces, uint64_t seed, float *obs,
                                 float *action, float *next_obs, float *reward, uint8_t *hit, int *length,

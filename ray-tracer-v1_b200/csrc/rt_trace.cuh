@@ -150,8 +150,48 @@ RT_DEV int brute_select_pk(const float4 *pk, int n_padded, int key_mask, V3<floa
     return best < RT_KEY_INF ? bbase + (best & 7) : -1;
 }
 
-template <typename T, bool kAbs, bool kBvh>
-RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests) {
+// The same selection with the pair array in the kernel parameter block (PkConst, rt_common.cuh): the group loop is
+// fully unrolled so that every LDCU.128 has an immediate constant-bank address, and the sphere operands of FFMA2 /
+// FADD2 are uniform registers.  Groups at or beyond n_padded are skipped by a uniform branch.
+RT_DEV int brute_select_pkc(const PkConst &pkc, int n_padded, int key_mask6, V3<float> O, V3<float> D) {
+    const float od = dot(O, D), oo = dot(O, O);
+    const f32x2 Dx = pack2(D.x, D.x), Dy = pack2(D.y, D.y), Dz = pack2(D.z, D.z), nod = pack2(-od, -od);
+    const f32x2 Bx = pack2(2.f * O.x, 2.f * O.x), By = pack2(2.f * O.y, 2.f * O.y), Bz = pack2(2.f * O.z, 2.f * O.z);
+    const f32x2 noo = pack2(-oo, -oo), neg1 = pack2(-1.f, -1.f);
+    // RT_PKC_MAX = 64 spheres: the key carries the SCENE index in its 6 low mantissa bits (the unrolled loop knows it
+    // at compile time), so the running minimum over all spheres is four VIMNMX3 per group and nothing else.
+    static_assert(RT_PKC_MAX == 64, "key layout: 6 index bits");
+    int best = RT_KEY_INF;
+#pragma unroll
+    for (int base = 0; base < RT_PKC_MAX; base += 8) {
+        if (base >= n_padded) break;                  // ONE exit: the groups behind it are never fetched
+        int key[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const ulonglong2 a = pkc.q[base + 2 * j], b = pkc.q[base + 2 * j + 1];
+            const f32x2 tca = fma2(b.x, Dz, fma2(a.y, Dy, fma2(a.x, Dx, nod)));
+            const f32x2 nm = fma2(b.x, Bz, fma2(a.y, By, fma2(a.x, Bx, add2(b.y, noo))));
+            const f32x2 disc = fma2(tca, tca, nm);
+            float tc0, tc1, d0, d1;
+            unpack2(tca, tc0, tc1); unpack2(disc, d0, d1);
+            const float s0 = M<float>::sqrt(__int_as_float(__float_as_int(d0) | (__float_as_int(tc0) & (int)0x80000000)));
+            const float s1 = M<float>::sqrt(__int_as_float(__float_as_int(d1) | (__float_as_int(tc1) & (int)0x80000000)));
+            float t0, t1;
+            unpack2(fma2(pack2(s0, s1), neg1, tca), t0, t1);
+            key[2 * j] = (__float_as_int(t0) & key_mask6) | (base + 2 * j);
+            key[2 * j + 1] = (__float_as_int(t1) & key_mask6) | (base + 2 * j + 1);
+        }
+        best = __vimin3_s32(best, key[0], key[1]);
+        best = __vimin3_s32(best, key[2], key[3]);
+        best = __vimin3_s32(best, key[4], key[5]);
+        best = __vimin3_s32(best, key[6], key[7]);
+    }
+    return best < RT_KEY_INF ? (best & 63) : -1;
+}
+
+template <typename T, bool kAbs, bool kBvh, typename PK = PkNone>
+RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests,
+                   const PK &pkc = PK()) {
     T best = M<T>::inf(), bt = T(0);
     int bi = -1;
     bool brute = true;
@@ -160,7 +200,8 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
         const int n = g.sv.n;
         if (suppress == RT_NO_ID_DEV) {
             if constexpr (!M<T>::exact) {
-                if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
+                if constexpr (kAbs && std::is_same<PK, PkConst>::value) bi = brute_select_pkc(pkc, g.sv.n_padded, g.sv.key_mask6, O, D);
+                else if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
                 else brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
                 if (bi >= 0) {
                     // winner's distance from the cancellation-free form |L - tca D|^2; a silhouette-grazing winner
@@ -467,6 +508,40 @@ RT_DEV uint32_t direct_light_pk(const float4 *lpk, int n_pairs, V3<float> p, V3<
         asm("mov.b64 {%0, %1}, %2;" : "=r"(g_lo), "=r"(g_hi) : "l"(fma2_rz(C.x, s, magic)));
         asm("mov.b64 {%0, %1}, %2;" : "=r"(b0), "=r"(b1) : "l"(fma2_rz(C.y, s, magic)));
         a0 += r_lo + r_hi; a1 += g_lo + g_hi; a2 += b0 + b1;
+    }
+    const unsigned bias = 2u * (unsigned)n_pairs * 0x4B000000u;          // bits of 2^23, once per light
+    a0 = min(a0 - bias, 255u); a1 = min(a1 - bias, 255u); a2 = min(a2 - bias, 255u);
+    return a0 | (a1 << 8) | (a2 << 16);
+}
+
+// direct_light_pk over the light pairs in the kernel parameter block (PkConst::l): fully unrolled, uniform operands.
+RT_DEV uint32_t direct_light_pkc(const PkConst &pkc, int n_pairs, V3<float> p, V3<float> n) {
+    const float qx = -128.f * p.x, qy = -128.f * p.y, qz = -128.f * p.z;
+    const f32x2 px = pack2(qx, qx), py = pack2(qy, qy), pz = pack2(qz, qz);
+    const f32x2 nx = pack2(n.x, n.x), ny = pack2(n.y, n.y), nz = pack2(n.z, n.z);
+    const f32x2 magic = pack2(8388608.f, 8388608.f);
+    unsigned a0 = 0u, a1 = 0u, a2 = 0u;
+#pragma unroll
+    for (int j = 0; j < RT_LPKC_MAX / 2; ++j) {
+        if (j >= n_pairs) break;                      // ONE exit (a guard per pair costs a taken branch per skipped pair)
+        {
+            const ulonglong2 A = pkc.l[3 * j], B = pkc.l[3 * j + 1], C = pkc.l[3 * j + 2];
+            const f32x2 tx = add2(A.x, px), ty = add2(A.y, py), tz = add2(B.x, pz);
+            const f32x2 qq = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
+            const f32x2 dn = fma2(tz, nz, fma2(ty, ny, mul2(tx, nx)));
+            float q0, q1;
+            unpack2(qq, q0, q1);
+            const f32x2 inv = pack2(M<float>::rsqrt(q0), M<float>::rsqrt(q1));
+            float a_lo, a_hi, b_lo, b_hi;
+            unpack2(mul2(dn, inv), a_lo, a_hi);
+            unpack2(mul2(inv, inv), b_lo, b_hi);
+            const f32x2 s = pack2(mul_sat(a_lo, b_lo), mul_sat(a_hi, b_hi));
+            unsigned r_lo, r_hi, g_lo, g_hi, b0, b1;
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(r_lo), "=r"(r_hi) : "l"(fma2_rz(B.y, s, magic)));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(g_lo), "=r"(g_hi) : "l"(fma2_rz(C.x, s, magic)));
+            asm("mov.b64 {%0, %1}, %2;" : "=r"(b0), "=r"(b1) : "l"(fma2_rz(C.y, s, magic)));
+            a0 += r_lo + r_hi; a1 += g_lo + g_hi; a2 += b0 + b1;
+        }
     }
     const unsigned bias = 2u * (unsigned)n_pairs * 0x4B000000u;          // bits of 2^23, once per light
     a0 = min(a0 - bias, 255u); a1 = min(a1 - bias, 255u); a2 = min(a2 - bias, 255u);
