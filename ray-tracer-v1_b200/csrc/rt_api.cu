@@ -39,6 +39,7 @@ template <typename T> struct SceneBufs {
     SceneDev<T> view;
 };
 
+#define RT_SCHED_SLOTS 64
 struct rt_scene {
     int device = 0;
     int n = 0, nG = 0, nP = 0, nL = 0;
@@ -49,6 +50,8 @@ struct rt_scene {
     size_t scratch_bytes = 0;
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
+    mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS pairs of work counters of the persistent path kernel (zero at rest)
+    mutable unsigned sched_next = 0; // launches rotate through the slots, so launches in flight never share a pair
     PkConst pkc;                  // host copy of the FP32 sphere pairs of a small scene (path kernel parameter block)
     bool pkc_ok = false;
 };
@@ -385,6 +388,7 @@ RT_EXPORT int rt_scene_destroy(rt_scene *scene) {
     if (scene->f.blob) cudaFree(scene->f.blob);
     if (scene->d.blob) cudaFree(scene->d.blob);
     if (scene->small_dev) cudaFree(scene->small_dev);
+    if (scene->sched_dev) cudaFree(scene->sched_dev);
     if (scene->scratch) cudaFree(scene->scratch);
     delete scene;
     return RT_OK;
@@ -562,8 +566,13 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         else { while (lk < 5 && (pixels << lk) / 256 < want && (ns >> (lk + 1)) >= 2) ++lk; }
         pp.ksplit_log2 = lk;
     }
+    if (!sc->sched_dev) {
+        CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
+        CU(cudaMemset(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
+    }
+    unsigned *sched = sc->sched_dev + 2 * (sc->sched_next++ % RT_SCHED_SLOTS);
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
-                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 ? &sc->pkc : nullptr));
+                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 ? &sc->pkc : nullptr, sched));
     return RT_OK;
 }
 

@@ -214,25 +214,37 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     const int ph_sh = (5 - lk) - pw_sh;
     const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
     const int sub = lane_ & (kk - 1), pl = lane_ >> lk;
-    const int x = ((((int)blockIdx.x << 2) + (w_ & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
     // CTA rows: cth = 2 << ph_sh of them; tile_step > 1: this launch owns every tile_step-th 8-row stripe from y0
     const int cth_sh = ph_sh + 1, cps_sh = 3 - cth_sh;                 // CTA rows per stripe = 1 << cps_sh
-    const int by = (int)blockIdx.y;
-    const int y = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
-                  ((w_ >> 2) << ph_sh) + (pl >> pw_sh);
-    const bool has_pixel = x < pp.W && y < pp.y1;
     unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
     const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
-    const uint32_t pixel = (uint32_t)(y * pp.W + x);
+    const int ns = pp.s1 - pp.s0;
     PathStack st;
     PathRng rng;
+    // PERSISTENT WARPS: the launch has as many CTAs as the device holds at once, and every WARP pulls its next work
+    // unit -- one warp tile (32 lanes: 32/k pixels x k sample lanes) of the gx x gy x 8 unit grid -- from a device
+    // counter, so the scene staging, the div255 table and the statistics flush are paid once per CTA instead of once
+    // per tile, the load balances at warp granularity, and the eight warps of a CTA drift apart freely (no barrier
+    // inside the loop).  The first units are static (CTA c, warp w -> unit 8c + w); the counter hands out the rest.
+    // The fetch for the NEXT unit is issued before the current one is traced, so its latency is never waited for.
+    // pp.sched = {next, done}: the last warp of the launch to finish resets both, so no memset precedes a launch.
+    const unsigned n_units = (unsigned)(pp.gx * pp.gy) << 3, first_dyn = (unsigned)gridDim.x << 3;
+    for (unsigned unit = ((unsigned)blockIdx.x << 3) + (unsigned)w_; unit < n_units;) {
+    unsigned nxt = 0;
+    if (lane_ == 0) nxt = first_dyn + atomicAdd(pp.sched, 1u);
+    const int tile = (int)(unit >> 3), wt = (int)(unit & 7u);      // wt: the warp's place in the 4 x 2 warp tile
+    const int by = tile / pp.gx, bx = tile - by * pp.gx;
+    const int x = (((bx << 2) + (wt & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
+    const int y = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
+                  ((wt >> 2) << ph_sh) + (pl >> pw_sh);
+    const bool has_pixel = x < pp.W && y < pp.y1;
+    const uint32_t pixel = (uint32_t)(y * pp.W + x);
     // integer-valued sums: exact in uint32 (int fold: colours <= 65535, samples per launch <= 65536) / in double
     typename std::conditional<kIntFold, unsigned, double>::type a0 = 0, a1 = 0, a2 = 0;
-    const int ns = pp.s1 - pp.s0;
 
     if (pp.max_bounces <= 0) {                        // degenerate: every call returns (2,2,5) at the depth check
         const int mine = has_pixel ? (ns - sub + kk - 1) >> lk : 0;      // samples of this lane
-        n_rays = (unsigned)mine;
+        n_rays += (unsigned)mine;
         a0 = 2 * mine; a1 = 2 * mine; a2 = 5 * mine;
     } else {
         int s = pp.s0 + sub, depth = 0;
@@ -384,6 +396,13 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             }
             accum[o] = out;
         }
+    }
+    unit = __shfl_sync(0xffffffffu, nxt, 0);
+    }   // work units of this warp
+    if (lane_ == 0) {
+        // every warp of the launch passes here exactly once, after its last fetch: the last one re-arms the counters
+        __threadfence();
+        if (atomicAdd(pp.sched + 1, 1u) == (gridDim.x << 3) - 1u) { pp.sched[0] = 0u; pp.sched[1] = 0u; __threadfence(); }
     }
     if (stats) {
         flush_stats(stats, STAT_RAYS, n_rays);
@@ -980,9 +999,19 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
     return cudaGetLastError();
 }
 
+// CTAs of a persistent launch: what the current device keeps resident for this kernel (occupancy x SM count)
+template <typename K> static unsigned persistent_ctas(K kernel, size_t smem_bytes, long long tiles) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        sms <= 0) sms = 148;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem_bytes) != cudaSuccess || per_sm <= 0) per_sm = 1;
+    const long long g = (long long)sms * per_sm;
+    return (unsigned)(tiles < g ? (tiles > 0 ? tiles : 1) : g);
+}
+
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
-                        cudaStream_t st, const PkConst *pkc) {
+                        cudaStream_t st, const PkConst *pkc, unsigned *sched) {
     const int rows = pp.y1 - pp.y0;
     if (rows <= 0 || pp.W <= 0) return cudaSuccess;
     const int tiles = (rows + 7) / 8, step = pp.tile_step > 1 ? pp.tile_step : 1;
@@ -991,7 +1020,11 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     const int ctw = 4 << pw_sh, cth = 2 << ph_sh;
     // stripes of 8 rows (8 / cth CTA rows each); without interleaving the last stripe may be cut short
     const unsigned gy = step > 1 ? (unsigned)((tiles + step - 1) / step) * (8 / cth) : (unsigned)((rows + cth - 1) / cth);
-    dim3 grid((pp.W + ctw - 1) / ctw, gy), block(256);
+    PathDev<T> ppl = pp;                                          // + the tile grid the persistent CTAs walk
+    ppl.gx = (pp.W + ctw - 1) / ctw; ppl.gy = (int)gy;
+    ppl.sched = sched;
+    const long long tiles_total = (long long)ppl.gx * ppl.gy;
+    dim3 grid(1), block(256);
     using v4 = typename M<T>::v4;
     const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold
     int mode = mode_for(sc, extra);
@@ -1001,12 +1034,14 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     cudaError_t e = cudaSuccess;
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \
-      path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats, PkNone()); }
+      grid.x = persistent_ctas(path_kernel<T, M_, F_, R_>, sm, tiles_total);                                       \
+      path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, ppl, (v4 *)accum, stats, PkNone()); }
     if (mode == 3) {
         if constexpr (sizeof(T) == 4) {
 #define RT_PATH_CASE3(F_, R_)                                                                                      \
     { e = allow_smem(path_kernel<T, 3, F_, R_>, sm); if (e != cudaSuccess) return e;                               \
-      path_kernel<T, 3, F_, R_><<<grid, block, sm, st>>>(sc, pp, (v4 *)accum, stats, *pkc); }
+      grid.x = persistent_ctas(path_kernel<T, 3, F_, R_>, sm, tiles_total);                                        \
+      path_kernel<T, 3, F_, R_><<<grid, block, sm, st>>>(sc, ppl, (v4 *)accum, stats, *pkc); }
             if (pp.int_fold) { if (pp.regenerate) RT_PATH_CASE3(true, true) else RT_PATH_CASE3(true, false) }
             else { if (pp.regenerate) RT_PATH_CASE3(false, true) else RT_PATH_CASE3(false, false) }
 #undef RT_PATH_CASE3
@@ -1114,7 +1149,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_whitted<T>(const SceneDev<T> &, const WhittedDev<T> &, void *, int *,                   \
                                            unsigned long long *, cudaStream_t);                                         \
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
-                                        cudaStream_t, const PkConst *);                                                 \
+                                        cudaStream_t, const PkConst *, unsigned *);                                     \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \
     template cudaError_t launch_trajectories<T>(const SceneDev<T> &, int, int, int, uint64_t, float *, float *, float *,  \
                                                 float *, uint8_t *, int *, uint8_t *, unsigned long long *, cudaStream_t); \

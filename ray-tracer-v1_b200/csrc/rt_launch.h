@@ -22,6 +22,8 @@ template <typename T> struct PathDev {
     int W, H, y0, y1, s0, s1, max_bounces;
     T aspect, half_w, half_h;    // W/H, tan(fov/2)*aspect, tan(fov/2)   (chandelier.py:412-415)
     T mirror_threshold;
+    int gx, gy;                          // tile grid of the launch (set by launch_path)
+    unsigned *sched;                     // {next work unit, warps done}: zero between launches (self-resetting)
     uint32_t k0, k1;
     uint32_t rk[20];                     // Philox round keys k0 + r*W0, k1 + r*W1 (constant-bank operands of the rounds)
     int accumulate;
@@ -71,7 +73,8 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
                            unsigned long long *stats, cudaStream_t st);
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
-                        cudaStream_t st, const PkConst *pkc = nullptr);   // pkc: host copy of the FP32 pair array or NULL
+                        cudaStream_t st, const PkConst *pkc, unsigned *sched);
+// pkc: host copy of the FP32 pair arrays (small scenes) or NULL; sched: two zeroed device counters owned by this launch
 template <typename T>
 cudaError_t launch_trajectories(const SceneDev<T> &sc, int n_traj, int max_steps, int max_bounces, uint64_t seed, float *obs,
                                 float *action, float *next_obs, float *reward, uint8_t *hit, int *length,

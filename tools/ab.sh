@@ -10,6 +10,6 @@ for spec in "$@"; do
   for cfg in "complex 16" "complex 64" "chandelier 16"; do
     set -- $cfg
     echo "== $spec $cfg" >> "$out"
-    env $envs RT_B200_LIB=$PWD/$lib python tools/time_path.py --scene $1 --spp $2 --reps 4 2>&1 | grep -v "^$" >> "$out"
+    env $envs RT_B200_LIB=$PWD/$lib python tools/time_path.py --scene $1 --spp $2 --reps 4 --schedules 0 $AB_ARGS 2>&1 | grep -v "^$" >> "$out"
   done
 done

@@ -20,6 +20,8 @@ def main():
     ap.add_argument("--w", type=int, default=1920)
     ap.add_argument("--h", type=int, default=1080)
     ap.add_argument("--lbvh", action="store_true")
+    ap.add_argument("--ksplit", type=int, default=-1, help="-1 auto, 0 off, k = lanes per pixel")
+    ap.add_argument("--schedules", default="0,1")
     args = ap.parse_args()
     spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
     fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
@@ -30,8 +32,8 @@ def main():
     accum = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     stats = torch.zeros(8, dtype=torch.int64, device="cuda")
     ref = None
-    for schedule in (0, 1):
-        p = sc.path_params(spec.camera, W, H, args.spp, spec.max_bounces, spec.mirror_threshold, seed=1, schedule=schedule)
+    for schedule in [int(v) for v in args.schedules.split(',')]:
+        p = sc.path_params(spec.camera, W, H, args.spp, spec.max_bounces, spec.mirror_threshold, seed=1, schedule=schedule, ksplit=args.ksplit)
         sc.render_path(p, accum, nat.F32, stats=stats)
         torch.cuda.synchronize()
         best = 1e9
@@ -45,7 +47,7 @@ def main():
         img = accum.cpu().numpy()
         same = None if ref is None else bool(np.array_equal(ref, img))
         ref = img if ref is None else ref
-        print(f"{args.scene} {W}x{H} spp {args.spp} schedule {schedule}: {best:.3f} ms  {st[4] / best / 1e6:.2f} Gqueries/s "
+        print(f"{args.scene} {W}x{H} spp {args.spp} schedule {schedule} ksplit {args.ksplit}: {best:.3f} ms  {st[4] / best / 1e6:.2f} Gqueries/s "
               f"rays/sample {st[0] / (W * H * args.spp):.3f}  tests/query {st[5] / st[4]:.1f} boxes/query {st[6] / st[4]:.1f} same_image={same}", flush=True)
 
 
