@@ -156,7 +156,9 @@ typedef struct rt_path_params {
     double mirror_threshold;/* material.reflective > threshold mirrors: 0.9 complex (:349), 0 chandelier (:481) */
     uint64_t seed;
     int32_t accumulate;
-    int32_t schedule;       /* 0 = lock-step warps (default), 1 = per-lane path regeneration; same image either way */
+    int32_t schedule;       /* bit 0: 0 = lock-step warps (default), 1 = per-lane path regeneration; bit 1 (value 2):
+                               diagnostic, switch off the camera-ray candidate lists of the FP32 lock-step kernel.
+                               Same image in every combination */
     int32_t ksplit;         /* lanes sharing one pixel's samples: -1 = automatic (keeps >= 64 waves of CTAs in the grid),
                                0 or 1 = one thread per pixel, 2..32 = that power of two.  Same image either way. */
     int32_t reserved_;

@@ -526,7 +526,8 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     for (uint32_t r = 0; r < 10; ++r) { pp.rk[2 * r] = pp.k0 + r * 0x9E3779B9u; pp.rk[2 * r + 1] = pp.k1 + r * 0xBB67AE85u; }
     pp.accumulate = p->accumulate;
     pp.int_fold = sc->int_colours && (p->s1 - p->s0) <= 65536;
-    pp.regenerate = p->schedule == 1;
+    pp.regenerate = (p->schedule & 1) != 0;
+    pp.primary_cull = (p->schedule & 2) == 0;
     pp.sink = RT_SINK_ACCUM; pp.tile_step = 1; pp.world = 1; pp.spp_total = p->s1 - p->s0;
     pp.ksplit_log2 = 0;
     if (sink && sink->mode != RT_SINK_ACCUM) {

@@ -199,6 +199,7 @@ template <typename T> struct SphereView {
     int key_mask, key_mask6; // SceneDev::key_mask, key_mask6
     const v4 *sph, *pk, *mat, *col;
     const int *ids;
+    const float4 *cw;        // path kernel kMode 3 only: (cx, cy, cz, w) per sphere, the pair array un-interleaved
 };
 
 enum : int { STAT_RAYS = 0, STAT_INTER = 1, STAT_LIGHT = 2, STAT_SMALL = 3, STAT_QUERIES = 4, STAT_SPHERE_TESTS = 5,

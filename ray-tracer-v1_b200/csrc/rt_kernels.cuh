@@ -115,6 +115,9 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #ifndef RT_PHILOX_RK
 #define RT_PHILOX_RK 1         /* Philox round keys from the parameter block instead of two IADD per round */
 #endif
+#ifndef RT_PRIMARY_CULL
+#define RT_PRIMARY_CULL 1      /* camera rays: warp-coherent candidate list instead of the full sphere loop */
+#endif
 #ifndef RT_SKIP_LAST_BOUNCE
 #define RT_SKIP_LAST_BOUNCE 1  /* no bounce direction for the ray that is never traced */
 #endif
@@ -203,8 +206,18 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     double *div255 = reinterpret_cast<double *>(smem);                 // [256] k / 255.0, correctly rounded
     for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
     Staged<T> S;
-    stage_scene<T, kShared>(sc, smem + 256 * sizeof(double), S);        // ends with __syncthreads() when staging
+    float4 *cw = reinterpret_cast<float4 *>(smem + 256 * sizeof(double));     // kMode 3: (cx, cy, cz, w) per sphere
+    const size_t cw_bytes = kMode == 3 ? (size_t)((sc.n + 7) & ~7) * sizeof(float4) : 0;
+    if constexpr (kMode == 3) {
+        const float *pkf = reinterpret_cast<const float *>(sc.pk);       // pair j: cx0 cx1 cy0 cy1 | cz0 cz1 w0 w1
+        for (int i = threadIdx.x; i < ((sc.n + 7) & ~7); i += blockDim.x) {
+            const float *q = pkf + 8 * (i >> 1) + (i & 1);
+            cw[i] = make_float4(q[0], q[2], q[4], q[6]);
+        }
+    }
+    stage_scene<T, kShared>(sc, smem + 256 * sizeof(double) + cw_bytes, S);   // ends with __syncthreads() when staging
     if constexpr (!kShared) __syncthreads();
+    S.g.sv.cw = cw;
     // Sample split: k = 2^ksplit_log2 lanes share one pixel, lane `sub` tracing samples s0 + sub, s0 + sub + k, ...
     // (summed with shuffles at the end).  A warp then covers 32/k pixels -- pw x ph = 8x4, 8x2, 4x2, 2x2, 2x1, 1x1 --
     // and a CTA (4 x 2 warps) 256/k pixels: finer work units for small frames, row bands and sample ranges, so the
@@ -241,6 +254,19 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     const uint32_t pixel = (uint32_t)(y * pp.W + x);
     // integer-valued sums: exact in uint32 (int fold: colours <= 65535, samples per launch <= 65536) / in double
     typename std::conditional<kIntFold, unsigned, double>::type a0 = 0, a1 = 0, a2 = 0;
+    // primary rays of this warp tile: spheres its cone of camera rays can touch (cone_candidates, rt_trace.cuh)
+    unsigned long long cand = ~0ull;
+    bool first_trip = false;                          // warp-uniform: every live lane is about to trace its camera ray
+    if constexpr (kMode == 3 && !kRegen && RT_PRIMARY_CULL) if (pp.primary_cull) {
+        const int bw = 1 << pw_sh, bh = 1 << ph_sh;   // the warp's pixel block
+        const int x0 = ((bx << 2) + (wt & 3)) << pw_sh;
+        const int y0 = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) + ((wt >> 2) << ph_sh);
+        const V3<T> d0 = path_camera_ray<T>(pp, x0, y0, T(0.5) * T(bw), T(0.5) * T(bh));
+        const float ex = 0.5f * (float)bw * (2.f / (float)pp.W) * (float)pp.aspect * (float)pp.half_w;
+        const float ey = 0.5f * (float)bh * (2.f / (float)pp.H) * (float)pp.half_h;
+        const float alpha = sqrtf(ex * ex + ey * ey) * 1.001f;      // angle <= distance on the z = -1 plane
+        cand = cone_candidates(S.g.sv.sph, S.g.sv.n, cam, d0, alpha, lane_);
+    }
 
     if (pp.max_bounces <= 0) {                        // degenerate: every call returns (2,2,5) at the depth check
         const int mine = has_pixel ? (ns - sub + kk - 1) >> lk : 0;      // samples of this lane
@@ -260,10 +286,13 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             n_rays++;                                 // trace_ray_traditional call count, chandelier.py:432
         };
         if (alive) start_sample(s);
+        first_trip = true;
         bool pend = false;                            // lock-step: path ended, fold deferred to the end of the sample
         int pl0 = 2, pl1 = 2, pl2 = 5;
         double pf0 = 2.0, pf1 = 2.0, pf2 = 5.0;
         for (;;) {
+            const bool primary_trip = first_trip;     // this trip traces the camera rays of a sample (lock-step only)
+            first_trip = false;
             bool ended = false;
             int leaf0 = 2, leaf1 = 2, leaf2 = 5;      // miss / depth limit: Colour(2,2,5)
             double lf0 = 2.0, lf1 = 2.0, lf2 = 5.0;
@@ -271,7 +300,14 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
                 T t;
                 n_query++;
-                const int i = nearest<T, true, kBvh, PK>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes, pkc);
+                int i;
+                if (kMode == 3 && !kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) {
+                    if constexpr (kMode == 3) {
+                        i = select_candidates(S.g.sv.cw, cand, S.g.sv.key_mask6, O, D);
+                        if (i >= 0) t = winner_distance(S.g.sv.sph[i], O, D);
+                        n_tests += (unsigned)__popcll(cand);
+                    }
+                } else i = nearest<T, true, kBvh, PK>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes, pkc);
                 if (i < 0) ended = true;
                 else {
                     n_inter++;
@@ -333,6 +369,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 s += kk;
                 if (s - sub >= pp.s1) break;
                 if (has_pixel && s < pp.s1) { alive = true; start_sample(s); }
+                first_trip = true;
                 continue;
             }
             if (alive && ended) {
@@ -357,6 +394,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 s += kk;
                 if (s - sub >= pp.s1) break;                       // s - sub is warp-uniform in this schedule
                 if (has_pixel && s < pp.s1) { alive = true; start_sample(s); }
+                first_trip = true;
             }
         }
     }
@@ -1030,7 +1068,7 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     int mode = mode_for(sc, extra);
     // small brute-force FP32 scenes: sphere pairs through the parameter block (kMode 3)
     if (mode == 0 && sizeof(T) == 4 && pkc && ((sc.n + 7) & ~7) <= RT_PKC_MAX && sc.nL <= RT_LPKC_MAX) mode = 3;
-    const size_t sm = (mode != 2 ? smem_for(sc) : 0) + extra;
+    const size_t sm = (mode != 2 ? smem_for(sc) : 0) + extra + (mode == 3 ? (size_t)((sc.n + 7) & ~7) * sizeof(float4) : 0);
     cudaError_t e = cudaSuccess;
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \

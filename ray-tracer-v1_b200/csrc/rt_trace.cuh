@@ -189,6 +189,69 @@ RT_DEV int brute_select_pkc(const PkConst &pkc, int n_padded, int key_mask6, V3<
     return best < RT_KEY_INF ? (best & 63) : -1;
 }
 
+// ---- primary rays: warp-coherent candidate list.
+// All rays of a warp tile start at the camera and pass through one small pixel block, i.e. they lie in a cone of
+// half-angle <= alpha around the block's central direction d0.  A sphere that no ray of that cone can touch is a miss
+// for every lane, so the nearest-hit query may skip it WITHOUT changing its result: keys of the remaining spheres are
+// computed with the very same operations as in brute_select_pkc (scalar FFMA instead of FFMA2 lanes), so the winner,
+// ties included, is identical and frames stay bit-for-bit the same.  cone_candidates builds the list once per warp
+// tile (it does not depend on the sample): lane l tests spheres l and l + 32.
+//   kept  <=>  camera inside the sphere, or  dist(centre, central ray) <= r + |L| alpha  and the centre is not behind
+// (rotating a ray by alpha moves its closest approach to a point at distance |L| by at most |L| alpha); margins cover
+// the rounding of this test itself.
+RT_DEV unsigned long long cone_candidates(const float4 *sph, int n, V3<float> cam, V3<float> d0, float alpha, int lane) {
+    unsigned m[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int i = lane + 32 * h;
+        bool keep = false;
+        if (i < n) {
+            const float4 s = sph[i];
+            const float lx = s.x - cam.x, ly = s.y - cam.y, lz = s.z - cam.z;
+            const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx)), tc = fmaf(lz, d0.z, fmaf(ly, d0.y, lx * d0.x));
+            const float reach = fmaf(sqrtf(ll), alpha, s.w) * 1.0005f + 1e-5f;       // r + |L| alpha, grown
+            const float perp2 = fmaf(-tc, tc, ll);
+            keep = !(ll > s.w * s.w * 1.001f) || (perp2 <= reach * reach && tc >= -reach);
+            keep = keep || !(ll == ll) || !(reach == reach);                          // never cull on NaN
+        }
+        m[h] = __ballot_sync(0xffffffffu, keep);
+    }
+    return ((unsigned long long)m[1] << 32) | m[0];
+}
+
+// nearest hit among the candidates (warp-uniform mask): the keys of brute_select_pkc, one sphere at a time
+RT_DEV int select_candidates(const float4 *cw, unsigned long long mask, int key_mask6, V3<float> O, V3<float> D) {
+    const float od = dot(O, D), oo = dot(O, O);
+    const float bx = 2.f * O.x, by = 2.f * O.y, bz = 2.f * O.z;
+    int best = RT_KEY_INF;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned m = h ? (unsigned)(mask >> 32) : (unsigned)mask;
+        const float4 *base = cw + 32 * h;
+        while (m) {
+            const int i = __ffs((int)m) - 1;
+            m &= m - 1u;
+            const float4 c = base[i];
+            const float tca = fmaf(c.z, D.z, fmaf(c.y, D.y, fmaf(c.x, D.x, -od)));
+            const float nm = fmaf(c.z, bz, fmaf(c.y, by, fmaf(c.x, bx, c.w + -oo)));
+            const float disc = fmaf(tca, tca, nm);
+            const float s = M<float>::sqrt(__int_as_float(__float_as_int(disc) | (__float_as_int(tca) & (int)0x80000000)));
+            const float t = fmaf(s, -1.f, tca);
+            best = min(best, (__float_as_int(t) & key_mask6) | (i + 32 * h));
+        }
+    }
+    return best < RT_KEY_INF ? (best & 63) : -1;
+}
+
+// winner's distance from the cancellation-free form |L - tca D|^2; a silhouette-grazing winner whose robust
+// discriminant rounds below zero gets thc = 0
+RT_DEV float winner_distance(float4 w, V3<float> O, V3<float> D) {
+    const V3<float> L = centre_of<float>(w) - O;
+    const float tca = dot(L, D);
+    const V3<float> f = L - D * tca;
+    return tca - M<float>::sqrt(fmaxf(fmaf(w.w, w.w, -dot(f, f)), 0.f));
+}
+
 template <typename T, bool kAbs, bool kBvh, typename PK = PkNone>
 RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests,
                    const PK &pkc = PK()) {
