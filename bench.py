@@ -31,7 +31,7 @@ os.dup2(2, 1)
 import numpy as np  # noqa: E402
 
 W, H, SPP, DEPTH, THRESHOLD, FOV = 1920, 1080, 64, 5, 0.9, 60.0
-NCU_DRAM_BYTES_PER_LAUNCH = 56064 + 1310464    # profiles/ncu_path_kernel_r1g.txt (one ncu --set full capture of a bench launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 92416 + 1076736    # profiles/ncu_path_kernel_r1j.txt (one ncu --set full capture of a 64-spp launch)
 CPU_W, CPU_H, CPU_SPP = 960, 540, 16          # bounded CPU sample: 1/16 of the frame's pixel-samples
 METRIC, UNIT = "Mrays/s (complex scene, 1920x1080, 64 spp)", "Mrays/s"
 WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer)"
@@ -305,6 +305,11 @@ def main():
         # per GPU (this rank's launches; all ranks run the same kernel on equal bands)
         q_rank0 = queries / world
         achieved = q_rank0 * fpq / (kernel_ms * 1e-3) / 1e12
+        # the same with the sphere tests the kernel actually executed (camera rays skip the spheres outside their warp
+        # tile's cone; secondary rays test all N): never above `achieved`
+        tests_per_query = tests / max(queries, 1)
+        fpq_exec = 20.0 * tests_per_query + 15 + 25 * n_l + 70
+        achieved_exec = q_rank0 * fpq_exec / (kernel_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -319,13 +324,17 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(r.h2d_bytes),
                     "d2h_bytes_per_step": int(W * H * 3 * 4), "ms_per_step": 1e3 * float(te[0]) / args.steps},
             "gpu_launches": launches,
-            "roofline": {"bound": "fp32", "kernel": "path_kernel<float, 0, true, false> (brute force, integer fold, lock-step)", "achieved": achieved, "peak": fp32_peak,
+            "roofline": {"bound": "fp32", "kernel": "path_kernel<float, 3, true, false> (persistent warps, sphere/light pairs as uniform operands, "
+                                                      "camera-ray candidate lists, integer fold, lock-step)",
+                         "achieved": achieved, "peak": fp32_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                          "peak_source": "rt_measure_fp32_peak (FFMA issue-rate micro-benchmark, measured in this run; "
                                         "MEASURED_PEAKS.json has no FP32 figure)",
                          "flop_per_query": fpq, "queries_per_launch": q_rank0 / args.steps,
+                         "sphere_tests_per_query_executed": tests_per_query, "flop_per_query_executed": fpq_exec,
+                         "achieved_executed": achieved_exec, "frac_executed": achieved_exec / fp32_peak,
                          "kernel_ms": kernel_ms / args.steps,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ncu_path_kernel_r1g.txt:
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ncu_path_kernel_r1j.txt:
                          # the 33 MB framebuffer write mostly stays in the 126 MB L2 past the end of the kernel
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "hbm_algorithmic_bytes_per_launch": W * H * 16 // world},

@@ -369,7 +369,8 @@ def test_sample_split_gives_the_same_frame(nat):
             p = sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, ksplit=k, schedule=schedule)
             _, out, st = sc.render_path_host(p, nat.F32)
             assert np.array_equal(out, ref), (k, schedule)
-            assert np.array_equal(st[:6], st_ref[:6]), (k, schedule)
+            assert np.array_equal(st[:5], st_ref[:5]), (k, schedule)      # slot 5 (executed sphere tests) depends on the tiling
+            assert st[5] <= st[4] * len(fs.ids)
     # row band + sample range, accumulated in two launches with different k
     acc = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
     for (s0, s1), k in (((0, 7), 4), ((7, 11), 8)):
