@@ -203,21 +203,43 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     RT_MODE_DECL;
     using PK = typename std::conditional<kMode == 3, PkConst, PkNone>::type;
     extern __shared__ __align__(32) unsigned char smem[];
-    double *div255 = reinterpret_cast<double *>(smem);                 // [256] k / 255.0, correctly rounded
-    for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
     Staged<T> S;
-    float4 *cw = reinterpret_cast<float4 *>(smem + 256 * sizeof(double));     // kMode 3: (cx, cy, cz, w) per sphere
-    const size_t cw_bytes = kMode == 3 ? (size_t)((sc.n + 7) & ~7) * sizeof(float4) : 0;
+    double *div255;                                                    // [256] k / 255.0, correctly rounded
+    const float4 *hitrec = nullptr;                                    // kMode 3: (1/r, reflective, emissive, -) per sphere
     if constexpr (kMode == 3) {
+        // <= RT_PKC_MAX spheres: STATIC shared arrays at fixed offsets, so every per-hit fetch is one LDS with an
+        // immediate base (the dynamic layout costs ~8 address instructions per fetch, its offsets depend on n)
+        __shared__ __align__(16) float4 s_sph[RT_PKC_MAX], s_hit[RT_PKC_MAX], s_col[RT_PKC_MAX], s_cw[RT_PKC_MAX];
+        __shared__ __align__(16) double s_div255[256];
+        const int n_pad = (sc.n + 7) & ~7;
         const float *pkf = reinterpret_cast<const float *>(sc.pk);       // pair j: cx0 cx1 cy0 cy1 | cz0 cz1 w0 w1
-        for (int i = threadIdx.x; i < ((sc.n + 7) & ~7); i += blockDim.x) {
+        for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
             const float *q = pkf + 8 * (i >> 1) + (i & 1);
-            cw[i] = make_float4(q[0], q[2], q[4], q[6]);
+            s_cw[i] = make_float4(q[0], q[2], q[4], q[6]);
+            s_sph[i] = reinterpret_cast<const float4 *>(sc.sph)[i];
+            if (i < sc.n) {
+                const float4 mt = reinterpret_cast<const float4 *>(sc.mat)[i], cl = reinterpret_cast<const float4 *>(sc.col)[i];
+                s_hit[i] = make_float4(cl.w, mt.x, mt.z, 0.f);           // (1/r, reflective, emissive, -)
+                s_col[i] = cl;
+            }
         }
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) s_div255[k] = __ddiv_rn((double)k, 255.0);
+        div255 = s_div255;
+        S.g.sv.n = sc.n; S.g.sv.n_padded = n_pad; S.g.sv.key_mask = sc.key_mask; S.g.sv.key_mask6 = sc.key_mask6;
+        S.g.bvh = sc.bvh;
+        hitrec = s_hit;
+        S.g.sv.sph = reinterpret_cast<const typename M<T>::v4 *>(s_sph); S.g.sv.mat = sc.mat;
+        S.g.sv.col = reinterpret_cast<const typename M<T>::v4 *>(s_col); S.g.sv.pk = sc.pk; S.g.sv.ids = sc.ids; S.g.sv.cw = s_cw;
+        S.lb.nL = sc.nL; S.lb.l_pos = sc.l_pos; S.lb.l_col = sc.l_col; S.lb.l_index = sc.l_index; S.lb.lpk = sc.lpk;
+        S.la.nG = 0; S.la.nP = 0;
+        __syncthreads();
+    } else {
+        div255 = reinterpret_cast<double *>(smem);
+        for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
+        stage_scene<T, kShared>(sc, smem + 256 * sizeof(double), S);    // ends with __syncthreads() when staging
+        if constexpr (!kShared) __syncthreads();
+        S.g.sv.cw = nullptr;
     }
-    stage_scene<T, kShared>(sc, smem + 256 * sizeof(double) + cw_bytes, S);   // ends with __syncthreads() when staging
-    if constexpr (!kShared) __syncthreads();
-    S.g.sv.cw = cw;
     // Sample split: k = 2^ksplit_log2 lanes share one pixel, lane `sub` tracing samples s0 + sub, s0 + sub + k, ...
     // (summed with shuffles at the end).  A warp then covers 32/k pixels -- pw x ph = 8x4, 8x2, 4x2, 2x2, 2x1, 1x1 --
     // and a CTA (4 x 2 warps) 256/k pixels: finer work units for small frames, row bands and sample ranges, so the
@@ -301,17 +323,32 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 T t;
                 n_query++;
                 int i;
-                if (kMode == 3 && !kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) {
-                    if constexpr (kMode == 3) {
+                typename M<T>::v4 m;                   // material: (reflective, transparent, emissive, ior)
+                T inv_r = T(0);
+                V3<T> centre = mk<T>(T(0), T(0), T(0));
+                if constexpr (kMode == 3) {
+                    // one LDS.128 for the winner's (centre, r) -- shared by the robust distance and the normal -- and one
+                    // for its (1/r, reflective, emissive) record
+                    if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) {
                         i = select_candidates(S.g.sv.cw, cand, S.g.sv.key_mask6, O, D);
-                        if (i >= 0) t = winner_distance(S.g.sv.sph[i], O, D);
                         n_tests += (unsigned)__popcll(cand);
+                    } else {
+                        i = brute_select_pkc(pkc, S.g.sv.n_padded, S.g.sv.key_mask6, O, D);
+                        n_tests += (unsigned)S.g.sv.n;
                     }
-                } else i = nearest<T, true, kBvh, PK>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes, pkc);
+                    if (i >= 0) {
+                        const float4 w = S.g.sv.sph[i], hr = hitrec[i];
+                        t = winner_distance(w, O, D);
+                        centre = mk<T>(w.x, w.y, w.z); inv_r = hr.x;
+                        m.x = hr.y; m.y = T(0); m.z = hr.z; m.w = T(1);
+                    }
+                } else {
+                    i = nearest<T, true, kBvh, PK>(S.g, O, D, RT_NO_ID_DEV, t, n_tests, n_boxes, pkc);
+                    if (i >= 0) m = S.g.sv.mat[i];
+                }
                 if (i < 0) ended = true;
                 else {
                     n_inter++;
-                    const typename M<T>::v4 m = S.g.sv.mat[i];
                     if (m.z != T(0)) {                                               // emissive: its own colour
                         n_light++;
                         if (sc.small && sc.small[i]) n_small++;
@@ -321,10 +358,12 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                         ended = true;
                     } else {
                         Hit<T> h;
-                        finish_hit<T>(S.g, O, D, i, t, h);
-                        st.idx[depth] = (uint32_t)i;
+                        if constexpr (kMode == 3) { h.idx = i; h.t = t; h.p = O + D * t; h.n = (h.p - centre) * inv_r; }
+                        else finish_hit<T>(S.g, O, D, i, t, h);
+                        if constexpr (kMode != 3) st.idx[depth] = (uint32_t)i;
                         if constexpr (M<T>::exact) st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
-                        else if constexpr (kMode == 3) st.direct[depth] = direct_light_pkc(pkc, (S.lb.nL + 1) >> 1, h.p, h.n);
+                        else if constexpr (kMode == 3)       // one stack word per level: sphere index above the 24 colour bits
+                            st.direct[depth] = direct_light_pkc(pkc, (S.lb.nL + 1) >> 1, h.p, h.n) | ((uint32_t)i << 24);
                         else st.direct[depth] = direct_light_pk(S.lb.lpk, (S.lb.nL + 1) >> 1, h.p, h.n);
                         depth++;
                         n_rays++;                                                    // the recursive call ...
@@ -358,11 +397,11 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     pend = false;
                     if constexpr (kIntFold) {
                         int c[3] = {pl0, pl1, pl2};
-                        fold_path_int<T>(S.g, st, depth, div255, c);
+                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c);
                         a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                     } else {
                         double c[3] = {pf0, pf1, pf2};
-                        fold_path<T>(S.g, st, depth, c);
+                        fold_path<T, kMode == 3>(S.g, st, depth, c);
                         a0 += c[0]; a1 += c[1]; a2 += c[2];
                     }
                 }
@@ -376,11 +415,11 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 alive = false;
                 if constexpr (kIntFold) {
                     int c[3] = {leaf0, leaf1, leaf2};
-                    fold_path_int<T>(S.g, st, depth, div255, c);
+                    fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c);
                     a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                 } else {
                     double c[3] = {lf0, lf1, lf2};
-                    fold_path<T>(S.g, st, depth, c);
+                    fold_path<T, kMode == 3>(S.g, st, depth, c);
                     a0 += c[0]; a1 += c[1]; a2 += c[2];
                 }
                 if constexpr (kRegen) {
@@ -1068,7 +1107,7 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     int mode = mode_for(sc, extra);
     // small brute-force FP32 scenes: sphere pairs through the parameter block (kMode 3)
     if (mode == 0 && sizeof(T) == 4 && pkc && ((sc.n + 7) & ~7) <= RT_PKC_MAX && sc.nL <= RT_LPKC_MAX) mode = 3;
-    const size_t sm = (mode != 2 ? smem_for(sc) : 0) + extra + (mode == 3 ? (size_t)((sc.n + 7) & ~7) * sizeof(float4) : 0);
+    const size_t sm = mode == 3 ? 0 : (mode != 2 ? smem_for(sc) : 0) + extra;      // kMode 3 uses static shared arrays
     cudaError_t e = cudaSuccess;
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \

@@ -481,11 +481,11 @@ struct PathStack {
 
 // final = int(albedo * (min(255, direct + indirect) / 255.0)) per channel, folded from the leaf back to the camera
 // (chandelier.py:509-521).  Always evaluated in double: the truncation must see the reference's rounding.
-template <typename T>
+template <typename T, bool kPacked = false>
 RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[3]) {
     for (int k = depth - 1; k >= 0; --k) {
-        const typename M<T>::v4 col = g.sv.col[st.idx[k]];
         const uint32_t d = st.direct[k];
+        const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
         double t0 = (double)(d & 255u) + c[0], t1 = (double)((d >> 8) & 255u) + c[1], t2 = (double)((d >> 16) & 255u) + c[2];
         t0 = t0 < 255.0 ? t0 : 255.0; t1 = t1 < 255.0 ? t1 : 255.0; t2 = t2 < 255.0 ? t2 : 255.0;
         c[0] = ::trunc(__dmul_rn((double)col.x, __ddiv_rn(t0, 255.0)));
@@ -497,11 +497,12 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
 // Same fold for integer-valued leaves (every scene of the reference: colours are 0-255 ints): tot is then an integer
 // in [0,255] at every level, so tot/255.0 comes from a 256-entry table of correctly rounded doubles (identical to
 // the division) and the running colour stays an int.  Still a double multiply: the truncation sees the same product.
-template <typename T>
+// kPacked: the level's sphere index rides in bits 24-31 of `direct` (scenes of <= 256 spheres), st.idx is not used.
+template <typename T, bool kPacked = false>
 RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3]) {
     for (int k = depth - 1; k >= 0; --k) {
-        const typename M<T>::v4 col = g.sv.col[st.idx[k]];
         const uint32_t d = st.direct[k];
+        const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
         const int t0 = min(255, (int)(d & 255u) + c[0]), t1 = min(255, (int)((d >> 8) & 255u) + c[1]),
                   t2 = min(255, (int)((d >> 16) & 255u) + c[2]);
         c[0] = __double2int_rz(__dmul_rn((double)col.x, div255[t0]));
