@@ -1,5 +1,6 @@
 // rt_api.cu -- the C ABI of librt_b200.so (include/rt_b200.h): scene handles resident in HBM, parameter marshalling
 // and stream-ordered launches of the kernels in rt_f32.cu / rt_f64.cu / rt_lbvh.cu.  No compute happens on the host.
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -51,7 +52,7 @@ struct rt_scene {
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
     mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS pairs of work counters of the persistent path kernel (zero at rest)
-    mutable unsigned sched_next = 0; // launches rotate through the slots, so launches in flight never share a pair
+    mutable std::atomic<unsigned> sched_next{0}; // launches rotate through the slots, so launches in flight never share a pair
     PkConst pkc;                  // host copy of the FP32 sphere pairs of a small scene (path kernel parameter block)
     bool pkc_ok = false;
 };
@@ -571,7 +572,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
         CU(cudaMemset(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
     }
-    unsigned *sched = sc->sched_dev + 2 * (sc->sched_next++ % RT_SCHED_SLOTS);
+    unsigned *sched = sc->sched_dev + 2 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
                       sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 ? &sc->pkc : nullptr, sched));
     return RT_OK;

@@ -299,8 +299,14 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         bool alive = has_pixel && s < pp.s1;          // lane has a path in flight
         bool more = alive;                            // lane still has samples to do (regen schedule)
         V3<T> O = cam, D = mk<T>(T(0), T(0), T(-1));
+        // colour at the end of the path: miss / depth limit give Colour(2,2,5), an emissive hit its own colour.  Lives
+        // across trips (reset per sample): in the lock-step schedule the fold waits for the warp's longest path.
+        int leaf0 = 2, leaf1 = 2, leaf2 = 5;
+        double lf0 = 2.0, lf1 = 2.0, lf2 = 5.0;
+        bool pend = false;                            // lane traced a sample whose fold is still due (lock-step)
         auto start_sample = [&](int smp) {
             depth = 0; O = cam;
+            leaf0 = 2; leaf1 = 2; leaf2 = 5; lf0 = 2.0; lf1 = 2.0; lf2 = 5.0; pend = true;
             rng.begin(pixel, (uint32_t)smp, pp.k0, pp.k1);
             uint32_t wa, wb;
             if (RT_PHILOX_RK) rng.pair_rk(0u, wa, wb, pp.rk); else rng.pair(0u, wa, wb);
@@ -309,15 +315,10 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         };
         if (alive) start_sample(s);
         first_trip = true;
-        bool pend = false;                            // lock-step: path ended, fold deferred to the end of the sample
-        int pl0 = 2, pl1 = 2, pl2 = 5;
-        double pf0 = 2.0, pf1 = 2.0, pf2 = 5.0;
         for (;;) {
             const bool primary_trip = first_trip;     // this trip traces the camera rays of a sample (lock-step only)
             first_trip = false;
             bool ended = false;
-            int leaf0 = 2, leaf1 = 2, leaf2 = 5;      // miss / depth limit: Colour(2,2,5)
-            double lf0 = 2.0, lf1 = 2.0, lf2 = 5.0;
             if (alive) {
                 // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
                 T t;
@@ -387,20 +388,16 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             if (RT_DEFER_FOLD && !kRegen) {
                 // lock-step: a lane whose path ends early only parks its leaf; the whole warp folds together once
                 // the sample's longest path has ended (one full-occupancy fold instead of several sparse ones)
-                if (alive && ended) {
-                    alive = false; pend = true;
-                    if constexpr (kIntFold) { pl0 = leaf0; pl1 = leaf1; pl2 = leaf2; }
-                    else { pf0 = lf0; pf1 = lf1; pf2 = lf2; }
-                }
+                if (ended) alive = false;             // (ended is only ever set by a live lane)
                 if (__any_sync(0xffffffffu, alive)) continue;
                 if (pend) {
                     pend = false;
                     if constexpr (kIntFold) {
-                        int c[3] = {pl0, pl1, pl2};
+                        int c[3] = {leaf0, leaf1, leaf2};
                         fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c);
                         a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                     } else {
-                        double c[3] = {pf0, pf1, pf2};
+                        double c[3] = {lf0, lf1, lf2};
                         fold_path<T, kMode == 3>(S.g, st, depth, c);
                         a0 += c[0]; a1 += c[1]; a2 += c[2];
                     }
