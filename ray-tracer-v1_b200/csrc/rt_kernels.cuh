@@ -109,6 +109,9 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #ifndef RT_PATH_MIN_BLOCKS
 #define RT_PATH_MIN_BLOCKS 3   /* 3 x 256 threads per SM at <= 85 registers: measured 2.7 % faster than 4 at <= 64 */
 #endif
+#ifndef RT_PATH_MIN_BLOCKS_PKC
+#define RT_PATH_MIN_BLOCKS_PKC 4   /* kMode 3 needs 72 registers unconstrained: 4 CTAs/SM at 64 measured 2.2 % faster (no spills) */
+#endif
 #ifndef RT_DEFER_FOLD
 #define RT_DEFER_FOLD 1        /* lock-step schedule: fold once per sample and warp (A/B: see DESIGN.md) */
 #endif
@@ -197,7 +200,7 @@ template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, 
 //                   trip.  Pays off only when early termination is common and the per-sample code is short.
 // kIntFold: integer fold through the div255 table (all leaf colours integer-valued), else the double-division fold.
 template <typename T, int kMode, bool kIntFold, bool kRegen>
-__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_PATH_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? (kMode == 3 ? RT_PATH_MIN_BLOCKS_PKC : RT_PATH_MIN_BLOCKS) : 1))
 path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned long long *stats,
             const __grid_constant__ typename std::conditional<kMode == 3, PkConst, PkNone>::type pkc) {
     RT_MODE_DECL;
