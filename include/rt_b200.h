@@ -206,7 +206,8 @@ int rt_render_simple_host(rt_scene *scene, int precision, const rt_simple_params
  *      non-emissive sphere; every step records (obs22, action2, next_obs22, reward, hit_light) until a light is hit,
  *      the ray escapes or max_steps transitions exist.  All outputs are device arrays padded to max_steps:
  *      obs/next_obs [n,max_steps,22] f32, action [n,max_steps,2] f32, reward [n,max_steps] f32, hit [n,max_steps] u8,
- *      length [n] int32 (transitions recorded), hit_light [n] u8.  stats_dev (optional) uint64[8]: [4] queries. */
+ *      length [n] int32 (transitions recorded), hit_light [n] u8 (obs / next_obs 8-byte aligned).  stats_dev
+ *      (optional) uint64[8]: [4] queries. */
 int rt_generate_trajectories(rt_scene *scene, int precision, int32_t n_traj, int32_t max_steps, int32_t max_bounces,
                              uint64_t seed, float *obs_dev, float *action_dev, float *next_obs_dev, float *reward_dev,
                              uint8_t *hit_dev, int32_t *length_dev, uint8_t *hit_light_dev, uint64_t *stats_dev,

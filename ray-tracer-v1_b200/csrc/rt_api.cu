@@ -871,6 +871,8 @@ RT_EXPORT int rt_generate_trajectories(rt_scene *scene, int precision, int32_t n
     if (n_traj < 0 || max_steps <= 0 || max_bounces <= 0) return fail(RT_ERR_INVALID, "bad trajectory counts");
     if (n_traj > 0 && (!obs_dev || !action_dev || !next_obs_dev || !reward_dev || !hit_dev || !length_dev || !hit_light_dev))
         return fail(RT_ERR_INVALID, "NULL output");
+    if (((uintptr_t)obs_dev | (uintptr_t)next_obs_dev) & 7u)
+        return fail(RT_ERR_INVALID, "obs / next_obs must be 8-byte aligned (88-byte records are written as 8-byte stores)");
     CU(cudaSetDevice(scene->device));
     unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
     if (precision == RT_F64)

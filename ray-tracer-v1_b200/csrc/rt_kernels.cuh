@@ -712,14 +712,15 @@ __global__ void __launch_bounds__(128) trajectory_kernel(SceneDev<T> sc, int n_t
                 const size_t tr = (size_t)j * max_steps + len;
                 const bool lit = S.g.sv.mat[hi].z != T(0);
                 float *po = obs + 22 * tr, *pn = next_obs + 22 * tr;
+                // 22 floats = 88 bytes per record, 8-byte aligned for every transition index: eleven 8-byte stores
 #pragma unroll
-                for (int k = 0; k < 22; ++k) po[k] = cur[k];
+                for (int k = 0; k < 11; ++k) reinterpret_cast<float2 *>(po)[k] = make_float2(cur[2 * k], cur[2 * k + 1]);
                 action[2 * tr] = a0; action[2 * tr + 1] = a1;
                 const typename M<T>::v4 col = S.g.sv.col[hi];
                 traj_obs<T>(S.g, h.p, h.n, rd, bounce + 1, lit ? col.x : T(0), lit ? col.y : T(0), lit ? col.z : T(0), hi,
                             max_bounces, cur);
 #pragma unroll
-                for (int k = 0; k < 22; ++k) pn[k] = cur[k];
+                for (int k = 0; k < 11; ++k) reinterpret_cast<float2 *>(pn)[k] = make_float2(cur[2 * k], cur[2 * k + 1]);
                 reward[tr] = lit ? 1.f : 0.f; hit[tr] = (uint8_t)lit;
                 len++;
                 if (lit) { lit_any = 1; break; }
