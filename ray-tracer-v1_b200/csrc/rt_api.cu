@@ -574,7 +574,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     }
     unsigned *sched = sc->sched_dev + 2 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
-                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 ? &sc->pkc : nullptr, sched));
+                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 && !(p->schedule & 4) ? &sc->pkc : nullptr, sched));
     return RT_OK;
 }
 

@@ -227,8 +227,9 @@ def build_optimized_env_scene(ns=default_ns):
 
 
 # ------------------------------------------------------------- C4 scaled (LBVH)
-def build_many_spheres_flat(n_small, seed=0):
+def build_many_spheres_flat(n_small, seed=0, emissive_fraction=0.01):
     """Chandelier room + ``n_small`` spheres r~U(0.02,0.1) uniform in [-4,4]x[-1,6]x[2,10], 1% emissive
+    (``emissive_fraction``)
     (SURVEY.md section 8d, C4 scaled variant for the on-device LBVH).  Returns a FlatScene directly (no
     per-sphere Python objects: n_small reaches 1e5)."""
     from .scene import flatten_scene
@@ -238,7 +239,7 @@ def build_many_spheres_flat(n_small, seed=0):
     lo, hi = np.array([-4.0, -1.0, 2.0]), np.array([4.0, 6.0, 10.0])
     centre = lo + (hi - lo) * rs.random_sample((n_small, 3))
     radius = 0.02 + 0.08 * rs.random_sample(n_small)
-    emissive = rs.random_sample(n_small) < 0.01
+    emissive = rs.random_sample(n_small) < emissive_fraction
     mirror = (~emissive) & (rs.random_sample(n_small) < 0.05)
     colour = np.floor(100 + 156 * rs.random_sample((n_small, 3)))
     material = np.zeros((n_small, 4))

@@ -186,6 +186,31 @@ def test_primary_candidate_lists_change_nothing(nat):
     sc.close()
 
 
+def test_parameter_block_loop_at_its_limits(nat):
+    """64 spheres / 32 lights is the largest scene whose sphere and light pairs ride in the kernel parameter block; one
+    more sphere falls back to the shared-memory loop.  Both sizes: FP32 against the FP64 parity build, and (64 spheres)
+    the two FP32 loops against each other."""
+    from ray_tracer_v1_b200 import scenes
+    for n in (64, 65, 8, 57):
+        fs = scenes.build_many_spheres_flat(n - 6, seed=5, emissive_fraction=0.45 if n == 64 else 0.1)
+        assert len(fs.ids) == n, len(fs.ids)
+        if n == 64:
+            assert len(fs.l_index) <= 32
+        sc = nat.DeviceScene(fs)
+        W, H, spp = 96, 54, 4
+        p = sc.path_params((0.0, 2.0, 0.0), W, H, spp, 4, 0.0, seed=9)
+        _, f64, st64 = sc.render_path_host(p, nat.F64)
+        _, f32, st32 = sc.render_path_host(p, nat.F32)
+        assert np.abs(st32[:4].astype(np.int64) - st64[:4].astype(np.int64)).max() <= 0.01 * st64[0]
+        assert ((np.abs(f32[..., :3] - f64[..., :3]) > spp).any(axis=2)).mean() < 0.03
+        if n <= 64:
+            p2 = sc.path_params((0.0, 2.0, 0.0), W, H, spp, 4, 0.0, seed=9, schedule=4)
+            _, smem, st_s = sc.render_path_host(p2, nat.F32)
+            assert (smem != f32).any(axis=2).mean() < 0.01
+            assert st_s[5] == st_s[4] * n and st32[5] < st_s[5]       # only the parameter-block kernel has candidate lists
+        sc.close()
+
+
 def test_path_schedules_agree(nat):
     """Lock-step and path-regeneration schedules are two orders of the same arithmetic: identical sums and counters."""
     for name in ("path_chandelier_48x27", "path_complex_48x27"):
