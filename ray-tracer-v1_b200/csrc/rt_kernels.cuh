@@ -109,6 +109,9 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #ifndef RT_PATH_MIN_BLOCKS
 #define RT_PATH_MIN_BLOCKS 3   /* 3 x 256 threads per SM at <= 85 registers: measured 2.7 % faster than 4 at <= 64 */
 #endif
+#ifndef RT_WHITTED_MIN_BLOCKS
+#define RT_WHITTED_MIN_BLOCKS 2   /* Algorithm A frame kernel: 120 registers unconstrained */
+#endif
 #ifndef RT_PATH_MIN_BLOCKS_PKC
 #define RT_PATH_MIN_BLOCKS_PKC 4   /* kMode 3 needs 72 registers unconstrained: 4 CTAs/SM at 64 measured 2.2 % faster (no spills) */
 #endif
@@ -128,7 +131,7 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 
 // ------------------------------------------------------------------ Algorithm A frame
 template <typename T, int kMode>
-__global__ void __launch_bounds__(256) whitted_kernel(SceneDev<T> sc, WhittedDev<T> wp, typename M<T>::v4 *accum,
+__global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS : 1)) whitted_kernel(SceneDev<T> sc, WhittedDev<T> wp, typename M<T>::v4 *accum,
                                                       int *hit_out, unsigned long long *stats) {
     RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];

@@ -209,8 +209,9 @@ RT_DEV unsigned long long cone_candidates(const float4 *sph, int n, V3<float> ca
             const float4 s = sph[i];
             const float lx = s.x - cam.x, ly = s.y - cam.y, lz = s.z - cam.z;
             const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx)), tc = fmaf(lz, d0.z, fmaf(ly, d0.y, lx * d0.x));
-            const float reach = fmaf(sqrtf(ll), alpha, s.w) * 1.0005f + 1e-5f;       // r + |L| alpha, grown
-            const float perp2 = fmaf(-tc, tc, ll);
+            const float reach = fmaf(sqrtf(ll), alpha, s.w) * 1.002f + 1e-4f;        // r + |L| alpha, grown
+            const float fx = fmaf(-tc, d0.x, lx), fy = fmaf(-tc, d0.y, ly), fz = fmaf(-tc, d0.z, lz);
+            const float perp2 = fmaf(fz, fz, fmaf(fy, fy, fx * fx));                  // |L - tc d0|^2: no cancellation
             keep = !(ll > s.w * s.w * 1.001f) || (perp2 <= reach * reach && tc >= -reach);
             keep = keep || !(ll == ll) || !(reach == reach);                          // never cull on NaN
         }
