@@ -224,6 +224,10 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
     std::vector<uint8_t> small((size_t)(s->n > 0 ? s->n : 1), 0);
     if (s->small) std::memcpy(small.data(), s->small, (size_t)s->n);
     CU(cudaMemcpyAsync(sc->small_dev, small.data(), small.size(), cudaMemcpyHostToDevice, st));
+    if (!sc->sched_dev) {                   // work counters of the persistent path kernel: zero at rest, re-armed by every launch
+        CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
+        CU(cudaMemsetAsync(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned), st));
+    }
     CU(cudaStreamSynchronize(st));          // the staging vectors die at return
     {   // small scenes: the path kernel takes the FP32 pair array through its parameter block (kMode 3)
         const int n_pad = (s->n + 7) & ~7;
@@ -568,10 +572,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         else { while (lk < 5 && (pixels << lk) / 256 < want && (ns >> (lk + 1)) >= 2) ++lk; }
         pp.ksplit_log2 = lk;
     }
-    if (!sc->sched_dev) {
-        CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
-        CU(cudaMemset(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
-    }
+    if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
     unsigned *sched = sc->sched_dev + 2 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
                       sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 && !(p->schedule & 4) ? &sc->pkc : nullptr, sched));

@@ -13,7 +13,9 @@
 #pragma once
 #include "rt_trace.cuh"
 #include "rt_launch.h"
+#include <mutex>
 #include <type_traits>
+#include <vector>
 
 namespace rt {
 
@@ -1080,13 +1082,28 @@ cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void 
     return cudaGetLastError();
 }
 
-// CTAs of a persistent launch: what the current device keeps resident for this kernel (occupancy x SM count)
+// CTAs of a persistent launch: what the current device keeps resident for this kernel (occupancy x SM count); the
+// answer is cached per (device, kernel, shared-memory size) so that a launch costs no runtime query
 template <typename K> static unsigned persistent_ctas(K kernel, size_t smem_bytes, long long tiles) {
-    int dev = 0, sms = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
-        sms <= 0) sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem_bytes) != cudaSuccess || per_sm <= 0) per_sm = 1;
-    const long long g = (long long)sms * per_sm;
+    struct Key { int dev; const void *fn; size_t smem; long long ctas; };
+    static std::mutex mu;
+    static std::vector<Key> cache;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    long long g = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const Key &k : cache)
+            if (k.dev == dev && k.fn == (const void *)kernel && k.smem == smem_bytes) { g = k.ctas; break; }
+    }
+    if (g == 0) {
+        int sms = 0, per_sm = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, smem_bytes) != cudaSuccess || per_sm <= 0) per_sm = 1;
+        g = (long long)sms * per_sm;
+        std::lock_guard<std::mutex> lock(mu);
+        cache.push_back(Key{dev, (const void *)kernel, smem_bytes, g});
+    }
     return (unsigned)(tiles < g ? (tiles > 0 ? tiles : 1) : g);
 }
 

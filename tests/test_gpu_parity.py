@@ -211,6 +211,40 @@ def test_parameter_block_loop_at_its_limits(nat):
         sc.close()
 
 
+def test_persistent_launches_rearm_their_counters(nat):
+    """The path kernel's warps pull work from device counters that the launch itself re-arms: 150 launches (more than the
+    64 counter pairs a scene rotates through), alternating between two streams without host synchronisation, all give
+    the frame of a lone launch; so does a CUDA-graph replay (no memset node is needed)."""
+    import torch
+    z, fs = load_golden("path_complex_48x27")
+    sc = nat.DeviceScene(fs)
+    W, H, spp = 64, 36, 3
+    args = (z["cam"], W, H, spp, int(z["max_bounces"]), float(z["mirror_threshold"]))
+    ref = {}
+    for seed in (1, 2):
+        buf = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        sc.render_path(sc.path_params(*args, seed=seed), buf, nat.F32)
+        torch.cuda.synchronize()
+        ref[seed] = buf.cpu().numpy()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = [torch.zeros((H, W, 4), dtype=torch.float32, device="cuda") for _ in range(150)]
+    for k, buf in enumerate(bufs):
+        sc.render_path(sc.path_params(*args, seed=1 + k % 2), buf, nat.F32, stream=streams[k % 2].cuda_stream)
+    torch.cuda.synchronize()
+    for k, buf in enumerate(bufs):
+        assert np.array_equal(buf.cpu().numpy(), ref[1 + k % 2]), k
+    g, out = torch.cuda.CUDAGraph(), torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+    cap = torch.cuda.Stream()
+    with torch.cuda.graph(g, stream=cap):
+        sc.render_path(sc.path_params(*args, seed=2), out, nat.F32, stream=torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), ref[2])
+    sc.close()
+
+
 def test_path_schedules_agree(nat):
     """Lock-step and path-regeneration schedules are two orders of the same arithmetic: identical sums and counters."""
     for name in ("path_chandelier_48x27", "path_complex_48x27"):
