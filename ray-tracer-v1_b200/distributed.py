@@ -192,6 +192,18 @@ class PeerFabric:
         self._opened, self._own, self.ptrs = [], [], {}
 
 
+class PendingFrame:
+    """A frame on its way to pinned host memory (``to_host="async"``).  ``result()`` waits for the copy and returns the
+    numpy view [H,W,3] float32; the view stays valid until the frame after the next one is requested."""
+
+    def __init__(self, host, event):
+        self._host, self._event = host, event
+
+    def result(self):
+        self._event.synchronize()
+        return self._host.numpy()
+
+
 class ShardedPathRenderer:
     """Algorithm B frames on this rank's GPU, sharded over the process group by tiles or by samples.
 
@@ -231,17 +243,45 @@ class ShardedPathRenderer:
             dev = torch.device("cuda", self.device)
             ft = torch.float64 if self.precision == self.nat.F64 else torch.float32
             self.accum = torch.zeros((H, W, 4), dtype=ft, device=dev)
-            self.image = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+            # device image and pinned host image are double-buffered: with to_host="async" frame f is still being
+            # copied out (on the copy stream) while frame f + 1 renders
+            self.images = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in (0, 1)]
+            self.image = self.images[0]
             self.stats = torch.zeros(8, dtype=torch.int64, device=dev)       # uint64 counters, read as int64
-            self.host_image = torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True)
+            self.host_images = [torch.empty((H, W, 3), dtype=torch.float32, pin_memory=True) for _ in (0, 1)]
+            self.host_image = self.host_images[0]
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._copied = [torch.cuda.Event(), torch.cuda.Event()]          # copy of slot k has finished
+            self._frame = 0
             self._key = (W, H)
 
+    def _to_host(self, src, slot, release=None):
+        """Queue the device->host copy of ``src`` on the copy stream (after everything the current stream has queued)
+        into pinned slot ``slot``; ``release`` (optional) runs on the copy stream after the copy."""
+        torch = self.torch
+        ready = torch.cuda.Event()
+        ready.record()
+        cs = self._copy_stream
+        cs.wait_event(ready)
+        with torch.cuda.stream(cs):
+            self.host_images[slot].copy_(src, non_blocking=True)
+            if release is not None:
+                release(cs.cuda_stream)
+            self._copied[slot].record(cs)
+        self.d2h_bytes = self.host_images[slot].numel() * 4
+        return PendingFrame(self.host_images[slot], self._copied[slot])
+
     def render(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, mode="tiles", to_host=False):
-        """Render one frame cooperatively.  Returns (image, stats) on rank 0 -- image a CUDA tensor [H,W,3] float32, or
-        a numpy view of pinned host memory when ``to_host`` -- and (None, stats) elsewhere.  stats = this rank's
-        uint64[8] counter block as a CUDA int64 tensor (not reduced: callers sum what they need)."""
+        """Render one frame cooperatively.  Returns (image, stats) on rank 0 -- image a CUDA tensor [H,W,3] float32, a
+        numpy view of pinned host memory when ``to_host`` is True, or a ``PendingFrame`` when ``to_host == "async"``
+        (the copy runs on a second stream while the next frame renders) -- and (None, stats) elsewhere.  stats = this
+        rank's uint64[8] counter block as a CUDA int64 tensor (not reduced: callers sum what they need)."""
         torch, nat, sc = self.torch, self.nat, self.scene
         self._ensure(W, H)
+        self._frame += 1
+        slot = self._frame & 1
+        self.image = self.images[slot]
+        torch.cuda.current_stream().wait_event(self._copied[slot])         # slot's previous copy-out has finished
         rows = (0, H)
         samples = (0, spp)
         if mode == "tiles":
@@ -269,10 +309,8 @@ class ShardedPathRenderer:
         if self.rank != 0:
             return None, self.stats
         if to_host:
-            self.host_image.copy_(self.image, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            self.d2h_bytes = self.host_image.numel() * 4
-            return self.host_image.numpy(), self.stats
+            pending = self._to_host(self.image, slot)
+            return (pending if to_host == "async" else pending.result()), self.stats
         return self.image, self.stats
 
     # ---- fused sinks over NVLink peer memory ------------------------------------------------------------------
@@ -356,11 +394,11 @@ class ShardedPathRenderer:
             fab.wait("flags", 16, world, e, self._timed_out)
             out = self._fused_images[buf]
             if to_host:
-                self.host_image.copy_(out, non_blocking=True)
-                torch.cuda.current_stream().synchronize()
-                self.d2h_bytes = self.host_image.numel() * 4
-                out = self.host_image.numpy()
-            fab.signal("flags", 32, everyone, e)                           # this image buffer may be reused at e + 2
+                # the copy-out runs on the copy stream; the "buffer may be reused at e + 2" signal follows it there
+                pending = self._to_host(out, buf, release=lambda st: fab.signal("flags", 32, everyone, e, stream=st))
+                out = pending if to_host == "async" else pending.result()
+            else:
+                fab.signal("flags", 32, everyone, e)                       # this image buffer may be reused at e + 2
         return out, self.stats
 
     def fused_timed_out(self):

@@ -355,6 +355,30 @@ def test_c3_full_size_properties(nat):
     sc.close()
 
 
+def test_sharded_renderer_async_host_frames(nat):
+    """ShardedPathRenderer (one rank): to_host="async" hands back PendingFrames whose copies overlap the next render;
+    the frames equal the synchronous ones, through the NCCL-path code and through the fused sinks."""
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.distributed import ShardedPathRenderer
+    spec = scenes.build_complex()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    r = ShardedPathRenderer()
+    r.set_scene(fs)
+    W, H, spp = 160, 90, 4
+    args = (spec.camera, W, H, spp, spec.max_bounces, spec.mirror_threshold)
+    for fn in (r.render, r.render_fused):
+        want = [np.array(fn(*args, seed=s, to_host=True)[0]) for s in (1, 2, 3, 4)]
+        pend = [fn(*args, seed=s, to_host="async")[0] for s in (1, 2)]          # two frames in flight
+        got = [np.array(p.result()) for p in pend]
+        pend = [fn(*args, seed=s, to_host="async")[0] for s in (3, 4)]
+        got += [np.array(p.result()) for p in pend]
+        for a, b in zip(want, got):
+            assert np.array_equal(a, b)
+        assert not np.array_equal(want[0], want[1])
+    r.close()
+
+
 # ------------------------------------------------------------------ fused multi-GPU sinks (one rank: peers = self)
 def test_fused_sinks_equal_accumulate_then_resolve(nat):
     """rt_render_path_sink: the image sink (interleaved stripes rendered by separate launches) and the scatter-add
