@@ -556,7 +556,9 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             if (pp.band_y[0] != 0 || pp.band_y[sink->world] != p->H) return fail(RT_ERR_INVALID, "owner bands must cover the image");
         } else return fail(RT_ERR_INVALID, "unknown sink mode");
     }
-    // sample split: grow k while the grid has fewer than ~64 waves of 256-thread CTAs and every lane keeps >= 2 samples
+    // sample split (automatic): k lanes per pixel so that a lane keeps about 8 samples -- measured best at 8, 16, 32 and
+    // 64 samples per launch (k = 1, 2, 4, 8: tighter camera-ray cones against per-unit overhead) -- and, for small frames,
+    // more lanes per pixel until there are ~4 warp tiles per resident warp (every lane keeps >= 2 samples)
     if (pp.int_fold && p->ksplit != 0) {
         static int sm_cache[64] = {0};
         int sms = sc->device >= 0 && sc->device < 64 ? sm_cache[sc->device] : 0;
@@ -564,12 +566,15 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, sc->device) != cudaSuccess || sms <= 0) sms = 148;
             if (sc->device >= 0 && sc->device < 64) sm_cache[sc->device] = sms;
         }
-        const long long want = 64LL * 4 * sms;
+        const long long want = 4LL * 32 * sms;                 // warp tiles: 4 per resident warp (32 warps per SM)
         const int rows = pp.y1 - pp.y0, step = pp.tile_step > 1 ? pp.tile_step : 1, ns = p->s1 - p->s0;
         const long long pixels = (long long)pp.W * ((rows + step - 1) / step);
         int lk = 0;
         if (p->ksplit > 0) { while ((1 << (lk + 1)) <= p->ksplit && lk < 5) ++lk; }
-        else { while (lk < 5 && (pixels << lk) / 256 < want && (ns >> (lk + 1)) >= 2) ++lk; }
+        else {
+            while (lk < 3 && (ns >> (lk + 1)) >= 8) ++lk;
+            while (lk < 5 && (pixels << lk) / 32 < want && (ns >> (lk + 1)) >= 2) ++lk;
+        }
         pp.ksplit_log2 = lk;
     }
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
