@@ -294,6 +294,28 @@ def gen_path(ref):
     print("path_complex", stats, "rays/sample", stats[0] / (W * H * spp))
 
 
+def gen_path_native(ref):
+    """The UNMODIFIED reference with its OWN random numbers: TraditionalRenderer.render of the chandelier scene with
+    numpy's global MT19937 (seeded, not patched).  The CUDA path cannot reproduce that stream; this golden pins the
+    statistical agreement of the mean image (tests/test_gpu_parity.py::test_mean_image_agrees_with_the_reference_rng)."""
+    V = ref.ns.Vector
+    spec = scenes.build_chandelier(ref.ns)
+    W, H, spp, depth = 40, 24, 48, 8
+    r = ref.chandelier.TraditionalRenderer()
+    r.scene = spec.spheres
+    r.light_sources = [s for s in spec.spheres if s.material.emitive]
+    r.small_lights = [s for s in r.light_sources if s.radius < 0.5]
+    r.camera_position = V(*spec.camera)
+    np.random.seed(20240229)
+    with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()), \
+            mock.patch.object(ref.chandelier, "tqdm", lambda it, **k: it):
+        img = r.render(W, H, spp, depth)
+    stats = np.array([r.stats[k] for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits")], np.int64)
+    np.savez_compressed(OUT / "path_chandelier_native_rng_40x24.npz", image=np.asarray(img, np.float32), stats=stats, W=W, H=H,
+                        spp=spp, max_bounces=depth, mirror_threshold=0.0, cam=np.array(spec.camera), **flat_dict(flat(spec)))
+    print("path_chandelier_native_rng", stats, "rays/sample", stats[0] / (W * H * spp))
+
+
 # ----------------------------------------------------------------- env rollouts
 REASON = {None: 0, "ray_missed": 1, "ray_escaped": 2, "max_bounces": 3, "hit_sun": 4, "already_on_sun": 5}
 
@@ -541,10 +563,10 @@ def gen_traj(ref):
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     ref = load_reference()
-    which = sys.argv[1:] or ["kat", "whitted", "path", "env", "simple", "traj", "fb"]
+    which = sys.argv[1:] or ["kat", "whitted", "path", "path_native", "env", "simple", "traj", "fb"]
     for w in which:
-        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "env": gen_env, "simple": gen_simple,
-         "traj": gen_traj, "fb": gen_fb}[w](ref)
+        {"kat": gen_kat, "whitted": gen_whitted, "path": gen_path, "path_native": gen_path_native, "env": gen_env,
+         "simple": gen_simple, "traj": gen_traj, "fb": gen_fb}[w](ref)
 
 
 if __name__ == "__main__":

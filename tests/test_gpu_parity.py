@@ -355,6 +355,31 @@ def test_c3_full_size_properties(nat):
     sc.close()
 
 
+@pytest.mark.parametrize("precision", ["F32", "F64"])
+def test_mean_image_agrees_with_the_reference_rng(nat, precision):
+    """The stochastic path against the UNMODIFIED reference drawing from numpy's own MT19937 (a stream the device cannot
+    reproduce; golden made by oracle/gen_golden.py path_native): the mean images agree like two seeds of our own
+    estimator agree with each other, i.e. within the 1/sqrt(spp) noise, and so do the ray statistics."""
+    z, fs = load_golden("path_chandelier_native_rng_40x24")
+    W, H, spp = int(z["W"]), int(z["H"]), int(z["spp"])
+    ref = z["image"].astype(np.float64) * 255.0
+    sc = nat.DeviceScene(fs)
+    imgs, rays = [], []
+    for seed in (1, 2, 3):
+        p = sc.path_params(z["cam"], W, H, spp, int(z["max_bounces"]), float(z["mirror_threshold"]), seed=seed)
+        image, _, st = sc.render_path_host(p, getattr(nat, precision))
+        imgs.append(image.astype(np.float64) * 255.0)
+        rays.append(int(st[0]))
+    rm = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))      # noqa: E731
+    own = np.mean([rm(imgs[0], imgs[1]), rm(imgs[0], imgs[2]), rm(imgs[1], imgs[2])])
+    for im in imgs:
+        assert rm(ref, im) < 1.25 * own, (rm(ref, im), own)
+        assert np.abs((ref - im).mean(axis=(0, 1))).max() < 0.25          # colour levels, averaged over the frame
+    assert own < 4.0                                                      # levels at 48 spp
+    assert abs(np.mean(rays) - int(z["stats"][0])) < 0.01 * int(z["stats"][0])
+    sc.close()
+
+
 def test_sharded_renderer_async_host_frames(nat):
     """ShardedPathRenderer (one rank): to_host="async" hands back PendingFrames whose copies overlap the next render;
     the frames equal the synchronous ones, through the NCCL-path code and through the fused sinks."""

@@ -182,3 +182,23 @@ def test_fb_guided_path_frame(orc):
     plain, st0 = orc.render_path_fb(fs, *args, None, 0.0, int(z["seed"]))
     trad, st1 = orc.render_path(fs, *args, seed=int(z["seed"]))
     assert np.array_equal(plain, trad) and st0["total_rays"] == st1["total_rays"] and st0["fb_used"] == 0
+
+
+def test_oracle_mean_image_agrees_with_the_reference_rng(orc):
+    """Statistical pin of the stochastic path: the unmodified reference, drawing from numpy's own MT19937 (golden made by
+    oracle/gen_golden.py path_native), and the oracle on the Philox stream give the same mean image within the noise
+    two seeds of the oracle show against each other."""
+    z, fs = load_golden("path_chandelier_native_rng_40x24")
+    W, H, spp = int(z["W"]), int(z["H"]), int(z["spp"])
+    ref = z["image"].astype(np.float64) * 255.0
+    imgs, rays = [], []
+    for seed in (1, 2):
+        sums, st = orc.render_path(fs, z["cam"], W, H, spp, int(z["max_bounces"]), float(z["mirror_threshold"]), seed=seed)[:2]
+        imgs.append(np.minimum(255.0, np.floor(np.asarray(sums)[..., :3] / spp)))
+        rays.append(st["total_rays"])
+    rm = lambda a, b: float(np.sqrt(np.mean((a - b) ** 2)))      # noqa: E731
+    own = rm(imgs[0], imgs[1])
+    for im in imgs:
+        assert rm(ref, im) < 1.25 * own, (rm(ref, im), own)
+        assert np.abs((ref - im).mean(axis=(0, 1))).max() < 0.25
+    assert abs(np.mean(rays) - int(z["stats"][0])) < 0.01 * int(z["stats"][0])
