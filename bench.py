@@ -179,6 +179,7 @@ def main():
 
     import torch
     import torch.distributed as dist
+    import ray_tracer_v1_b200 as rtb
     from ray_tracer_v1_b200 import _native as nat
     from ray_tracer_v1_b200.distributed import ShardedPathRenderer, row_bands, sample_ranges
 
@@ -287,7 +288,9 @@ def main():
     t0 = time.perf_counter()
     pending, checksum = None, 0.0
     for i in range(args.steps):
-        spec_i, fs_i = (spec, fs)
+        # the reference-facing objects (54 Sphere / Material / Colour instances) are re-flattened EVERY frame, as the
+        # drop-in classes do (scenes are mutable lists: SURVEY 8b) -- host work that overlaps the previous frame's render
+        fs_i = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
         r.set_scene(fs_i)                                     # H2D: the flattened scene, re-uploaded every frame
         img, st = step(i, to_host="async")                     # D2H: the float32 image into pinned host memory, on the
         e2e_q += st[4:5]                                       # copy stream while the next frame renders ...
