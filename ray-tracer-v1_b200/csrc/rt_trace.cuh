@@ -97,6 +97,28 @@ RT_DEV void brute_select(const float4 *sph, int n_padded, V3<float> O, V3<float>
     }
 }
 
+// The same loop for queries that exclude spheres by id (ray.py:165: secondary and shadow rays suppress the sphere they
+// start on): the id test becomes one compare + one select on the key instead of a divergent early-out per sphere.
+template <bool kAbs>
+RT_DEV void brute_select_sup(const float4 *sph, const int *ids, int n, int suppress, V3<float> O, V3<float> D, float &best,
+                             int &bi, unsigned &tests) {
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) {
+        const float4 s = sph[i];
+        const bool skip = ids[i] == suppress;
+        const float lx = s.x - O.x, ly = s.y - O.y, lz = s.z - O.z;
+        const float tca = fmaf(lz, D.z, fmaf(ly, D.y, lx * D.x));
+        const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+        const float disc = fmaf(tca, tca, fmaf(s.w, s.w, -ll));
+        const float dm = __int_as_float(__float_as_int(disc) | (__float_as_int(tca) & (int)0x80000000));
+        const float t = tca - M<float>::sqrt(dm);
+        float key = kAbs ? fabsf(t) : t;
+        key = skip ? __int_as_float(0x7fc00000) : key;          // NaN compares false
+        tests += skip ? 0u : 1u;
+        if (key < best) { best = key; bi = i; }
+    }
+}
+
 // ---- packed FP32 (sm_100 f32x2) helpers: one issue slot for two FP32 lanes of work.  A pair lives in a 64-bit register.
 typedef unsigned long long f32x2;
 RT_DEV f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
@@ -287,6 +309,16 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
                 }
             }
             tests += n;
+        } else if constexpr (!M<T>::exact) {
+            // FP32, spheres excluded by id: branch-free selection, then the winner's robust distance as above
+            brute_select_sup<kAbs>(g.sv.sph, g.sv.ids, n, suppress, O, D, best, bi, tests);
+            if (bi >= 0) {
+                const typename M<T>::v4 w = g.sv.sph[bi];
+                const V3<T> L = centre_of<T>(w) - O;
+                const T tca = dot(L, D);
+                const V3<T> f = L - D * tca;
+                bt = tca - M<T>::sqrt(fmaxf(fmaf(w.w, w.w, -dot(f, f)), 0.f));
+            }
         } else {
 #pragma unroll 2
             for (int i = 0; i < n; ++i) consider<T, kAbs>(g, i, O, D, suppress, best, bt, bi, tests);
