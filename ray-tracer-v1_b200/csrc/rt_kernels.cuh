@@ -144,6 +144,26 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
     const int y = wp.y0 + yr;
     Counters ct = {0u, 0u, 0u};
     unsigned primaries = 0;
+    // camera rays of this warp's 8x4 pixel tile: the spheres their cone can touch (cone_candidates, rt_trace.cuh), built
+    // once for all samples.  Tiles of sky get an empty list and skip the sphere loop altogether; frames are unchanged.
+    unsigned long long cand = ~0ull;
+    if constexpr (!M<T>::exact && kMode == 0) {
+        if (sc.n <= 64 && wp.W > 0 && wp.y1 > wp.y0) {
+            const float gx = (float)wp.X[min(x, wp.W - 1)], gy = (float)wp.Y[min(y, wp.y1 - 1)];
+            float xlo = gx, xhi = gx, ylo = gy, yhi = gy;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+                ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+            }
+            const float jx = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_x) : 0.f, jy = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_y) : 0.f;
+            const float ex = 0.5f * (xhi - xlo) + jx, ey = 0.5f * (yhi - ylo) + jy;
+            const V3<float> d0 = normalise(mk<float>(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.f));
+            const float alpha = sqrtf(ex * ex + ey * ey) * 1.001f + 1e-6f;       // angle <= distance on the z = -1 plane
+            cand = cone_candidates(reinterpret_cast<const float4 *>(S.g.sv.sph), S.g.sv.n,
+                                   mk<float>((float)wp.cam[0], (float)wp.cam[1], (float)wp.cam[2]), d0, alpha, threadIdx.x & 31);
+        }
+    }
     if (x < wp.W && y < wp.y1) {
         const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
         const T X0 = wp.X[x], Y0 = wp.Y[y];
@@ -160,7 +180,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
             V3<T> d = mk<T>(Xj, Yj, T(-1));
             if constexpr (M<T>::exact) { if (wp.prenorm) d = normalise(d); }
             d = normalise(d);                                            // Ray.__init__, ray.py:69-71
-            Hit<T> h = trace_terminal<T, kBvh>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct);
+            Hit<T> h = trace_terminal<T, kBvh>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct, cand);
             primaries++;
             T c[3];
             if (h.idx >= 0) { terminal_rgb<T, kBvh>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); last = h.idx; }

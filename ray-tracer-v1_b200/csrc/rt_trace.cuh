@@ -101,21 +101,45 @@ RT_DEV void brute_select(const float4 *sph, int n_padded, V3<float> O, V3<float>
 // start on): the id test becomes one compare + one select on the key instead of a divergent early-out per sphere.
 template <bool kAbs>
 RT_DEV void brute_select_sup(const float4 *sph, const int *ids, int n, int suppress, V3<float> O, V3<float> D, float &best,
-                             int &bi, unsigned &tests) {
+                             float &bt, int &bi, unsigned &tests) {
 #pragma unroll 4
     for (int i = 0; i < n; ++i) {
         const float4 s = sph[i];
         const bool skip = ids[i] == suppress;
-        const float lx = s.x - O.x, ly = s.y - O.y, lz = s.z - O.z;
-        const float tca = fmaf(lz, D.z, fmaf(ly, D.y, lx * D.x));
-        const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
-        const float disc = fmaf(tca, tca, fmaf(s.w, s.w, -ll));
+        // the discriminant of sphere_test (cancellation-free form), so hit / miss decisions are the same as there
+        const V3<float> L = centre_of<float>(s) - O;
+        const float tca = dot(L, D);
+        const V3<float> f = L - D * tca;
+        const float disc = fmaf(s.w, s.w, -dot(f, f));
         const float dm = __int_as_float(__float_as_int(disc) | (__float_as_int(tca) & (int)0x80000000));
-        const float t = tca - M<float>::sqrt(dm);
+        const float t = tca - M<float>::sqrt(dm);                // NaN unless tca >= 0 and disc >= 0
         float key = kAbs ? fabsf(t) : t;
         key = skip ? __int_as_float(0x7fc00000) : key;          // NaN compares false
         tests += skip ? 0u : 1u;
-        if (key < best) { best = key; bi = i; }
+        if (key < best) { best = key; bt = t; bi = i; }
+    }
+}
+
+// brute_select over the spheres of a warp-uniform candidate mask (camera rays of a warp tile, cone_candidates below):
+// the same operations per sphere in the same ascending order, so the same winner.
+template <bool kAbs>
+RT_DEV void brute_select_mask(const float4 *sph, unsigned long long mask, V3<float> O, V3<float> D, float &best, int &bi) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        unsigned m = h ? (unsigned)(mask >> 32) : (unsigned)mask;
+        while (m) {
+            const int i = __ffs((int)m) - 1 + 32 * h;
+            m &= m - 1u;
+            const float4 s = sph[i];
+            const float lx = s.x - O.x, ly = s.y - O.y, lz = s.z - O.z;
+            const float tca = fmaf(lz, D.z, fmaf(ly, D.y, lx * D.x));
+            const float ll = fmaf(lz, lz, fmaf(ly, ly, lx * lx));
+            const float disc = fmaf(tca, tca, fmaf(s.w, s.w, -ll));
+            const float dm = __int_as_float(__float_as_int(disc) | (__float_as_int(tca) & (int)0x80000000));
+            const float t = tca - M<float>::sqrt(dm);
+            const float key = kAbs ? fabsf(t) : t;
+            if (key < best) { best = key; bi = i; }
+        }
     }
 }
 
@@ -277,7 +301,7 @@ RT_DEV float winner_distance(float4 w, V3<float> O, V3<float> D) {
 
 template <typename T, bool kAbs, bool kBvh, typename PK = PkNone>
 RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, unsigned &tests, unsigned &box_tests,
-                   const PK &pkc = PK()) {
+                   const PK &pkc = PK(), unsigned long long cand = ~0ull) {
     T best = M<T>::inf(), bt = T(0);
     int bi = -1;
     bool brute = true;
@@ -288,6 +312,7 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
             if constexpr (!M<T>::exact) {
                 if constexpr (kAbs && std::is_same<PK, PkConst>::value) bi = brute_select_pkc(pkc, g.sv.n_padded, g.sv.key_mask6, O, D);
                 else if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
+                else if (cand != ~0ull) brute_select_mask<kAbs>(g.sv.sph, cand, O, D, best, bi);     // warp-uniform
                 else brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);
                 if (bi >= 0) {
                     // winner's distance from the cancellation-free form |L - tca D|^2; a silhouette-grazing winner
@@ -308,17 +333,10 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
                     }
                 }
             }
-            tests += n;
+            tests += cand != ~0ull ? (unsigned)__popcll(cand) : (unsigned)n;
         } else if constexpr (!M<T>::exact) {
-            // FP32, spheres excluded by id: branch-free selection, then the winner's robust distance as above
-            brute_select_sup<kAbs>(g.sv.sph, g.sv.ids, n, suppress, O, D, best, bi, tests);
-            if (bi >= 0) {
-                const typename M<T>::v4 w = g.sv.sph[bi];
-                const V3<T> L = centre_of<T>(w) - O;
-                const T tca = dot(L, D);
-                const V3<T> f = L - D * tca;
-                bt = tca - M<T>::sqrt(fmaxf(fmaf(w.w, w.w, -dot(f, f)), 0.f));
-            }
+            // FP32, spheres excluded by id: branch-free selection on sphere_test's own discriminant
+            brute_select_sup<kAbs>(g.sv.sph, g.sv.ids, n, suppress, O, D, best, bt, bi, tests);
         } else {
 #pragma unroll 2
             for (int i = 0; i < n; ++i) consider<T, kAbs>(g, i, O, D, suppress, best, bt, bi, tests);
@@ -412,14 +430,15 @@ struct Counters { unsigned queries, tests, boxes; };
 // most recent mirror hit, else None.  D is a unit vector.
 template <typename T, bool kBvh>
 RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, int bounces, int max_bounces, int through,
-                             Counters &ct) {
+                             Counters &ct, unsigned long long cand = ~0ull) {     // cand: spheres the FIRST query may hit
     Hit<T> fallback;
     fallback.idx = -1; fallback.t = T(0); fallback.bounces = 0; fallback.through = 0;
     fallback.p = mk<T>(0, 0, 0); fallback.n = mk<T>(0, 0, 0);
     for (;;) {
         ct.queries++;
         T t;
-        int i = nearest<T, false, kBvh>(g, O, D, suppress, t, ct.tests, ct.boxes);
+        int i = nearest<T, false, kBvh>(g, O, D, suppress, t, ct.tests, ct.boxes, PkNone(), cand);
+        cand = ~0ull;
         if (i < 0) return fallback;                           // ray.py:170-171
         if (bounces > max_bounces) return fallback;           // ray.py:173-174
         Hit<T> h;
