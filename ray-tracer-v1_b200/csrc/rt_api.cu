@@ -572,7 +572,10 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         int lk = 0;
         if (p->ksplit > 0) { while ((1 << (lk + 1)) <= p->ksplit && lk < 5) ++lk; }
         else {
-            while (lk < 3 && (ns >> (lk + 1)) >= 8) ++lk;
+            // with a hierarchy the lanes of a pixel traverse together: coherence wins, 8 lanes per pixel whenever a
+            // lane keeps >= 2 samples (1e3-1e5-sphere scenes: 11.3 / 48.5 / 222 ms per 16 spp against 12.5 / 51.9 / 227)
+            const int per_lane = view.bvh.nodes > 0 ? 2 : 8;
+            while (lk < 3 && (ns >> (lk + 1)) >= per_lane) ++lk;
             while (lk < 5 && (pixels << lk) / 32 < want && (ns >> (lk + 1)) >= 2) ++lk;
         }
         pp.ksplit_log2 = lk;
