@@ -31,7 +31,7 @@ os.dup2(2, 1)
 import numpy as np  # noqa: E402
 
 W, H, SPP, DEPTH, THRESHOLD, FOV = 1920, 1080, 64, 5, 0.9, 60.0
-NCU_DRAM_BYTES_PER_LAUNCH = 69888 + 759296    # profiles/ncu_path_kernel_r1l.txt (one ncu --set full capture of a 64-spp launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 417024 + 647936    # profiles/ncu_path_kernel_r1n.txt (one ncu --set full capture of a 64-spp launch)
 CPU_W, CPU_H, CPU_SPP = 960, 540, 16          # bounded CPU sample: 1/16 of the frame's pixel-samples
 METRIC, UNIT = "Mrays/s (complex scene, 1920x1080, 64 spp)", "Mrays/s"
 WORKLOAD = "complex scene (54 spheres, 3 lights) 1920x1080 64 spp depth 5, Algorithm B (TraditionalRenderer)"
@@ -345,7 +345,7 @@ def main():
                          "sphere_tests_per_query_executed": tests_per_query, "flop_per_query_executed": fpq_exec,
                          "achieved_executed": achieved_exec, "frac_executed": achieved_exec / fp32_peak,
                          "kernel_ms": kernel_ms / args.steps,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ncu_path_kernel_r1l.txt:
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/ncu_path_kernel_r1n.txt:
                          # the 33 MB framebuffer write mostly stays in the 126 MB L2 past the end of the kernel
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                          "hbm_algorithmic_bytes_per_launch": W * H * 16 // world},
