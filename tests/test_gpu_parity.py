@@ -106,6 +106,10 @@ def test_whitted_frames_fp32_within_1_of_255(nat, name):
     # every pixel whose terminal object agrees must be within one 8-bit level, bar shadow-edge flips
     assert bad.mean() < 2e-3, f"{bad.sum()} of {bad.size} pixels off by more than 1/255 ({flipped.sum()} hit flips)"
     assert flipped.mean() < 2e-3
+    if name == "whitted_c1_balls_320x240":
+        # BASELINE config 1, the reference's own render_custom_scene frame: the north star's "within 1/255 per channel
+        # after 8-bit quantisation" holds on every one of the 76,800 pixels (measured: 0; one pixel of slack)
+        assert bad.sum() <= 1 and flipped.sum() <= 1, (int(bad.sum()), int(flipped.sum()))
     sc.close()
 
 
