@@ -137,7 +137,9 @@ class TraditionalRenderer:
         view, st = self._ctx.render_path(_xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
                                          self.mirror_threshold, seed=seed, fov=self.fov,
                                          precision=_precision(self.precision))
-        image = view.copy()                             # a fresh array per render, like the reference
+        # a fresh array per render, like the reference; reuse_output = True hands out the renderer's pinned buffer
+        # itself (valid until the next render) and saves the 24.9 MB copy of a 1080p frame (~3 ms)
+        image = view if getattr(self, "reuse_output", False) else view.copy()
         for i, k in enumerate(('total_rays', 'total_intersections', 'light_hits', 'small_light_hits')):
             self.stats[k] = int(st[i])
         render_time = time.time() - start
