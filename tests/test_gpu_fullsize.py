@@ -1,0 +1,157 @@
+"""GPU parity at the FULL sizes of BASELINE.json's configurations: the FP64 parity build against the CPU oracle bit for
+bit, then the FP32 product build against the FP64 build at gates three times the figures measured on the B200
+(profiles/parity_r1.txt, profiles/parity_r2.txt).
+
+    C2  marbles4 and planets2, 1280x720, depth 4, spp 1 and 16     /root/reference/RL/output5.py:1437-1512
+    C3  complex scene 1920x1080, depth 5, spp 1 and 4              /root/reference/FB/fb_vs_traditional_complex.py:391-416
+    C4  chandelier 1920x1080, depth 8, spp 1 and 2, brute force and LBVH
+    C5  65,536 envs x (max_bounces + 1) steps, RL and FB flavours   /root/reference/RL/ray_tracer_env.py:295-401
+
+Gates (FP32 vs FP64, same Philox stream):
+    Algorithm A   at most 1e-4 of the pixels beyond 1/255 after 8-bit quantisation, hit-index flips at most 1e-4
+    Algorithm B   at most 0.6 % of the pixels beyond one colour level, RMSE <= 1.5 / sqrt(spp) levels, ray counts 1e-5
+    env           at least 99 % of the episodes follow the FP64 trajectory to the end; on those obs / reward 2e-3
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GATE_A_PIXELS = 1e-4
+GATE_B_PIXELS = 6e-3
+GATE_B_RMSE = 1.5
+
+
+@pytest.fixture(scope="module")
+def nat(rt):
+    from ray_tracer_v1_b200 import _native
+    return _native
+
+
+def quant8(rgb):
+    return np.clip(np.rint(rgb), 0, 255)
+
+
+def _flat(spec):
+    from ray_tracer_v1_b200 import flatten_scene
+    return flatten_scene(spec.spheres, spec.global_lights, spec.point_lights, spec.background)
+
+
+def _c2_grid(spec, W=1280, H=720):
+    k = 640 * spec.ray_step
+    return np.linspace(-k * 16 / 9, k * 16 / 9, W), np.linspace(k, -k, H)
+
+
+# ------------------------------------------------------------------ C2
+@pytest.mark.parametrize("scene", ["marbles4", "planets2"])
+@pytest.mark.parametrize("spp", [1, 16])
+def test_c2_full_size_equals_oracle(nat, orc, scene, spp):
+    from ray_tracer_v1_b200 import scenes
+    spec = getattr(scenes, "build_" + scene)()
+    fs = _flat(spec)
+    X, Y = _c2_grid(spec)
+    miss = [spec.miss.r, spec.miss.g, spec.miss.b]
+    sum_o, hit_o, q_o = orc.render_whitted(fs, spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=3)
+    sc = nat.DeviceScene(fs)
+    p = sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=3)
+    _, s64, hit64, st64 = sc.render_whitted_host(p, nat.F64)
+    assert np.array_equal(s64[..., :3], sum_o), "FP64 whitted kernel differs from the oracle at 1280x720"
+    assert np.array_equal(hit64, hit_o) and int(st64[4]) == q_o
+    _, s32, hit32, _ = sc.render_whitted_host(p, nat.F32)
+    bad = np.abs(quant8(s32[..., :3] / spp) - quant8(s64[..., :3] / spp)).max(axis=2) > 1
+    assert bad.mean() <= GATE_A_PIXELS, (int(bad.sum()), bad.size)
+    if spp == 1:
+        assert (hit32 != hit64).mean() <= GATE_A_PIXELS, int((hit32 != hit64).sum())
+    sc.close()
+
+
+# ------------------------------------------------------------------ C3 / C4
+def _path_case(nat, orc, spec, depth, thr, spp, seed, lbvh=False):
+    from ray_tracer_v1_b200 import flatten_scene
+    fs = flatten_scene(spec.spheres, background_colour=spec.background)
+    W, H = 1920, 1080
+    sums_o, st_o = orc.render_path(fs, spec.camera, W, H, spp, depth, thr, seed=seed)
+    sc = nat.DeviceScene(fs)
+    if lbvh:
+        sc.build_lbvh(50.0)
+    p = sc.path_params(spec.camera, W, H, spp, depth, thr, seed=seed)
+    _, s64, st64 = sc.render_path_host(p, nat.F64)
+    assert np.array_equal(s64[..., :3], sums_o), "FP64 path kernel differs from the oracle at 1920x1080"
+    assert [int(x) for x in st64[:5]] == [st_o[k] for k in ("total_rays", "total_intersections", "light_hits",
+                                                            "small_light_hits", "queries")]
+    _, s32, st32 = sc.render_path_host(p, nat.F32)
+    d = np.abs(s32[..., :3] - s64[..., :3]) / spp
+    beyond = (d.max(axis=2) > 1.0).mean()
+    rmse = float(np.sqrt(np.mean(d ** 2)))
+    assert beyond <= GATE_B_PIXELS, beyond
+    assert rmse <= GATE_B_RMSE / np.sqrt(spp), rmse
+    assert abs(int(st32[0]) - int(st64[0])) <= 1e-5 * int(st64[0])
+    assert np.all(s32[..., 3] == spp)
+    sc.close()
+
+
+@pytest.mark.parametrize("spp", [1, 4])
+def test_c3_full_size_equals_oracle(nat, orc, spp):
+    from ray_tracer_v1_b200 import scenes
+    _path_case(nat, orc, scenes.build_complex(), 5, 0.9, spp, seed=7)
+
+
+@pytest.mark.parametrize("spp,lbvh", [(1, False), (2, False), (2, True)])
+def test_c4_full_size_equals_oracle(nat, orc, spp, lbvh):
+    from ray_tracer_v1_b200 import scenes
+    _path_case(nat, orc, scenes.build_chandelier(), 8, 0.0, spp, seed=11, lbvh=lbvh)
+
+
+# ------------------------------------------------------------------ C5
+def _c5_case(flavour):
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    if flavour == "fb":
+        spec = scenes.build_balls_in_space(as_rendered=False)
+        fs = flatten_scene(spec.spheres, spec.global_lights, [], spec.background)
+        kw = dict(image_width=320, image_height=240, camera_position=(0, 0, 1), fov=60, max_bounces=5, flavour="fb")
+        lo, hi = (-1.0, -1.0), (1.0, 1.0)
+    else:
+        spec = scenes.build_optimized_env_scene()
+        fs = _flat(spec)
+        kw = dict(image_width=320, image_height=240, camera_position=(0, 0, 0), fov=80, max_bounces=6, flavour="rl")
+        lo, hi = (0.0, 0.0), (np.pi / 2, 2 * np.pi)
+    return fs, kw, lo, hi
+
+
+@pytest.mark.parametrize("flavour", ["rl", "fb"])
+def test_c5_full_size_equals_oracle(rt, orc, flavour):
+    """65,536 episodes stepped until every one has ended (max_bounces + 1 steps, stepping on past termination like the
+    reference rollouts): FP64 flags / reasons exact and rewards 1e-9 against OracleEnv; FP32 close on the episodes whose
+    hit / miss pattern agrees."""
+    from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
+    fs, kw, lo, hi = _c5_case(flavour)
+    B = 65536
+    rs = np.random.RandomState(5)
+    pixels = np.stack([rs.randint(0, kw["image_width"], B), rs.randint(0, kw["image_height"], B)], 1).astype(np.int32)
+    steps = kw["max_bounces"] + 1
+    actions = rs.uniform(lo, hi, (steps, B, 2)).astype(np.float32)
+    ref = orc.OracleEnv(fs, B, kw["image_width"], kw["image_height"], camera=kw["camera_position"], fov=kw["fov"],
+                        max_bounces=kw["max_bounces"], flavour=flavour)
+    e64 = BatchedRayTracerEnv(fs, B, precision="f64", **kw)
+    e32 = BatchedRayTracerEnv(fs, B, precision="f32", **kw)
+    o_ref = ref.reset(pixels)
+    o64, _ = e64.reset(options={"pixels": pixels})
+    o32, _ = e32.reset(options={"pixels": pixels})
+    np.testing.assert_allclose(o64.cpu().numpy(), o_ref, rtol=1e-6, atol=1e-7)
+    follows = np.ones(B, bool)
+    done = np.zeros(B, bool)
+    for t in range(steps):
+        obs_r, rew_r, term_r, trunc_r, reason_r = ref.step(actions[t])
+        obs, rew, term, trunc, info = e64.step(actions[t])
+        np.testing.assert_allclose(obs.cpu().numpy(), obs_r, rtol=1e-6, atol=1e-7, err_msg=f"obs step {t}")
+        np.testing.assert_allclose(rew.cpu().numpy(), rew_r, rtol=1e-9, atol=1e-12, err_msg=f"reward step {t}")
+        assert np.array_equal(term.cpu().numpy(), term_r) and np.array_equal(trunc.cpu().numpy(), trunc_r)
+        assert np.array_equal(info["reason"].cpu().numpy(), reason_r)
+        done |= term_r
+        obs3, rew3, _, _, info3 = e32.step(actions[t])
+        follows &= info3["reason"].cpu().numpy() == reason_r
+        np.testing.assert_allclose(obs3.cpu().numpy()[follows], obs_r[follows], rtol=2e-3, atol=2e-3)
+        np.testing.assert_allclose(rew3.cpu().numpy()[follows], rew_r[follows], rtol=2e-3, atol=6e-3)
+    assert done.all()
+    assert follows.mean() >= 0.99, follows.mean()
+    e64.close(); e32.close()
