@@ -112,7 +112,9 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector
     // in double from the T-rounded centre and radius (NaN for padding spheres: never hit)
     for (int i = 0; i < n_pad; ++i) {
         const double cx = (double)sph[i].x, cy = (double)sph[i].y, cz = (double)sph[i].z, r = (double)sph[i].w;
-        const T w = (T)(r * r - (cx * cx + cy * cy + cz * cz));
+        // padding spheres: w = -inf, so disc = -inf on every ray (never hit, and its sign bit lets the warp vote of
+        // brute_select_pkc skip the pair; a NaN would read as "maybe")
+        const T w = i < n ? (T)(r * r - (cx * cx + cy * cy + cz * cz)) : -std::numeric_limits<T>::infinity();
         v4 &a = pk[i & ~1], &b = pk[(i & ~1) + 1];
         if (i & 1) { a.y = sph[i].x; a.w = sph[i].y; b.y = sph[i].z; b.w = w; }
         else { a.x = sph[i].x; a.z = sph[i].y; b.x = sph[i].z; b.z = w; }

@@ -347,24 +347,25 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             const bool primary_trip = first_trip;     // this trip traces the camera rays of a sample (lock-step only)
             first_trip = false;
             bool ended = false;
+            int i = -1;
+            if constexpr (kMode == 3) {
+                // the selection runs on the CONVERGED warp (its pair votes take the full mask): a lane without a path in
+                // flight goes through the arithmetic on its stale ray and votes "no"; its result is never read
+                if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) i = select_candidates(S.g.sv.cw, cand, S.g.sv.key_mask6, O, D);
+                else i = brute_select_pkc<!kRegen>(pkc, S.g.sv.n_padded, S.g.sv.key_mask6, O, D, alive);   // regen: lanes leave the loop one by one
+            }
             if (alive) {
                 // ---- one call of trace_ray_traditional below the depth limit: a nearest-hit query
                 T t;
                 n_query++;
-                int i;
                 typename M<T>::v4 m;                   // material: (reflective, transparent, emissive, ior)
                 T inv_r = T(0);
                 V3<T> centre = mk<T>(T(0), T(0), T(0));
                 if constexpr (kMode == 3) {
                     // one LDS.128 for the winner's (centre, r) -- shared by the robust distance and the normal -- and one
                     // for its (1/r, reflective, emissive) record
-                    if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) {
-                        i = select_candidates(S.g.sv.cw, cand, S.g.sv.key_mask6, O, D);
-                        n_tests += (unsigned)__popcll(cand);
-                    } else {
-                        i = brute_select_pkc(pkc, S.g.sv.n_padded, S.g.sv.key_mask6, O, D);
-                        n_tests += (unsigned)S.g.sv.n;
-                    }
+                    if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) n_tests += (unsigned)__popcll(cand);
+                    else n_tests += (unsigned)S.g.sv.n;
                     if (i >= 0) {
                         const float4 w = S.g.sv.sph[i], hr = hitrec[i];
                         t = winner_distance(w, O, D);

@@ -199,38 +199,75 @@ RT_DEV int brute_select_pk(const float4 *pk, int n_padded, int key_mask, V3<floa
 // The same selection with the pair array in the kernel parameter block (PkConst, rt_common.cuh): the group loop is
 // fully unrolled so that every LDCU.128 has an immediate constant-bank address, and the sphere operands of FFMA2 /
 // FADD2 are uniform registers.  Groups at or beyond n_padded are skipped by a uniform branch.
-RT_DEV int brute_select_pkc(const PkConst &pkc, int n_padded, int key_mask6, V3<float> O, V3<float> D) {
+//
+// RT_VOTE_SKIP: the second half of a pair's test -- sign merge, MUFU.SQRT, t, key, running minimum: 10 of its 27 issue
+// cycles -- only matters if SOME lane can hit one of the two spheres, i.e. has tca >= 0 and disc >= 0 (the conditions
+// the sign merge folds into the square root).  For the small spheres of a scene that is rare even for 32 incoherent
+// bounce rays (complex scene: 2-24 % of the warp trips per pair, tools/sim/cull_sim.py), so one warp vote on the sign
+// bits of (tca | disc) skips it for the whole warp; a skipped pair would have produced two NaN keys, so the winner,
+// ties included, is unchanged and frames stay bit-identical.  The first RT_PKC_ALWAYS_PAIRS pairs (the wall spheres
+// of every reference scene, hit by some lane in ~100 % of the trips) are finished unconditionally.
+#ifndef RT_VOTE_SKIP
+#define RT_VOTE_SKIP 1
+#endif
+#ifndef RT_PKC_ALWAYS_PAIRS
+#define RT_PKC_ALWAYS_PAIRS 3
+#endif
+#ifndef RT_VOTE_PAIRS
+#define RT_VOTE_PAIRS 2
+#endif
+static_assert(RT_VOTE_PAIRS == 1 || RT_VOTE_PAIRS == 2 || RT_VOTE_PAIRS == 4, "pairs per vote");
+// kWarp: ALL 32 lanes of the warp call this together (`live` = this lane carries a ray; the others only vote "no"), so
+// the votes use the full mask and compile to ISETP (live folded into its predicate input) + VOTE.ANY + BRA.  Callers
+// that cannot guarantee a converged warp use kWarp = false: no votes, every pair is finished.
+template <bool kWarp>
+RT_DEV int brute_select_pkc(const PkConst &pkc, int n_padded, int key_mask6, V3<float> O, V3<float> D, bool live = true) {
     const float od = dot(O, D), oo = dot(O, O);
     const f32x2 Dx = pack2(D.x, D.x), Dy = pack2(D.y, D.y), Dz = pack2(D.z, D.z), nod = pack2(-od, -od);
     const f32x2 Bx = pack2(2.f * O.x, 2.f * O.x), By = pack2(2.f * O.y, 2.f * O.y), Bz = pack2(2.f * O.z, 2.f * O.z);
     const f32x2 noo = pack2(-oo, -oo), neg1 = pack2(-1.f, -1.f);
     // RT_PKC_MAX = 64 spheres: the key carries the SCENE index in its 6 low mantissa bits (the unrolled loop knows it
-    // at compile time), so the running minimum over all spheres is four VIMNMX3 per group and nothing else.
+    // at compile time), so the running minimum over all spheres is one VIMNMX3 per pair and nothing else.
     static_assert(RT_PKC_MAX == 64, "key layout: 6 index bits");
     int best = RT_KEY_INF;
 #pragma unroll
     for (int base = 0; base < RT_PKC_MAX; base += 8) {
         if (base >= n_padded) break;                  // ONE exit: the groups behind it are never fetched
-        int key[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const ulonglong2 a = pkc.q[base + 2 * j], b = pkc.q[base + 2 * j + 1];
-            const f32x2 tca = fma2(b.x, Dz, fma2(a.y, Dy, fma2(a.x, Dx, nod)));
-            const f32x2 nm = fma2(b.x, Bz, fma2(a.y, By, fma2(a.x, Bx, add2(b.y, noo))));
-            const f32x2 disc = fma2(tca, tca, nm);
-            float tc0, tc1, d0, d1;
-            unpack2(tca, tc0, tc1); unpack2(disc, d0, d1);
-            const float s0 = M<float>::sqrt(__int_as_float(__float_as_int(d0) | (__float_as_int(tc0) & (int)0x80000000)));
-            const float s1 = M<float>::sqrt(__int_as_float(__float_as_int(d1) | (__float_as_int(tc1) & (int)0x80000000)));
-            float t0, t1;
-            unpack2(fma2(pack2(s0, s1), neg1, tca), t0, t1);
-            key[2 * j] = (__float_as_int(t0) & key_mask6) | (base + 2 * j);
-            key[2 * j + 1] = (__float_as_int(t1) & key_mask6) | (base + 2 * j + 1);
+        for (int j0 = 0; j0 < 4; j0 += RT_VOTE_PAIRS) {
+            // RT_VOTE_PAIRS pairs share one vote (1, 2 or 4: fewer votes and branches against a lower skip rate)
+            f32x2 tca[RT_VOTE_PAIRS], disc[RT_VOTE_PAIRS];
+            int x = -1;
+#pragma unroll
+            for (int v = 0; v < RT_VOTE_PAIRS; ++v) {
+                const int j = j0 + v;
+                const ulonglong2 a = pkc.q[base + 2 * j], b = pkc.q[base + 2 * j + 1];
+                tca[v] = fma2(b.x, Dz, fma2(a.y, Dy, fma2(a.x, Dx, nod)));
+                const f32x2 nm = fma2(b.x, Bz, fma2(a.y, By, fma2(a.x, Bx, add2(b.y, noo))));
+                disc[v] = fma2(tca[v], tca[v], nm);
+                float tc0, tc1, d0, d1;
+                unpack2(tca[v], tc0, tc1); unpack2(disc[v], d0, d1);
+                // sign bit of x stays set <=> no sphere so far has tca >= 0 and disc >= 0 on this lane
+                x &= (__float_as_int(tc0) | __float_as_int(d0)) & (__float_as_int(tc1) | __float_as_int(d1));
+            }
+            const bool always = base / 2 + j0 < RT_PKC_ALWAYS_PAIRS;
+            bool some = true;
+            if (RT_VOTE_SKIP && kWarp && !always) some = __any_sync(0xffffffffu, x >= 0 && live);
+            if (__builtin_expect(some, always)) {
+#pragma unroll
+                for (int v = 0; v < RT_VOTE_PAIRS; ++v) {
+                    const int j = j0 + v;
+                    float tc0, tc1, d0, d1;
+                    unpack2(tca[v], tc0, tc1); unpack2(disc[v], d0, d1);
+                    const float s0 = M<float>::sqrt(__int_as_float(__float_as_int(d0) | (__float_as_int(tc0) & (int)0x80000000)));
+                    const float s1 = M<float>::sqrt(__int_as_float(__float_as_int(d1) | (__float_as_int(tc1) & (int)0x80000000)));
+                    float t0, t1;
+                    unpack2(fma2(pack2(s0, s1), neg1, tca[v]), t0, t1);
+                    best = __vimin3_s32(best, (__float_as_int(t0) & key_mask6) | (base + 2 * j),
+                                        (__float_as_int(t1) & key_mask6) | (base + 2 * j + 1));
+                }
+            }
         }
-        best = __vimin3_s32(best, key[0], key[1]);
-        best = __vimin3_s32(best, key[2], key[3]);
-        best = __vimin3_s32(best, key[4], key[5]);
-        best = __vimin3_s32(best, key[6], key[7]);
     }
     return best < RT_KEY_INF ? (best & 63) : -1;
 }
@@ -310,7 +347,7 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
         const int n = g.sv.n;
         if (suppress == RT_NO_ID_DEV) {
             if constexpr (!M<T>::exact) {
-                if constexpr (kAbs && std::is_same<PK, PkConst>::value) bi = brute_select_pkc(pkc, g.sv.n_padded, g.sv.key_mask6, O, D);
+                if constexpr (kAbs && std::is_same<PK, PkConst>::value) bi = brute_select_pkc<false>(pkc, g.sv.n_padded, g.sv.key_mask6, O, D);
                 else if constexpr (kAbs) bi = brute_select_pk(g.sv.pk, g.sv.n_padded, g.sv.key_mask, O, D);
                 else if (cand != ~0ull) brute_select_mask<kAbs>(g.sv.sph, cand, O, D, best, bi);     // warp-uniform
                 else brute_select<kAbs>(g.sv.sph, g.sv.n_padded, O, D, best, bi);

@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 GATE_A_PIXELS = 1e-4
 GATE_B_PIXELS = 6e-3
 GATE_B_RMSE = 1.5
+GATE_ENV_FOLLOW = {"rl": 1 - 1.7e-3, "fb": 1 - 5e-5}    # measured drop-outs: 5.5e-4 (36 episodes), 1.5e-5 (1 episode)
 
 
 @pytest.fixture(scope="module")
@@ -148,10 +149,15 @@ def test_c5_full_size_equals_oracle(rt, orc, flavour):
         assert np.array_equal(term.cpu().numpy(), term_r) and np.array_equal(trunc.cpu().numpy(), trunc_r)
         assert np.array_equal(info["reason"].cpu().numpy(), reason_r)
         done |= term_r
+        # FP32: an episode "follows" while its reasons agree AND its observation / reward stay within 2e-3 (a flipped
+        # hit / miss or shadow test sends it down another path or changes a light's contribution: it is dropped)
         obs3, rew3, _, _, info3 = e32.step(actions[t])
+        o3, r3 = obs3.cpu().numpy(), rew3.cpu().numpy()
         follows &= info3["reason"].cpu().numpy() == reason_r
-        np.testing.assert_allclose(obs3.cpu().numpy()[follows], obs_r[follows], rtol=2e-3, atol=2e-3)
-        np.testing.assert_allclose(rew3.cpu().numpy()[follows], rew_r[follows], rtol=2e-3, atol=6e-3)
+        follows &= (np.abs(o3 - obs_r) <= 2e-3 + 2e-3 * np.abs(obs_r)).all(axis=1)
+        follows &= np.abs(r3 - rew_r) <= 6e-3 + 2e-3 * np.abs(rew_r)
     assert done.all()
-    assert follows.mean() >= 0.99, follows.mean()
+    # measured on the B200: see profiles/parity_r2.txt (gate = 3x the measured drop-out rate)
+    assert follows.mean() >= GATE_ENV_FOLLOW[flavour], follows.mean()
+    print(f"C5 {flavour}: FP32 episodes following the FP64 trajectory to the end: {follows.mean():.6f}")
     e64.close(); e32.close()

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--lbvh", action="store_true")
     ap.add_argument("--ksplit", type=int, default=-1, help="-1 auto, 0 off, k = lanes per pixel")
     ap.add_argument("--schedules", default="0,1")
+    ap.add_argument("--save", default=None, help="write the last accumulation buffer to this .npy")
     args = ap.parse_args()
     spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
     fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
@@ -48,6 +49,8 @@ def main():
         img = accum.cpu().numpy()
         same = None if ref is None else bool(np.array_equal(ref, img))
         ref = img if ref is None else ref
+        if args.save:
+            np.save(args.save, img)
         print(f"{args.scene} {W}x{H} spp {args.spp} schedule {schedule} ksplit {args.ksplit}: {best:.3f} ms  {st[4] / best / 1e6:.2f} Gqueries/s "
               f"rays/sample {st[0] / (W * H * args.spp):.3f}  tests/query {st[5] / st[4]:.1f} boxes/query {st[6] / st[4]:.1f} same_image={same} "
               f"sha1 {hashlib.sha1(np.ascontiguousarray(img).tobytes()).hexdigest()[:12]}", flush=True)
