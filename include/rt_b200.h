@@ -140,7 +140,11 @@ typedef struct rt_whitted_params {
 /* accum_dev: [H,W,4] float (RT_F32) or double (RT_F64): sum r,g,b over the sample range + sample count.
  * hit_dev (optional) [H,W] int32 terminal scene index of the last sample (-1 miss).
  * stats_dev (optional) uint64[8]: [0] primary rays, [4] nearest-hit/occlusion queries, [5] sphere tests,
- * [6] AABB tests (LBVH only). */
+ * [6] AABB tests (LBVH only).
+ * X / Y are HOST arrays; the scene keeps their device copies resident (keyed by value), so only the first frame with
+ * a given grid uploads it (asynchronously, from a pinned copy) and later frames are a pure stream-ordered kernel
+ * launch: no copy, no synchronisation, graph-capturable, and safe from any number of streams.  A handle is not
+ * thread-safe: serialise host calls on one rt_scene. */
 int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted_params *p, void *accum_dev, int32_t *hit_dev,
                       uint64_t *stats_dev, void *stream);
 

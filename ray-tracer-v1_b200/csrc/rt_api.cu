@@ -47,8 +47,25 @@ struct rt_scene {
     SceneBufs<float> f;
     SceneBufs<double> d;
     uint8_t *small_dev = nullptr;
-    void *scratch = nullptr;      // X/Y grids of whitted frames
-    size_t scratch_bytes = 0;
+    // Direction grids of Algorithm-A frames, resident per scene: an entry is uploaded ONCE (from a pinned copy it owns,
+    // so the copy is asynchronous and nothing synchronises) and reused by every later frame with the same X[] / Y[]
+    // values and precision; launches on other streams wait for the upload event.  Entries are never overwritten while
+    // a kernel may read them: a changed grid gets a new entry, the oldest of RT_GRID_SLOTS is retired after a device sync.
+    struct Grid {
+        std::vector<double> key;      // X[0..W) then Y[0..H), as given
+        int precision = 0;
+        size_t nx = 0, ny = 0;
+        void *dev = nullptr, *pinned = nullptr;
+        cudaEvent_t ready = nullptr;
+        cudaStream_t upload_stream = nullptr;
+        bool settled = false;
+    };
+    std::vector<Grid> grids;
+    // pinned staging area of scene uploads (FP32 blob, FP64 blob, small-light mask): the copies are asynchronous and
+    // rt_scene_update never synchronises the stream; the next update waits for `staged` before it repacks the area
+    unsigned char *stage = nullptr;
+    size_t stage_bytes = 0;
+    cudaEvent_t staged = nullptr;
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
     mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS pairs of work counters of the persistent path kernel (zero at rest)
@@ -75,10 +92,10 @@ template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int 
 }
 
 // Pack the double SoA description into the vec4 arrays of one precision (layout: rt_common.cuh "scene views").
-template <typename T> static void pack_scene(const rt_scene_desc *s, std::vector<unsigned char> &host, size_t bytes) {
+template <typename T> static void pack_scene(const rt_scene_desc *s, unsigned char *host, size_t bytes) {
     using v4 = typename M<T>::v4;
-    host.assign(bytes, 0);
-    v4 *p = reinterpret_cast<v4 *>(host.data());
+    std::memset(host, 0, bytes);
+    v4 *p = reinterpret_cast<v4 *>(host);
     const int n = s->n, nG = s->nG, nP = s->nP, nL = s->nL;
     const int n_pad = (n + 7) & ~7;          // brute_select reads whole groups of 8: pad with never-hit spheres
     v4 *sph = p; p += n_pad;
@@ -218,19 +235,30 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
         const double c = s->colour[i];
         if (!(c >= 0.0 && c <= 65535.0 && c == std::floor(c))) sc->int_colours = false;
     }
-    std::vector<unsigned char> hf, hd;
+    // pack into the pinned staging area and copy from there: nothing below waits for the stream
+    const size_t n_small = (size_t)(s->n > 0 ? s->n : 1);
+    const size_t need = sc->f.bytes + sc->d.bytes + ((n_small + 255) & ~size_t(255));
+    if (!sc->staged) CU(cudaEventCreateWithFlags(&sc->staged, cudaEventDisableTiming));
+    else CU(cudaEventSynchronize(sc->staged));          // the previous upload has left the staging area (long ago)
+    if (need > sc->stage_bytes) {
+        if (sc->stage) CU(cudaFreeHost(sc->stage));
+        sc->stage = nullptr; sc->stage_bytes = 0;
+        CU(cudaMallocHost((void **)&sc->stage, need));
+        sc->stage_bytes = need;
+    }
+    unsigned char *hf = sc->stage, *hd = sc->stage + sc->f.bytes, *hs = hd + sc->d.bytes;
     pack_scene<float>(s, hf, sc->f.bytes);
     pack_scene<double>(s, hd, sc->d.bytes);
-    CU(cudaMemcpyAsync(sc->f.blob, hf.data(), sc->f.bytes, cudaMemcpyHostToDevice, st));
-    CU(cudaMemcpyAsync(sc->d.blob, hd.data(), sc->d.bytes, cudaMemcpyHostToDevice, st));
-    std::vector<uint8_t> small((size_t)(s->n > 0 ? s->n : 1), 0);
-    if (s->small) std::memcpy(small.data(), s->small, (size_t)s->n);
-    CU(cudaMemcpyAsync(sc->small_dev, small.data(), small.size(), cudaMemcpyHostToDevice, st));
+    std::memset(hs, 0, n_small);
+    if (s->small) std::memcpy(hs, s->small, (size_t)s->n);
+    CU(cudaMemcpyAsync(sc->f.blob, hf, sc->f.bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sc->d.blob, hd, sc->d.bytes, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(sc->small_dev, hs, n_small, cudaMemcpyHostToDevice, st));
     if (!sc->sched_dev) {                   // work counters of the persistent path kernel: zero at rest, re-armed by every launch
         CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
         CU(cudaMemsetAsync(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned), st));
     }
-    CU(cudaStreamSynchronize(st));          // the staging vectors die at return
+    CU(cudaEventRecord(sc->staged, st));
     {   // small scenes: the path kernel takes the FP32 pair array through its parameter block (kMode 3)
         const int n_pad = (s->n + 7) & ~7;
         static const bool off = std::getenv("RT_B200_NO_PKC") != nullptr;      // A/B switch for measurements
@@ -238,7 +266,7 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
         std::memset(&sc->pkc, 0, sizeof sc->pkc);
         if (sc->pkc_ok) {
             // blob layout (pack_scene): sph[n_pad] pk[n_pad] mat[n] col[n] g_vec g_col [nG] p_pos p_col [nP] l_pos l_col [nL] lpk
-            const float4 *v = reinterpret_cast<const float4 *>(hf.data());
+            const float4 *v = reinterpret_cast<const float4 *>(hf);
             std::memcpy(sc->pkc.q, v + n_pad, (size_t)n_pad * sizeof(float4));
             const size_t lpk_at = 2 * (size_t)n_pad + 2 * (size_t)s->n + 2 * (size_t)s->nG + 2 * (size_t)s->nP + 2 * (size_t)s->nL;
             std::memcpy(sc->pkc.l, v + lpk_at, 3 * (size_t)((s->nL + 1) / 2) * sizeof(float4));
@@ -250,13 +278,50 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
     return RT_OK;
 }
 
-static int ensure_scratch(rt_scene *sc, size_t bytes) {
-    if (bytes <= sc->scratch_bytes) return RT_OK;
-    if (sc->scratch) CU(cudaFree(sc->scratch));
-    sc->scratch = nullptr; sc->scratch_bytes = 0;
-    size_t want = (bytes + 4095) & ~size_t(4095);
-    CU(cudaMalloc(&sc->scratch, want));
-    sc->scratch_bytes = want;
+#define RT_GRID_SLOTS 8
+static void grid_free(rt_scene::Grid &g) {
+    if (g.dev) cudaFree(g.dev);
+    if (g.pinned) cudaFreeHost(g.pinned);
+    if (g.ready) cudaEventDestroy(g.ready);
+    g.dev = g.pinned = nullptr; g.ready = nullptr;
+}
+
+// device copy of the (X, Y) direction grid in precision T, ordered before anything launched on `st` after the call
+template <typename T> static int resident_grid(rt_scene *sc, const rt_whitted_params *p, cudaStream_t st, const T **out) {
+    const size_t nx = (size_t)p->W, ny = (size_t)p->H;
+    const int prec = sizeof(T) == 8 ? RT_F64 : RT_F32;
+    for (rt_scene::Grid &g : sc->grids) {
+        if (g.precision != prec || g.nx != nx || g.ny != ny) continue;
+        if (std::memcmp(g.key.data(), p->X, nx * sizeof(double)) || std::memcmp(g.key.data() + nx, p->Y, ny * sizeof(double))) continue;
+        if (!g.settled) {
+            if (cudaEventQuery(g.ready) == cudaSuccess) g.settled = true;
+            else if (st != g.upload_stream) CU(cudaStreamWaitEvent(st, g.ready, 0));
+        }
+        *out = reinterpret_cast<const T *>(g.dev);
+        return RT_OK;
+    }
+    if (sc->grids.size() >= RT_GRID_SLOTS) {          // retire the oldest entry: no kernel may still be reading it
+        CU(cudaDeviceSynchronize());
+        grid_free(sc->grids.front());
+        sc->grids.erase(sc->grids.begin());
+    }
+    rt_scene::Grid g;
+    g.precision = prec; g.nx = nx; g.ny = ny;
+    g.key.assign(p->X, p->X + nx);
+    g.key.insert(g.key.end(), p->Y, p->Y + ny);
+    cudaError_t e = cudaMallocHost(&g.pinned, (nx + ny) * sizeof(T));
+    if (e == cudaSuccess) e = cudaMalloc(&g.dev, (nx + ny) * sizeof(T));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) {
+        T *h = reinterpret_cast<T *>(g.pinned);
+        for (size_t i = 0; i < nx + ny; ++i) h[i] = (T)g.key[i];
+        e = cudaMemcpyAsync(g.dev, g.pinned, (nx + ny) * sizeof(T), cudaMemcpyHostToDevice, st);
+    }
+    if (e == cudaSuccess) e = cudaEventRecord(g.ready, st);
+    if (e != cudaSuccess) { grid_free(g); return cuda_fail(e, "direction grid upload"); }
+    g.upload_stream = st;
+    *out = reinterpret_cast<const T *>(g.dev);
+    sc->grids.push_back(std::move(g));
     return RT_OK;
 }
 
@@ -396,7 +461,10 @@ RT_EXPORT int rt_scene_destroy(rt_scene *scene) {
     if (scene->d.blob) cudaFree(scene->d.blob);
     if (scene->small_dev) cudaFree(scene->small_dev);
     if (scene->sched_dev) cudaFree(scene->sched_dev);
-    if (scene->scratch) cudaFree(scene->scratch);
+    if (scene->stage) cudaFreeHost(scene->stage);
+    if (scene->staged) cudaEventDestroy(scene->staged);
+    for (rt_scene::Grid &g : scene->grids) grid_free(g);
+    scene->grids.clear();
     delete scene;
     return RT_OK;
 }
@@ -473,17 +541,13 @@ RT_EXPORT int rt_terminal_rgb(rt_scene *scene, int precision, int m, const doubl
 template <typename T>
 static int render_whitted_t(rt_scene *sc, const SceneDev<T> &view, const rt_whitted_params *p, void *accum, int32_t *hit,
                             uint64_t *stats, cudaStream_t st) {
-    const size_t nx = (size_t)p->W, ny = (size_t)p->H;
-    int rc = ensure_scratch(sc, (nx + ny) * sizeof(T));
+    const size_t nx = (size_t)p->W;
+    const T *grid = nullptr;
+    int rc = resident_grid<T>(sc, p, st, &grid);      // no copy and no synchronisation once the grid is resident
     if (rc) return rc;
-    std::vector<T> grid(nx + ny);
-    for (size_t i = 0; i < nx; ++i) grid[i] = (T)p->X[i];
-    for (size_t i = 0; i < ny; ++i) grid[nx + i] = (T)p->Y[i];
-    CU(cudaMemcpyAsync(sc->scratch, grid.data(), (nx + ny) * sizeof(T), cudaMemcpyHostToDevice, st));
-    CU(cudaStreamSynchronize(st));      // `grid` is pageable and dies at return
     WhittedDev<T> wp;
     wp.cam[0] = (T)p->cam[0]; wp.cam[1] = (T)p->cam[1]; wp.cam[2] = (T)p->cam[2];
-    wp.X = reinterpret_cast<const T *>(sc->scratch);
+    wp.X = grid;
     wp.Y = wp.X + nx;
     wp.W = p->W; wp.H = p->H; wp.y0 = p->y0; wp.y1 = p->y1; wp.s0 = p->s0; wp.s1 = p->s1; wp.spp = p->spp;
     wp.max_bounces = p->max_bounces; wp.shadow_max_bounces = p->shadow_max_bounces;

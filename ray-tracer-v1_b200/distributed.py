@@ -217,7 +217,8 @@ class ShardedPathRenderer:
         self.group = group
         self.rank, self.world = _world(group)
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.precision = nat.F64 if precision in ("f64", nat.F64) and precision != nat.F32 else nat.F32
+        from .renderers import _precision
+        self.precision = _precision(precision)        # 'fp64' / 'float64' / 'double' too; unknown strings raise ValueError
         self.scene = None
         self._key = None
         self.h2d_bytes = self.d2h_bytes = 0

@@ -101,7 +101,8 @@ class BatchedRayTracerEnv:
         if reward_mode == "adaptive" and flavour != "rl":
             raise ValueError("the adaptive reward (RL/train_raytracer_optimized.py) shapes the RL flavour's reward")
         self.reward_mode, self.light_ids = reward_mode, (int(light_ids[0]), int(light_ids[1]))
-        self.precision = nat.F64 if precision in ("f64", "fp64", "float64", "double", nat.F64) and precision != nat.F32 else nat.F32
+        from .renderers import _precision
+        self.precision = _precision(precision)        # unknown strings raise ValueError
         self.device = int(device)
         self.seed = int(seed)
         self.observation_space, self.action_space = _spaces(self.max_bounces, flavour)
@@ -121,6 +122,7 @@ class BatchedRayTracerEnv:
         self.handle = None
         self._resets = 0
         self._step_args = None
+        self._desc_key = None
 
     # ---- sharding ------------------------------------------------------------------------------------------------
     @classmethod
@@ -148,18 +150,27 @@ class BatchedRayTracerEnv:
             self.scene = nat.DeviceScene(fs, self.device)
         else:
             self.scene.update(fs)
+        # the reference re-reads camera / fov / max_bounces / image size on every reset (RL/ray_tracer_env.py:254-293):
+        # a changed descriptor gets a fresh device env (the episode state is re-initialised by the reset anyway)
+        desc_key = (self.n_envs, int(self.image_width), int(self.image_height), _xyz(self.camera_position),
+                    _xyz(self.camera_angle), float(self.fov), int(self.max_bounces), self.flavour, int(self.sun_id),
+                    self.reward_mode, tuple(int(v) for v in self.light_ids))
+        if self.handle is not None and desc_key != self._desc_key:
+            nat.load_symbols().rt_env_destroy(self.handle)
+            self.handle = None
         if self.handle is None:
             d = nat.EnvDesc()
-            d.B, d.W, d.H = self.n_envs, self.image_width, self.image_height
+            d.B, d.W, d.H = self.n_envs, int(self.image_width), int(self.image_height)
             d.cam[:] = _xyz(self.camera_position)
             d.cam_angle[:] = _xyz(self.camera_angle)
-            d.fov, d.max_bounces = float(self.fov), self.max_bounces
-            d.flavour, d.sun_id = (nat.ENV_FB if self.flavour == "fb" else nat.ENV_RL), self.sun_id
+            d.fov, d.max_bounces = float(self.fov), int(self.max_bounces)
+            d.flavour, d.sun_id = (nat.ENV_FB if self.flavour == "fb" else nat.ENV_RL), int(self.sun_id)
             d.reward_mode = 1 if self.reward_mode == "adaptive" else 0
-            d.light_ids[:] = self.light_ids
+            d.light_ids[:] = [int(v) for v in self.light_ids]
             h = C.c_void_p()
             nat.check(nat.lib().rt_env_create(self.scene.handle, self.precision, C.byref(d), C.byref(h)))
             self.handle = h.value
+            self._desc_key = desc_key
 
     def _dev_tensor(self, x, dtype, shape):
         torch = self.torch
@@ -400,7 +411,11 @@ class RayTracerVecEnv(_VecEnvBase):
     of dicts (no device->host copy on the rollout path)."""
 
     def __init__(self, spheres, n_envs, as_torch=False, **env_kwargs):
+        import time
         self.env = BatchedRayTracerEnv(spheres, n_envs, **env_kwargs)
+        if _VecEnvBase is not object:
+            # SB3's own constructor: num_envs, the spaces, reset_infos / _seeds / _options (VecEnv.__init__)
+            super().__init__(int(n_envs), self.env.observation_space, self.env.action_space)
         self.num_envs = int(n_envs)
         self.observation_space, self.action_space = self.env.observation_space, self.env.action_space
         self.as_torch = bool(as_torch)
@@ -408,6 +423,9 @@ class RayTracerVecEnv(_VecEnvBase):
         self._actions = None
         self._seed = env_kwargs.get("seed", 0)
         self.episode_returns = None
+        torch = self.env.torch
+        self._ep_len = torch.zeros(self.num_envs, dtype=torch.int32, device=self.env.obs.device)   # steps of the running episode
+        self._t0 = time.time()
 
     def seed(self, seed=None):
         self._seed = 0 if seed is None else int(seed)
@@ -416,32 +434,45 @@ class RayTracerVecEnv(_VecEnvBase):
     def reset(self):
         obs, _ = self.env.reset(seed=self._seed)
         self._seed += 1
+        self._ep_len.zero_()
+        if hasattr(self, "reset_infos"):
+            self.reset_infos = [{} for _ in range(self.num_envs)]
         return obs.clone() if self.as_torch else obs.cpu().numpy().copy()
 
     def step_async(self, actions):
         self._actions = actions
 
     def step_wait(self):
+        import time
         torch = self.env.torch
         obs, rew, term, trunc, binfo = self.env.step(self._actions)
         dones = term | trunc
         rew = rew.clone()
         last_obs = obs.clone()
-        trunc_now = trunc.clone()
+        # SB3's DummyVecEnv sets TimeLimit.truncated = truncated and not terminated; the reference env returns
+        # terminated = truncated = True at max_bounces (RL/ray_tracer_env.py:384-392), so the flag is False there and
+        # SB3 does not bootstrap the value at those ends -- exactly as when it trains on the reference env
+        time_limit = (trunc & ~term).clone()
         reason = binfo["reason"].clone()
         total = binfo["total_reward"].clone()
+        self._ep_len += 1
+        ep_len = self._ep_len.clone()
         if bool(dones.any()):
             obs, _ = self.env.reset(mask=dones.to(torch.uint8))            # only the finished episodes restart
+            self._ep_len.masked_fill_(dones, 0)
         if self.as_torch:
-            infos = {"terminal_observation": last_obs, "TimeLimit.truncated": trunc_now, "reason": reason,
-                     "total_reward": total, "done": dones}
+            infos = {"terminal_observation": last_obs, "TimeLimit.truncated": time_limit, "reason": reason,
+                     "total_reward": total, "done": dones, "episode_length": ep_len}
             return obs.clone(), rew.to(torch.float32), dones, infos
         d = dones.cpu().numpy()
-        lo, tn, rs, tt = last_obs.cpu().numpy(), trunc_now.cpu().numpy(), reason.cpu().numpy(), total.cpu().numpy()
+        lo, tn, rs, tt, ln = (last_obs.cpu().numpy(), time_limit.cpu().numpy(), reason.cpu().numpy(), total.cpu().numpy(),
+                              ep_len.cpu().numpy())
         infos = [{} for _ in range(self.num_envs)]
+        elapsed = round(time.time() - self._t0, 6)
         for i in np.nonzero(d)[0]:
+            # 'episode' carries what SB3's Monitor writes and its logger reads: return, length, elapsed seconds
             infos[i] = {"terminal_observation": lo[i].copy(), "TimeLimit.truncated": bool(tn[i]),
-                        "reason": nat.REASONS[int(rs[i])], "episode": {"r": float(tt[i])}}
+                        "reason": nat.REASONS[int(rs[i])], "episode": {"r": float(tt[i]), "l": int(ln[i]), "t": elapsed}}
         return obs.cpu().numpy().copy(), rew.cpu().numpy().astype(np.float32), d, infos
 
     def step(self, actions):

@@ -54,10 +54,18 @@ def save_png(image, path):
 
 
 def render_whitted(fs, camera, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0, miss=None, seed=0, prenorm=False,
-                   precision="f32", device=0, return_raw=False):
+                   precision="f32", device=0, return_raw=False, context=None):
     """Algorithm A frame over the direction grid (X[i], Y[j], -1) -> float32 image [H,W,3] (``int(sum/spp)/255``).
 
-    return_raw=True also returns (sums [H,W,4], hit [H,W] int32, stats dict)."""
+    return_raw=True also returns (sums [H,W,4], hit [H,W] int32, stats dict).
+    context: a ``FrameContext`` to render through -- its scene handle, HBM buffers, pinned host image and resident
+    direction grid are reused from frame to frame (the render entries keep one); None = a throw-away scene handle."""
+    if context is not None and not return_raw:
+        context.set_scene(fs)
+        view, _ = context.render_whitted(_xyz(camera), X, Y, spp=spp, max_bounces=max_bounces,
+                                         shadow_max_bounces=shadow_max_bounces, miss=miss, seed=seed, prenorm=prenorm,
+                                         precision=_precision(precision))
+        return view.copy()
     sc = nat.DeviceScene(fs, device)
     try:
         p = sc.whitted_params(_xyz(camera), X, Y, spp=spp, max_bounces=max_bounces, shadow_max_bounces=shadow_max_bounces,
@@ -168,6 +176,12 @@ class CustomSceneExperiment:
         self.timing_data = {'traditional': []}
         self.rendered_images = {}
         self.device, self.precision, self.seed = device, precision, seed
+        self._ctx = None            # persistent FrameContext: scene handle, HBM buffers, pinned image, resident grid
+
+    def _context(self):
+        if self._ctx is None:
+            self._ctx = FrameContext(self.device)
+        return self._ctx
 
     @staticmethod
     def _as_rendered(scene_spheres):
@@ -186,7 +200,7 @@ class CustomSceneExperiment:
         X, Y = notebook_grid(300, 0.01 / 3)
         fs = self._as_rendered(scene_spheres)
         image = render_whitted(fs, (0, 0, 1), X, Y, spp=1, max_bounces=5, miss=(2, 2, 5), prenorm=False,
-                               precision=self.precision, device=self.device)
+                               precision=self.precision, device=self.device, context=self._context())
         if save_path is not None:
             save_png(image, save_path)
         return image
@@ -201,7 +215,8 @@ class CustomSceneExperiment:
         X, Y = custom_scene_grid(width, height)
         fs = self._as_rendered(scene_spheres)
         image = render_whitted(fs, (0, 0, 1), X, Y, spp=spp, max_bounces=self.config['max_bounces'], miss=(2, 2, 5),
-                               seed=self.seed, prenorm=True, precision=self.precision, device=self.device)
+                               seed=self.seed, prenorm=True, precision=self.precision, device=self.device,
+                               context=self._context())
         render_time = time.time() - start
         self.timing_data['traditional'].append(render_time)
         self.rendered_images[method] = image
@@ -233,13 +248,19 @@ class SimplifiedFBRenderer:
         self.stats = {'total_rays': 0, 'sun_hits': 0, 'fb_used': 0, 'fb_success': 0, 'render_time': 0}
         self.device, self.precision, self.seed = device, precision, seed
         self._renders = 0
+        self._sc = None
 
     def _scene_and_params(self, width, height):
         if self.fb_usage_prob:
             raise NotImplementedError("FB-guided sampling is outside the traditional hot path (fb_usage_prob must be 0)")
         seed = self.seed if self.seed is not None else (time.time_ns() ^ (self._renders * 0x9E3779B97F4A7C15)) & (2 ** 64 - 1)
         self._renders += 1
-        sc = nat.DeviceScene(flatten_scene(self.scene), self.device)       # re-flattened: the scene list is mutable
+        fs = flatten_scene(self.scene)                                      # re-flattened: the scene list is mutable
+        if self._sc is None:
+            self._sc = nat.DeviceScene(fs, self.device)                     # persistent handle, re-uploaded per call
+        else:
+            self._sc.update(fs)
+        sc = self._sc
         p = sc.simple_params(width, height, cam=(0.0, 0.0, 1.0), sun_pos=_xyz(self.sun_position),
                              sun_col=self.sun_color.getList(), sun_id=7, max_bounces=self.max_bounces, seed=seed)
         return sc, p
@@ -247,12 +268,9 @@ class SimplifiedFBRenderer:
     def trace_ray_simple(self, ray):
         """One ray -> accumulated ``Colour`` (output6.py:434-577); a batch of one through the same kernel."""
         sc, p = self._scene_and_params(1, 1)
-        try:
-            o, d = _xyz(ray.origin), _xyz(ray.D)
-            _, rgb, st = sc.render_simple_host(p, _precision(self.precision), rays=np.array([[*o, *d]], np.float64),
-                                               want_image=False)
-        finally:
-            sc.close()
+        o, d = _xyz(ray.origin), _xyz(ray.D)
+        _, rgb, st = sc.render_simple_host(p, _precision(self.precision), rays=np.array([[*o, *d]], np.float64),
+                                           want_image=False)
         self.stats['total_rays'] += int(st[0])
         self.stats['sun_hits'] += int(st[1])
         return Colour(int(rgb[0, 0, 0]), int(rgb[0, 0, 1]), int(rgb[0, 0, 2]))
@@ -264,10 +282,7 @@ class SimplifiedFBRenderer:
         self.stats = {'total_rays': 0, 'sun_hits': 0, 'fb_used': 0, 'fb_success': 0, 'render_time': 0}
         start = time.time()
         sc, p = self._scene_and_params(width, height)
-        try:
-            image, _, st = sc.render_simple_host(p, _precision(self.precision))
-        finally:
-            sc.close()
+        image, _, st = sc.render_simple_host(p, _precision(self.precision))
         self.stats['total_rays'], self.stats['sun_hits'] = int(st[0]), int(st[1])
         self.stats['render_time'] = time.time() - start
         if output_path:

@@ -261,6 +261,12 @@ def test_vec_env_adapter(rt):
         for i in np.nonzero(dones)[0][:8]:
             assert infos[i]["terminal_observation"].shape == (18,) and "TimeLimit.truncated" in infos[i]
             assert infos[i]["reason"] in ("ray_missed", "ray_escaped", "max_bounces")
+            # what SB3's logger reads from Monitor-style infos, and its DummyVecEnv rule for TimeLimit.truncated
+            # (truncated and not terminated: the reference env ends max_bounces episodes with BOTH flags set)
+            ep = infos[i]["episode"]
+            assert set(ep) == {"r", "l", "t"} and 1 <= ep["l"] <= spec.max_bounces + 1 and ep["t"] >= 0
+            assert infos[i]["TimeLimit.truncated"] is False
+            assert int(tinfos["episode_length"][i]) == ep["l"] and not bool(tinfos["TimeLimit.truncated"][i])
             assert np.array_equal(infos[i]["terminal_observation"], tinfos["terminal_observation"][i].cpu().numpy())
         assert all(not infos[i] for i in np.nonzero(~dones)[0][:8])
         finished += int(dones.sum())
@@ -274,3 +280,37 @@ def test_vec_env_adapter(rt):
     o, r, term, trunc, info = env.step(np.array([0.3, 1.0], np.float32))
     assert o.shape == (18,) and isinstance(r, float) and "total_reward" in info
     env.close()
+
+
+def test_vec_env_adapter_under_sb3(rt):
+    """The adapter is a real stable_baselines3 VecEnv when SB3 is installed: PPO.learn runs a few updates on it."""
+    sb3 = pytest.importorskip("stable_baselines3")
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.ray_tracer_env import RayTracerVecEnv
+    spec = scenes.build_optimized_env_scene()
+    ve = RayTracerVecEnv(spec.spheres, 64, image_width=spec.width, image_height=spec.height, fov=spec.fov,
+                         max_bounces=spec.max_bounces, point_light_sources=spec.point_lights, seed=1)
+    assert hasattr(ve, "reset_infos") and len(ve.reset_infos) == 64
+    model = sb3.PPO("MlpPolicy", ve, n_steps=16, batch_size=256, verbose=0, device="cpu")
+    model.learn(total_timesteps=64 * 16 * 2)
+    ve.close()
+
+
+def test_env_descriptor_is_reread_on_reset(rt):
+    """The reference re-reads camera / fov / max_bounces at every reset: editing them between resets takes effect."""
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
+    spec = scenes.build_optimized_env_scene()
+    kw = dict(image_width=spec.width, image_height=spec.height, max_bounces=spec.max_bounces,
+              point_light_sources=spec.point_lights, precision="float64")
+    pix = np.array([[160, 120], [10, 200], [300, 30], [200, 150]], np.int32)
+    a = BatchedRayTracerEnv(spec.spheres, 4, fov=80, **kw)
+    o80 = a.reset(options={"pixels": pix})[0].clone()
+    a.fov = 50
+    o50 = a.reset(options={"pixels": pix})[0].clone()
+    b = BatchedRayTracerEnv(spec.spheres, 4, fov=50, **kw)
+    assert np.array_equal(o50.cpu().numpy(), b.reset(options={"pixels": pix})[0].cpu().numpy())
+    assert not np.array_equal(o80.cpu().numpy(), o50.cpu().numpy())
+    with pytest.raises(ValueError):
+        BatchedRayTracerEnv(spec.spheres, 4, precision="float16")
+    a.close(); b.close()
