@@ -262,12 +262,38 @@ enum { RT_SINK_ACCUM = 0, RT_SINK_IMAGE = 1, RT_SINK_SCATTER_ADD = 2 };
 #define RT_IPC_HANDLE_BYTES 64
 typedef struct rt_path_sink {
     int32_t mode;
-    int32_t world;                    /* ranks (SCATTER_ADD) */
+    int32_t world;                    /* ranks (SCATTER_ADD; with sync: both modes) */
     int32_t tile_first, tile_step;    /* IMAGE: 8-row tiles rendered by this launch */
-    float *image;                     /* IMAGE: [H,W,3] float32, device or peer pointer */
+    float *image;                     /* IMAGE: [H,W,3] float32, device or peer pointer (with sync: both modes, = the
+                                         collecting rank's image) */
     void *accum[RT_MAX_PEERS];        /* SCATTER_ADD: per-owner [H,W,4] float32 accumulators (zeroed by the owner) */
     int32_t band_y[RT_MAX_PEERS + 1]; /* SCATTER_ADD: owner row bands */
+    /* ---- sync = 1: the WHOLE frame protocol runs inside this one launch (one kernel per rank and frame; see below) */
+    int32_t sync;
+    int32_t rank;                     /* this rank; rank 0 collects the image */
+    uint32_t epoch;                   /* frame number, starting at 1, the same on every rank */
+    uint32_t go_epoch;                /* rank 0: publish "frames <= go_epoch are consumed" to every rank at kernel start
+                                         (everything queued on this stream before the launch has finished by then);
+                                         0 = nothing to publish (e.g. the consumer signals from another stream) */
+    uint32_t *flags[RT_MAX_PEERS];    /* flag block of every rank (own block at [rank], peer mappings elsewhere):
+                                         RT_FLAG_WORDS uint32, zero-initialised: [r] added, [16 + r] done, [32] go */
+    int32_t *timed_out;               /* device int32 (optional): set to 1 if a flag wait gives up */
+    int32_t timeout_ms;               /* <= 0: 20 s */
+    int32_t max_ctas;                 /* 0 = as many CTAs as the device keeps resident; smaller values let several
+                                         "ranks" share ONE device (tests) */
 } rt_path_sink;
+#define RT_FLAG_WORDS 64
+/* sync = 1 -- one launch per rank and frame, no other kernel and no host round trip on the data path:
+ *   start    every CTA waits (acquire) until go >= epoch - 2: the image / accumulator buffers of this parity are free
+ *   render   as above: IMAGE stores resolved pixels into rank 0's image, SCATTER_ADD adds sums into the owners' bands
+ *   publish  the last warp of the launch to finish (system fence, release store): IMAGE sets done[rank] on rank 0;
+ *            SCATTER_ADD sets added[rank] on every rank
+ *   resolve  SCATTER_ADD only: once added[0..world) have all reached the epoch, the CTAs of the launch resolve the own
+ *            band [band_y[rank], band_y[rank+1]) of accum[rank] into rank 0's image, clear it for frame epoch + 2,
+ *            and the last CTA sets done[rank] on rank 0
+ *   collect  rank 0 only: the launch ends after done[0..world) have reached the epoch, i.e. kernel completion = frame
+ *            complete in `image`.
+ * The launches of all ranks must be able to run concurrently (one per GPU; tests: max_ctas). */
 /* FP32 product path only.  p->y0/y1 are ignored for RT_SINK_IMAGE (the tiles say which rows); p->s0/s1 must be the
  * full [0, spp) range there. */
 int rt_render_path_sink(rt_scene *scene, const rt_path_params *p, const rt_path_sink *sink, uint64_t *stats_dev,

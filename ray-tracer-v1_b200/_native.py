@@ -74,7 +74,13 @@ SINK_ACCUM, SINK_IMAGE, SINK_SCATTER_ADD = 0, 1, 2
 
 class PathSink(C.Structure):
     _fields_ = [("mode", C.c_int32), ("world", C.c_int32), ("tile_first", C.c_int32), ("tile_step", C.c_int32),
-                ("image", C.c_void_p), ("accum", C.c_void_p * RT_MAX_PEERS), ("band_y", C.c_int32 * (RT_MAX_PEERS + 1))]
+                ("image", C.c_void_p), ("accum", C.c_void_p * RT_MAX_PEERS), ("band_y", C.c_int32 * (RT_MAX_PEERS + 1)),
+                ("sync", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("go_epoch", C.c_uint32),
+                ("flags", C.c_void_p * RT_MAX_PEERS), ("timed_out", C.c_void_p), ("timeout_ms", C.c_int32),
+                ("max_ctas", C.c_int32)]
+
+
+FLAG_WORDS = 64
 
 
 class EnvDesc(C.Structure):

@@ -68,7 +68,7 @@ struct rt_scene {
     cudaEvent_t staged = nullptr;
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
-    mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS pairs of work counters of the persistent path kernel (zero at rest)
+    mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS x 4 work counters of the persistent path kernel (zero at rest)
     mutable std::atomic<unsigned> sched_next{0}; // launches rotate through the slots, so launches in flight never share a pair
     PkConst pkc;                  // host copy of the FP32 sphere pairs of a small scene (path kernel parameter block)
     bool pkc_ok = false;
@@ -255,8 +255,8 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
     CU(cudaMemcpyAsync(sc->d.blob, hd, sc->d.bytes, cudaMemcpyHostToDevice, st));
     CU(cudaMemcpyAsync(sc->small_dev, hs, n_small, cudaMemcpyHostToDevice, st));
     if (!sc->sched_dev) {                   // work counters of the persistent path kernel: zero at rest, re-armed by every launch
-        CU(cudaMalloc((void **)&sc->sched_dev, 2 * RT_SCHED_SLOTS * sizeof(unsigned)));
-        CU(cudaMemsetAsync(sc->sched_dev, 0, 2 * RT_SCHED_SLOTS * sizeof(unsigned), st));
+        CU(cudaMalloc((void **)&sc->sched_dev, 4 * RT_SCHED_SLOTS * sizeof(unsigned)));
+        CU(cudaMemsetAsync(sc->sched_dev, 0, 4 * RT_SCHED_SLOTS * sizeof(unsigned), st));
     }
     CU(cudaEventRecord(sc->staged, st));
     {   // small scenes: the path kernel takes the FP32 pair array through its parameter block (kMode 3)
@@ -621,6 +621,28 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             for (int k = 0; k <= sink->world; ++k) pp.band_y[k] = sink->band_y[k];
             if (pp.band_y[0] != 0 || pp.band_y[sink->world] != p->H) return fail(RT_ERR_INVALID, "owner bands must cover the image");
         } else return fail(RT_ERR_INVALID, "unknown sink mode");
+        pp.max_ctas = sink->max_ctas > 0 ? sink->max_ctas : 0;
+        if (sink->sync) {
+            // the whole frame protocol inside the launch (include/rt_b200.h): flags of every rank, epoch, collecting image
+            if (sink->world < 1 || sink->world > RT_MAX_PEERS || sink->rank < 0 || sink->rank >= sink->world)
+                return fail(RT_ERR_INVALID, "bad world / rank for a synchronised sink");
+            if (sink->epoch == 0u) return fail(RT_ERR_INVALID, "epochs start at 1");
+            if (!sink->image) return fail(RT_ERR_INVALID, "a synchronised sink needs the collecting rank's image");
+            for (int k = 0; k < sink->world; ++k) {
+                if (!sink->flags[k]) return fail(RT_ERR_INVALID, "missing flag block");
+                pp.flags[k] = sink->flags[k];
+            }
+            pp.sync = 1; pp.rank = sink->rank; pp.world = sink->world; pp.epoch = sink->epoch; pp.go_epoch = sink->go_epoch;
+            pp.image = sink->image;
+            pp.timed_out = sink->timed_out;
+            static int khz_cache[64] = {0};
+            int khz = sc->device >= 0 && sc->device < 64 ? khz_cache[sc->device] : 0;
+            if (khz == 0) {
+                if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, sc->device) != cudaSuccess || khz <= 0) khz = 2000000;
+                if (sc->device >= 0 && sc->device < 64) khz_cache[sc->device] = khz;
+            }
+            pp.timeout_cycles = (long long)(sink->timeout_ms > 0 ? sink->timeout_ms : 20000) * (long long)khz;
+        }
     }
     // sample split (automatic): k lanes per pixel so that a lane keeps about 8 samples -- measured best at 8, 16, 32 and
     // 64 samples per launch (k = 1, 2, 4, 8: tighter camera-ray cones against per-unit overhead) -- and, for small frames,
@@ -647,7 +669,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         pp.ksplit_log2 = lk;
     }
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
-    unsigned *sched = sc->sched_dev + 2 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
+    unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);      // {next unit, warps done, CTAs resolved, -}
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
                       sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 && !(p->schedule & 4) ? &sc->pkc : nullptr, sched));
     return RT_OK;

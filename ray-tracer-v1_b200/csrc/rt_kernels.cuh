@@ -204,6 +204,26 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
     }
 }
 
+// ------------------------------------------------------------------ epoch flags in peer memory (rt_path_sink::sync)
+// wait: system-scope acquire loads until the flag has reached the epoch (wrap-safe compare); gives up after
+// timeout_cycles and reports instead of hanging.  post: system-scope release store; the caller has fenced.
+RT_DEV void flag_wait(const unsigned *flag, unsigned epoch, long long timeout_cycles, int *timed_out) {
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if ((int)(v - epoch) >= 0) return;
+        if (clock64() - t0 > timeout_cycles) { if (timed_out) *timed_out = 1; return; }
+        __nanosleep(64);
+    }
+}
+RT_DEV void flag_post(unsigned *flag, unsigned epoch) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(epoch) : "memory");
+}
+#define RT_FLAG_ADDED 0
+#define RT_FLAG_DONE 16
+#define RT_FLAG_GO 32
+
 // ------------------------------------------------------------------ Algorithm B frame
 // TraditionalRenderer.generate_camera_ray (chandelier.py:417-429): aspect is applied twice on x.
 template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, int y, T u0, T u1) {
@@ -267,6 +287,18 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         stage_scene<T, kShared>(sc, smem + 256 * sizeof(double), S);    // ends with __syncthreads() when staging
         if constexpr (!kShared) __syncthreads();
         S.g.sv.cw = nullptr;
+    }
+    if constexpr (!M<T>::exact && kIntFold) {
+        if (pp.sync) {
+            // frame protocol, start: rank 0 publishes what its stream has consumed (everything queued before this launch
+            // has finished), then every CTA waits until the buffers of this frame's parity are free
+            if (threadIdx.x == 0) {
+                if (pp.go_epoch != 0u && blockIdx.x == 0)
+                    for (int k = 0; k < pp.world; ++k) flag_post(pp.flags[k] + RT_FLAG_GO, pp.go_epoch);
+                flag_wait(pp.flags[pp.rank] + RT_FLAG_GO, pp.epoch - 2u, pp.timeout_cycles, pp.timed_out);
+            }
+            __syncthreads();
+        }
     }
     // Sample split: k = 2^ksplit_log2 lanes share one pixel, lane `sub` tracing samples s0 + sub, s0 + sub + k, ...
     // (summed with shuffles at the end).  A warp then covers 32/k pixels -- pw x ph = 8x4, 8x2, 4x2, 2x2, 2x1, 1x1 --
@@ -502,10 +534,55 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     }
     unit = __shfl_sync(0xffffffffu, nxt, 0);
     }   // work units of this warp
+    bool sync = false;
+    if constexpr (!M<T>::exact && kIntFold) sync = pp.sync != 0;
     if (lane_ == 0) {
         // every warp of the launch passes here exactly once, after its last fetch: the last one re-arms the counters
-        __threadfence();
-        if (atomicAdd(pp.sched + 1, 1u) == (gridDim.x << 3) - 1u) { pp.sched[0] = 0u; pp.sched[1] = 0u; __threadfence(); }
+        // and, under the frame protocol, publishes this rank's part (its peer writes, and through the fence + counter
+        // chain those of every other warp, are ordered before the release stores)
+        if (sync) __threadfence_system(); else __threadfence();
+        if (atomicAdd(pp.sched + 1, 1u) == (gridDim.x << 3) - 1u) {
+            if (sync) {
+                __threadfence_system();
+                if (pp.sink == 1) flag_post(pp.flags[0] + RT_FLAG_DONE + pp.rank, pp.epoch);
+                else for (int k = 0; k < pp.world; ++k) flag_post(pp.flags[k] + RT_FLAG_ADDED + pp.rank, pp.epoch);
+            }
+            pp.sched[0] = 0u; pp.sched[1] = 0u; __threadfence();
+        }
+    }
+    if constexpr (!M<T>::exact && kIntFold) {
+        if (sync) {
+            __syncthreads();                          // the CTA's eight warps have all finished their units
+            if (pp.sink == 2) {
+                // resolve: once every rank's sums have arrived in this rank's band, turn it into pixels of rank 0's
+                // image and clear it for the frame after next; the launch's CTAs share the band
+                if ((int)threadIdx.x < pp.world) flag_wait(pp.flags[pp.rank] + RT_FLAG_ADDED + threadIdx.x, pp.epoch, pp.timeout_cycles, pp.timed_out);
+                __syncthreads();
+                float4 *own = pp.peer_accum[pp.rank];
+                const size_t first = (size_t)pp.band_y[pp.rank] * pp.W, count = (size_t)(pp.band_y[pp.rank + 1] - pp.band_y[pp.rank]) * pp.W;
+                const double spp = (double)pp.spp_total;
+                for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+                    const size_t o = first + i;
+                    const float4 a = __ldcg(own + o);                  // L2: where the peers' reductions landed
+                    const double r = floor((double)a.x / spp) / 255.0, g = floor((double)a.y / spp) / 255.0, b = floor((double)a.z / spp) / 255.0;
+                    float *px = pp.image + 3 * o;
+                    px[0] = (float)(r < 1.0 ? r : 1.0); px[1] = (float)(g < 1.0 ? g : 1.0); px[2] = (float)(b < 1.0 ? b : 1.0);
+                    __stcg(own + o, make_float4(0.f, 0.f, 0.f, 0.f));
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    __threadfence_system();
+                    if (atomicAdd(pp.sched + 2, 1u) == gridDim.x - 1u) {
+                        pp.sched[2] = 0u;
+                        __threadfence_system();
+                        flag_post(pp.flags[0] + RT_FLAG_DONE + pp.rank, pp.epoch);
+                    }
+                }
+            }
+            // collect: rank 0's launch ends when every rank's part of the image is in place
+            if (pp.rank == 0 && blockIdx.x == 0 && (int)threadIdx.x < pp.world)
+                flag_wait(pp.flags[0] + RT_FLAG_DONE + threadIdx.x, pp.epoch, pp.timeout_cycles, pp.timed_out);
+        }
     }
     if (stats) {
         flush_stats(stats, STAT_RAYS, n_rays);
@@ -1154,12 +1231,14 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \
       grid.x = persistent_ctas(path_kernel<T, M_, F_, R_>, sm, tiles_total);                                       \
+      if (pp.max_ctas > 0 && grid.x > (unsigned)pp.max_ctas) grid.x = (unsigned)pp.max_ctas;                        \
       path_kernel<T, M_, F_, R_><<<grid, block, sm, st>>>(sc, ppl, (v4 *)accum, stats, PkNone()); }
     if (mode == 3) {
         if constexpr (sizeof(T) == 4) {
 #define RT_PATH_CASE3(F_, R_)                                                                                      \
     { e = allow_smem(path_kernel<T, 3, F_, R_>, sm); if (e != cudaSuccess) return e;                               \
       grid.x = persistent_ctas(path_kernel<T, 3, F_, R_>, sm, tiles_total);                                        \
+      if (pp.max_ctas > 0 && grid.x > (unsigned)pp.max_ctas) grid.x = (unsigned)pp.max_ctas;                        \
       path_kernel<T, 3, F_, R_><<<grid, block, sm, st>>>(sc, ppl, (v4 *)accum, stats, *pkc); }
             if (pp.int_fold) { if (pp.regenerate) RT_PATH_CASE3(true, true) else RT_PATH_CASE3(true, false) }
             else { if (pp.regenerate) RT_PATH_CASE3(false, true) else RT_PATH_CASE3(false, false) }

@@ -36,6 +36,13 @@ template <typename T> struct PathDev {
     float *image;
     float4 *peer_accum[16];
     int band_y[17];
+    // in-kernel frame protocol (rt_path_sink::sync): epoch flags in peer memory, see include/rt_b200.h
+    int sync, rank;
+    unsigned epoch, go_epoch;
+    unsigned *flags[16];                 // [r] added, [16 + r] done, [32] go -- in every rank's flag block
+    int *timed_out;
+    long long timeout_cycles;
+    int max_ctas;
 };
 
 // "Algorithm C" frame (rt_simple_params)

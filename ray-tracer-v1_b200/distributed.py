@@ -335,71 +335,98 @@ class ShardedPathRenderer:
         self._fab_key = (W, H)
 
     def render_fused(self, cam, W, H, spp, max_bounces, mirror_threshold, seed=0, fov=60.0, mode="tiles", to_host=False,
-                     kernel_events=None):
-        """The same frame as ``render`` with the collective fused into the kernels: no NCCL call on the data path.
+                     kernel_events=None, in_kernel=True):
+        """The same frame as ``render`` with the collective fused into the path kernel: no NCCL call on the data path.
 
         tiles    every rank renders interleaved 8-row stripes (tile_stripes) and its path kernel stores the resolved
                  float32 pixels straight into rank 0's image through the NVLink peer mapping.
         samples  every rank renders its sample range of all pixels; the path kernel's epilogue adds each pixel's sums
                  into the accumulators of the rank that owns the pixel's row band (one 16-byte system-scope reduction
                  per pixel: a reduce-scatter), then every rank resolves its band into rank 0's image.
-        Ordering across ranks: epoch flags in peer memory (signal after the writes, wait before the reads), frames
-        double-buffered so rank 0 can still be reading frame f while frame f+1 is written: a returned CUDA image stays
-        valid until the frame after the next one is rendered.  kernel_events = (start, end) CUDA events recorded
-        around the path kernel alone (bench.py's roofline)."""
+        Ordering across ranks: epoch flags in peer memory.  ``in_kernel=True`` (default): the whole protocol -- wait
+        for free buffers, render, publish, resolve the own band, collect on rank 0 -- runs inside ONE launch per rank
+        (``rt_path_sink.sync``); ``False``: the round-1 chain of small wait / signal / resolve launches around the
+        path kernel (kept for comparison).  Frames are double-buffered so rank 0 can still be reading frame f while
+        frame f+1 is written: a returned CUDA image stays valid until the frame after the next one is rendered,
+        PROVIDED its consumer is queued on the current stream before the next ``render_fused`` call (the "consumed"
+        signal of frame f is published by rank 0's stream at the start of frame f+1, i.e. after everything queued in
+        between; with ``to_host`` it follows the copy-out on the copy stream).  kernel_events = (start, end) CUDA
+        events recorded around the path kernel alone (bench.py's roofline)."""
         nat, sc, torch = self.nat, self.scene, self.torch
         self._ensure_fabric(W, H)
         fab, rank, world = self.fabric, self.rank, self.world
+        if mode not in ("tiles", "samples"):
+            raise ValueError("mode must be 'tiles' or 'samples'")
         self._epoch += 1
         e, buf = self._epoch, self._epoch & 1
         everyone = list(range(world))
         self.stats.zero_()
-        fab.wait("flags", 32, 1, e - 2, self._timed_out)                  # rank 0 has consumed this image buffer
         p = sc.path_params(cam, W, H, spp, max_bounces, mirror_threshold, seed=seed, fov=fov)
         sink = nat.PathSink()
+        bands = row_bands(H, world)
+        s0, s1 = sample_ranges(spp, world)[rank] if mode == "samples" else (0, spp)
         if mode == "tiles":
             sink.mode, sink.tile_first, sink.tile_step = nat.SINK_IMAGE, rank, world
-            sink.image = fab.ptrs[f"image{buf}"][0]
+        else:
+            p.s0, p.s1 = s0, s1
+            sink.mode = nat.SINK_SCATTER_ADD
+            for k in range(world):
+                sink.accum[k] = fab.ptrs[f"accum{buf}"][k]
+                sink.band_y[k] = bands[k][0]
+            sink.band_y[world] = H
+        sink.world = world
+        sink.image = fab.ptrs[f"image{buf}"][0]
+        pending_go, self._pending_go = getattr(self, "_pending_go", 0), 0
+        if in_kernel:
+            sink.sync, sink.rank, sink.epoch = 1, rank, e
+            sink.go_epoch = pending_go if rank == 0 else 0
+            for k in range(world):
+                sink.flags[k] = fab.ptrs["flags"][k]
+            sink.timed_out = self._timed_out.data_ptr()
             if kernel_events:
                 kernel_events[0].record()
-            sc.render_path_sink(p, sink, stats=self.stats)
+            sc.render_path_sink(p, sink, stats=self.stats)                     # ONE launch: the frame is complete on rank 0 when it ends
             if kernel_events:
                 kernel_events[1].record()
-            self.launches = 3 + (2 if rank == 0 else 0)
-        elif mode == "samples":
-            s0, s1 = sample_ranges(spp, world)[rank]
-            bands = row_bands(H, world)
-            if s1 > s0:
-                p.s0, p.s1 = s0, s1
-                sink.mode, sink.world = nat.SINK_SCATTER_ADD, world
-                for k in range(world):
-                    sink.accum[k] = fab.ptrs[f"accum{buf}"][k]
-                    sink.band_y[k] = bands[k][0]
-                sink.band_y[world] = H
+            self.launches = 1
+        else:
+            if rank == 0 and pending_go:
+                fab.signal("flags", 32, everyone, pending_go)                  # after whatever the caller queued on frame e - 1
+            fab.wait("flags", 32, 1, e - 2, self._timed_out)                  # rank 0 has consumed this image buffer
+            if mode == "tiles":
                 if kernel_events:
                     kernel_events[0].record()
                 sc.render_path_sink(p, sink, stats=self.stats)
                 if kernel_events:
                     kernel_events[1].record()
-            fab.signal("flags", rank, everyone, e)                         # my sums have been added everywhere
-            fab.wait("flags", 0, world, e, self._timed_out)                # everyone's sums are in my band
-            y0, y1 = bands[rank]
-            nat.check(nat.lib().rt_resolve_clear(self.device, fab.ptrs[f"accum{buf}"][rank], W, H, y0, y1, spp,
-                                                 fab.ptrs[f"image{buf}"][0], 1, None))
-            self.launches = 6 + (2 if rank == 0 else 0)     # wait, path, signal, wait, resolve, signal (+ wait, signal)
-        else:
-            raise ValueError("mode must be 'tiles' or 'samples'")
-        fab.signal("flags", 16 + rank, [0], e)                             # my part of rank 0's image is written
+                self.launches = 3 + (2 if rank == 0 else 0)
+            else:
+                if kernel_events:
+                    kernel_events[0].record()
+                if s1 > s0:
+                    sc.render_path_sink(p, sink, stats=self.stats)
+                if kernel_events:
+                    kernel_events[1].record()
+                fab.signal("flags", rank, everyone, e)                         # my sums have been added everywhere
+                fab.wait("flags", 0, world, e, self._timed_out)                # everyone's sums are in my band
+                y0, y1 = bands[rank]
+                nat.check(nat.lib().rt_resolve_clear(self.device, fab.ptrs[f"accum{buf}"][rank], W, H, y0, y1, spp,
+                                                     fab.ptrs[f"image{buf}"][0], 1, None))
+                self.launches = 6 + (2 if rank == 0 else 0)     # wait, path, signal, wait, resolve, signal (+ wait, signal)
+            fab.signal("flags", 16 + rank, [0], e)                             # my part of rank 0's image is written
+            if rank == 0:
+                fab.wait("flags", 16, world, e, self._timed_out)
         out = None
         if rank == 0:
-            fab.wait("flags", 16, world, e, self._timed_out)
             out = self._fused_images[buf]
             if to_host:
-                # the copy-out runs on the copy stream; the "buffer may be reused at e + 2" signal follows it there
+                # the copy-out runs on the copy stream; the "consumed" signal follows it there
                 pending = self._to_host(out, buf, release=lambda st: fab.signal("flags", 32, everyone, e, stream=st))
                 out = pending if to_host == "async" else pending.result()
             else:
-                fab.signal("flags", 32, everyone, e)                       # this image buffer may be reused at e + 2
+                # the caller's consumer of this CUDA image comes AFTER this call: publish "consumed" at the start of the
+                # next frame on this stream (in the kernel's own prologue), never right away
+                self._pending_go = e
         return out, self.stats
 
     def fused_timed_out(self):

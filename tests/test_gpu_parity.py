@@ -464,6 +464,61 @@ def test_fused_sinks_equal_accumulate_then_resolve(nat):
     sc.close()
 
 
+@pytest.mark.parametrize("mode", ["tiles", "samples"])
+def test_single_launch_frame_protocol(nat, mode):
+    """rt_path_sink.sync: the whole frame protocol (wait for free buffers, render, publish, resolve the own band,
+    collect on rank 0) inside ONE launch per rank.  Three "ranks" share this GPU (max_ctas keeps their persistent
+    launches co-resident, one stream each, rank 0 launched LAST); four frames through the two buffer parities, the
+    "consumed" signal of frame e - 1 published by rank 0's launch of frame e; every frame equals the unsharded one."""
+    import torch
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.distributed import row_bands, sample_ranges
+    spec = scenes.build_complex()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp, world = 384, 216, 7, 3
+    dev = torch.device("cuda", 0)
+    images = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in (0, 1)]
+    accum = [[torch.zeros((H, W, 4), dtype=torch.float32, device=dev) for _ in range(world)] for _ in (0, 1)]
+    flags = [torch.zeros(nat.FLAG_WORDS, dtype=torch.int32, device=dev) for _ in range(world)]
+    timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    bands = row_bands(H, world)
+    torch.cuda.synchronize()
+    for e in range(1, 5):
+        buf = e & 1
+        ref, _, _ = sc.render_path_host(sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=100 + e), nat.F32)
+        for rank in reversed(range(world)):
+            p = sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=100 + e)
+            sink = nat.PathSink()
+            sink.world, sink.rank, sink.sync, sink.epoch = world, rank, 1, e
+            sink.go_epoch = e - 1 if rank == 0 else 0
+            sink.image = images[buf].data_ptr()
+            sink.timed_out, sink.timeout_ms, sink.max_ctas = timed_out.data_ptr(), 4000, 148
+            for k in range(world):
+                sink.flags[k] = flags[k].data_ptr()
+            if mode == "tiles":
+                sink.mode, sink.tile_first, sink.tile_step = nat.SINK_IMAGE, rank, world
+            else:
+                sink.mode = nat.SINK_SCATTER_ADD
+                p.s0, p.s1 = sample_ranges(spp, world)[rank]
+                for k in range(world):
+                    sink.accum[k] = accum[buf][k].data_ptr()
+                    sink.band_y[k] = bands[k][0]
+                sink.band_y[world] = H
+            sc.render_path_sink(p, sink, stream=streams[rank].cuda_stream)
+        # rank 0's launch ends when the frame is complete: its stream alone orders the read-back
+        streams[0].synchronize()
+        assert int(timed_out.item()) == 0, "a flag wait timed out: the launches did not run concurrently"
+        assert np.array_equal(images[buf].cpu().numpy(), ref), f"frame {e}"
+        torch.cuda.synchronize()
+        if mode == "samples":
+            assert not any(bool(a.any()) for a in accum[buf]), "bands are cleared for the frame after next"
+    assert [int(f[32]) for f in flags] == [3] * world          # go: frames <= 3 consumed, published to every rank
+    sc.close()
+
+
 def test_sample_split_gives_the_same_frame(nat):
     """ksplit: 1..32 lanes sharing a pixel's samples (butterfly-summed) render the frame of one thread per pixel, for
     ragged sizes, row bands, sample ranges that do not divide by k, both schedules and the image sink."""

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Fused multi-GPU sinks vs the NCCL paths: same frame bit for bit, device-timed side by side.
+"""Fused multi-GPU sinks (single launch per rank and frame; the round-1 launch chain) vs the NCCL paths: same frame bit
+for bit, device-timed side by side.
 
     python tools/fused_check.py                                   # 1 GPU (peers = self)
     torchrun --nproc-per-node N --master-addr 127.0.0.1 tools/fused_check.py [--spp 64]
@@ -54,7 +55,12 @@ def main():
         if rank == 0:
             out[f"{mode}_identical"] = bool(torch.equal(ref, img))
             out[f"{mode}_maxdiff"] = float((ref - img).abs().max())
-        for name, fn in (("nccl", r.render), ("fused", r.render_fused)):
+        chain = lambda *a, **k: r.render_fused(*a, in_kernel=False, **k)      # round-1 chain of wait / signal / resolve launches
+        img2, _ = chain(spec.camera, W, H, spp, depth, thr, seed=3, mode=mode)
+        sync()
+        if rank == 0:
+            out[f"{mode}_chain_identical"] = bool(torch.equal(ref, img2))
+        for name, fn in (("nccl", r.render), ("chain", chain), ("fused", r.render_fused)):
             for i in range(2):
                 fn(spec.camera, W, H, spp, depth, thr, seed=10 + i, mode=mode)
             sync()
