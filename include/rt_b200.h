@@ -281,6 +281,9 @@ typedef struct rt_path_sink {
     int32_t timeout_ms;               /* <= 0: 20 s */
     int32_t max_ctas;                 /* 0 = as many CTAs as the device keeps resident; smaller values let several
                                          "ranks" share ONE device (tests) */
+    int32_t spp_total;                /* sync + SCATTER_ADD: samples per pixel of the whole frame (the band resolve
+                                         divides by it; p->s0/s1 is only this rank's range) */
+    int32_t reserved_;
 } rt_path_sink;
 #define RT_FLAG_WORDS 64
 /* sync = 1 -- one launch per rank and frame, no other kernel and no host round trip on the data path:
@@ -350,6 +353,17 @@ int rt_env_reset(rt_env *env, const int32_t *pixels_dev, const uint8_t *mask_dev
  * hit_sun.  stats_dev (optional) uint64[8]: [0] nearest-hit/occlusion queries. */
 int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev, double *reward_dev, uint8_t *terminated_dev,
                 uint8_t *truncated_dev, int32_t *reason_dev, double *info_dev, uint64_t *stats_dev, void *stream);
+/* step() with the restart of finished episodes IN THE SAME LAUNCH (the VecEnv protocol of Stable-Baselines3, which the
+ * reference trains through: RL/train_raytracer.py:128-147): an env whose episode ends in this step gets its last
+ * observation written to final_obs_dev (optional, [B,18] float32, rows of finished envs only) and is reset at once --
+ * start pixel = Philox(env index, episode number) under `seed`, written to pixels_out_dev (optional, [B,2]) -- so
+ * obs_dev holds the FIRST observation of the new episode while reward / terminated / truncated / reason / info
+ * describe the step that ended the old one.  reward_dev [B] and info_dev (optional) [B,4] are float for an RT_F32 env
+ * and double for an RT_F64 env.  One launch per step, no host round trip, graph-capturable (nothing in the parameter
+ * block changes from step to step). */
+int rt_env_step_auto(rt_env *env, const float *actions_dev, float *obs_dev, void *reward_dev, uint8_t *terminated_dev,
+                     uint8_t *truncated_dev, int32_t *reason_dev, void *info_dev, float *final_obs_dev,
+                     int32_t *pixels_out_dev, uint64_t seed, uint64_t *stats_dev, void *stream);
 
 #ifdef __cplusplus
 }

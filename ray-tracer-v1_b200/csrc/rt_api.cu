@@ -634,6 +634,10 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             }
             pp.sync = 1; pp.rank = sink->rank; pp.world = sink->world; pp.epoch = sink->epoch; pp.go_epoch = sink->go_epoch;
             pp.image = sink->image;
+            if (sink->mode == RT_SINK_SCATTER_ADD) {
+                if (sink->spp_total < p->s1) return fail(RT_ERR_INVALID, "spp_total must cover the sample range");
+                pp.spp_total = sink->spp_total;
+            }
             pp.timed_out = sink->timed_out;
             static int khz_cache[64] = {0};
             int khz = sc->device >= 0 && sc->device < 64 ? khz_cache[sc->device] : 0;
@@ -1109,10 +1113,29 @@ RT_EXPORT int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev,
     CU(cudaSetDevice(env->scene->device));
     unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
     if (env->precision == RT_F64)
-        CU(launch_env_step<double>(env->scene->d.view, env->d, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev,
-                                   reason_dev, info_dev, st, S(stream)));
+        CU((launch_env_step<double, double, false>(env->scene->d.view, env->d, actions_dev, obs_dev, reward_dev, terminated_dev,
+                                                   truncated_dev, reason_dev, info_dev, nullptr, nullptr, 0, st, S(stream))));
     else
-        CU(launch_env_step<float>(env->scene->f.view, env->f, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev,
-                                  reason_dev, info_dev, st, S(stream)));
+        CU((launch_env_step<float, double, false>(env->scene->f.view, env->f, actions_dev, obs_dev, reward_dev, terminated_dev,
+                                                  truncated_dev, reason_dev, info_dev, nullptr, nullptr, 0, st, S(stream))));
+    return RT_OK;
+}
+
+RT_EXPORT int rt_env_step_auto(rt_env *env, const float *actions_dev, float *obs_dev, void *reward_dev, uint8_t *terminated_dev,
+                               uint8_t *truncated_dev, int32_t *reason_dev, void *info_dev, float *final_obs_dev,
+                               int32_t *pixels_out_dev, uint64_t seed, uint64_t *stats_dev, void *stream) {
+    if (!env || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev || !reason_dev)
+        return fail(RT_ERR_INVALID, "NULL argument");
+    if (((uintptr_t)final_obs_dev) & 7u) return fail(RT_ERR_INVALID, "final_obs must be 8-byte aligned");
+    CU(cudaSetDevice(env->scene->device));
+    unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
+    if (env->precision == RT_F64)
+        CU((launch_env_step<double, double, true>(env->scene->d.view, env->d, actions_dev, obs_dev, (double *)reward_dev,
+                                                  terminated_dev, truncated_dev, reason_dev, (double *)info_dev, final_obs_dev,
+                                                  pixels_out_dev, seed, st, S(stream))));
+    else
+        CU((launch_env_step<float, float, true>(env->scene->f.view, env->f, actions_dev, obs_dev, (float *)reward_dev,
+                                                terminated_dev, truncated_dev, reason_dev, (float *)info_dev, final_obs_dev,
+                                                pixels_out_dev, seed, st, S(stream))));
     return RT_OK;
 }

@@ -943,10 +943,10 @@ template <typename T> RT_DEV void env_store_hit(const EnvDev<T> &e, int b, const
     e.d[b] = D.x; e.d[B + b] = D.y; e.d[2 * B + b] = D.z;
 }
 
-// _get_observation (RL/ray_tracer_env.py:184-222): 18 x float32
-template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, int b, float *obs) {
+// _get_observation (RL/ray_tracer_env.py:184-222): 18 x float32 into the row `o` (a shared-memory staging row: the
+// CTA writes its rows out together, coalesced, see env_flush_obs)
+template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, int b, float *o) {
     const size_t B = (size_t)e.B;
-    float *o = obs + 18 * (size_t)b;
     if (!e.has_hit[b]) {
 #pragma unroll
         for (int k = 0; k < 18; ++k) o[k] = 0.f;
@@ -1022,6 +1022,41 @@ template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const E
     return shadow ? 0.3 : 0.3 + 0.7 * (double)ca;
 }
 
+// Observation rows of a CTA: every thread builds its 18 floats in shared memory (stride 18: two-way bank conflicts on
+// 18 stores), then the CTA copies the block of rows to HBM as consecutive 16-byte stores -- the per-thread rows would
+// be 72-byte strided 4-byte stores, 18 partial sectors per warp instruction.
+#define RT_ENV_BLOCK 128
+RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
+    __syncthreads();
+    const int base = blockIdx.x * RT_ENV_BLOCK;
+    const int n = min(RT_ENV_BLOCK, B - base) * 18;                      // floats of this CTA's rows
+    float *dst = obs + (size_t)base * 18;                                // 128 * 72 bytes per CTA: 16-byte aligned
+    const int n4 = (((uintptr_t)obs & 15u) == 0) ? n >> 2 : 0;
+    for (int j = threadIdx.x; j < n4; j += RT_ENV_BLOCK)
+        reinterpret_cast<float4 *>(dst)[j] = reinterpret_cast<const float4 *>(rows)[j];
+    for (int j = 4 * n4 + threadIdx.x; j < n; j += RT_ENV_BLOCK) dst[j] = rows[j];
+}
+
+// reset of one episode (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142): camera ray through pixel (px, py),
+// first nearestSphereIntersect, zeroed counters.  Shared by env_reset_kernel and the auto-reset of env_step_kernel.
+template <typename T, bool kBvh>
+RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int px, int py, Counters &ct) {
+    const size_t B = (size_t)e.B;
+    if (e.episode) e.episode[b] += 1;
+    const T aspect = T(e.W) / T(e.H);
+    const T x = (T(2) * (T(px) + T(0.5)) / T(e.W) - T(1)) * aspect * e.tan_half;
+    const T y = (T(1) - T(2) * (T(py) + T(0.5)) / T(e.H)) * e.tan_half;
+    V3<T> d = normalise(mk<T>(x, y, T(-1)));
+    if (e.cam_angle[0] != T(0) || e.cam_angle[1] != T(0) || e.cam_angle[2] != T(0))
+        d = rotate<T>(d, mk<T>(e.cam_angle[0], e.cam_angle[1], e.cam_angle[2]));
+    d = normalise(d);
+    Hit<T> h = trace_terminal<T, kBvh>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
+    env_store_hit<T>(e, b, h, d);
+    e.bounce[b] = 0; e.through[b] = 0; e.consec[b] = 0;
+    e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
+    e.total[b] = 0.0;
+}
+
 // reset (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142).  pixels == NULL: draw with Philox(seed) keyed by
 // the env index.  mask != NULL: only envs with mask[b] != 0 are reset.
 template <typename T, int kMode>
@@ -1035,7 +1070,6 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     Counters ct = {0u, 0u, 0u};
     if (b < e.B && (!mask || mask[b])) {
-        const size_t B = (size_t)e.B;
         int px, py;
         if (pixels) { px = pixels[2 * b]; py = pixels[2 * b + 1]; }
         else {
@@ -1043,35 +1077,31 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
             px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
             py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
         }
-        if (e.episode) e.episode[b] += 1;
         if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
-        const T aspect = T(e.W) / T(e.H);
-        const T x = (T(2) * (T(px) + T(0.5)) / T(e.W) - T(1)) * aspect * e.tan_half;
-        const T y = (T(1) - T(2) * (T(py) + T(0.5)) / T(e.H)) * e.tan_half;
-        V3<T> d = normalise(mk<T>(x, y, T(-1)));
-        if (e.cam_angle[0] != T(0) || e.cam_angle[1] != T(0) || e.cam_angle[2] != T(0))
-            d = rotate<T>(d, mk<T>(e.cam_angle[0], e.cam_angle[1], e.cam_angle[2]));
-        d = normalise(d);
-        Hit<T> h = trace_terminal<T, kBvh>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
-        env_store_hit<T>(e, b, h, d);
-        e.bounce[b] = 0; e.through[b] = 0; e.consec[b] = 0;
-        e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
-        e.total[b] = 0.0;
-        env_obs<T>(S.g, e, b, obs);
+        env_begin_episode<T, kBvh>(S, e, b, px, py, ct);
+        env_obs<T>(S.g, e, b, obs + 18 * (size_t)b);
     }
     if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
 }
 
 // step (RL/ray_tracer_env.py:295-401, FB/ray_tracer_env.py:378-514)
-template <typename T, int kMode>
-__global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
-                                                       double *reward, uint8_t *terminated, uint8_t *truncated,
-                                                       int *reason, double *info, unsigned long long *stats) {
+// R = type of the reward / info outputs (double: rt_env_step; the env's own precision: rt_env_step_auto).
+// kAuto: an episode that ends in this step is restarted IN THE SAME LAUNCH (SB3 VecEnv semantics): its last observation
+// goes to final_obs (optional), the observation returned is the first one of the new episode, whose start pixel is
+// Philox(env, episode number) under the key (k0, k1) -- no host round trip and no second launch per step, and the
+// lanes of finished episodes go straight back to work.
+template <typename T, int kMode, typename R, bool kAuto>
+__global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
+                                                                R *reward, uint8_t *terminated, uint8_t *truncated,
+                                                                int *reason, R *info, float *final_obs, int *pixels_out,
+                                                                uint32_t k0, uint32_t k1, unsigned long long *stats) {
     RT_MODE_DECL;
     extern __shared__ __align__(32) unsigned char smem[];
+    __shared__ __align__(16) float s_rows[RT_ENV_BLOCK * 18];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    float *row = s_rows + 18 * threadIdx.x;
     Counters ct = {0u, 0u, 0u};
     if (b < e.B) {
         const size_t B = (size_t)e.B;
@@ -1127,13 +1157,29 @@ __global__ void __launch_bounds__(256) env_step_kernel(SceneDev<T> sc, EnvDev<T>
                 else if (bc >= e.max_bounces) { term = 1; trunc = 1; rsn = 3; }
             } else if (!term && bc >= e.max_bounces) { term = 1; trunc = 1; rsn = 3; }
         }
-        reward[b] = rw; terminated[b] = (uint8_t)term; truncated[b] = (uint8_t)trunc; reason[b] = rsn;
+        reward[b] = (R)rw; terminated[b] = (uint8_t)term; truncated[b] = (uint8_t)trunc; reason[b] = rsn;
         if (info) {
-            double *q = info + 4 * (size_t)b;
-            q[0] = (double)info_bounce; q[1] = (double)through; q[2] = info_total; q[3] = info_sun;
+            R *q = info + 4 * (size_t)b;
+            q[0] = (R)info_bounce; q[1] = (R)through; q[2] = (R)info_total; q[3] = (R)info_sun;
         }
-        env_obs<T>(S.g, e, b, obs);
+        env_obs<T>(S.g, e, b, row);
+        if constexpr (kAuto) {
+            if (term | trunc) {
+                if (final_obs) {                         // 72-byte rows: nine 8-byte stores
+                    float2 *fo = reinterpret_cast<float2 *>(final_obs + 18 * (size_t)b);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) fo[k] = make_float2(row[2 * k], row[2 * k + 1]);
+                }
+                const Philox4 o = philox4x32_10((uint32_t)b, (uint32_t)e.episode[b], 1u, 0x52544556u /* "RTEV" */, k0, k1);
+                const int px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
+                const int py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
+                if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
+                env_begin_episode<T, kBvh>(S, e, b, px, py, ct);
+                env_obs<T>(S.g, e, b, row);
+            }
+        }
     }
+    env_flush_obs(s_rows, obs, e.B);
     if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
 }
 
@@ -1331,15 +1377,25 @@ cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const in
     return cudaGetLastError();
 }
 
-template <typename T>
-cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, double *reward,
-                            uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
-                            unsigned long long *stats, cudaStream_t st) {
+// kAuto = false: plain step (rt_env_step); true: step + in-launch restart of finished episodes (rt_env_step_auto)
+template <typename T, typename R, bool kAuto>
+cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, R *reward,
+                            uint8_t *terminated, uint8_t *truncated, int *reason, R *info, float *final_obs, int *pixels_out,
+                            uint64_t seed, unsigned long long *stats, cudaStream_t st) {
     if (e.B <= 0) return cudaSuccess;
-    const int block = 128, grid = (e.B + block - 1) / block;
-    const int mode = mode_for(sc);
-    RT_DISPATCH_MODE(mode, env_step_kernel, grid, block, smem_for(sc), st, sc, e, actions, obs, reward, terminated,
-                     truncated, reason, info, stats);
+    const int block = RT_ENV_BLOCK, grid = (e.B + block - 1) / block;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    const size_t rows = RT_ENV_BLOCK * 18 * sizeof(float);                 // static shared rows on top of the staged scene
+    const int mode = mode_for(sc, rows);
+    const size_t sm = mode != 2 ? smem_for(sc) : 0;
+    cudaError_t e__ = cudaSuccess;
+    switch (mode) {
+        case 0: e__ = allow_smem(env_step_kernel<T, 0, R, kAuto>, sm); if (e__ != cudaSuccess) return e__;
+                env_step_kernel<T, 0, R, kAuto><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
+        case 1: e__ = allow_smem(env_step_kernel<T, 1, R, kAuto>, sm); if (e__ != cudaSuccess) return e__;
+                env_step_kernel<T, 1, R, kAuto><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
+        default: env_step_kernel<T, 2, R, kAuto><<<grid, block, 0, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
+    }
     return cudaGetLastError();
 }
 
@@ -1360,7 +1416,9 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_shade_hits<T>(const SceneDev<T> &, int, const double *, int, double *, cudaStream_t);    \
     template cudaError_t launch_env_reset<T>(const SceneDev<T> &, const EnvDev<T> &, const int *, const uint8_t *,      \
                                              uint64_t, float *, int *, unsigned long long *, cudaStream_t);             \
-    template cudaError_t launch_env_step<T>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, double *,   \
-                                            uint8_t *, uint8_t *, int *, double *, unsigned long long *, cudaStream_t);
+    template cudaError_t launch_env_step<T, double, false>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, double *, \
+                                            uint8_t *, uint8_t *, int *, double *, float *, int *, uint64_t, unsigned long long *, cudaStream_t); \
+    template cudaError_t launch_env_step<T, T, true>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, T *,   \
+                                            uint8_t *, uint8_t *, int *, T *, float *, int *, uint64_t, unsigned long long *, cudaStream_t);
 
 }  // namespace rt

@@ -110,10 +110,10 @@ cudaError_t launch_shade_hits(const SceneDev<T> &sc, int m, const double *hits, 
 template <typename T>
 cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
                              uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st);
-template <typename T>
-cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, double *reward,
-                            uint8_t *terminated, uint8_t *truncated, int *reason, double *info,
-                            unsigned long long *stats, cudaStream_t st);
+template <typename T, typename R, bool kAuto>
+cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, R *reward,
+                            uint8_t *terminated, uint8_t *truncated, int *reason, R *info, float *final_obs, int *pixels_out,
+                            uint64_t seed, unsigned long long *stats, cudaStream_t st);
 
 template <typename T>
 cudaError_t launch_wf_begin(const WaveDev<T> &w, const PathDev<T> &pp, unsigned long long *stats, cudaStream_t st);

@@ -378,7 +378,7 @@ class ShardedPathRenderer:
         sink.image = fab.ptrs[f"image{buf}"][0]
         pending_go, self._pending_go = getattr(self, "_pending_go", 0), 0
         if in_kernel:
-            sink.sync, sink.rank, sink.epoch = 1, rank, e
+            sink.sync, sink.rank, sink.epoch, sink.spp_total = 1, rank, e, spp
             sink.go_epoch = pending_go if rank == 0 else 0
             for k in range(world):
                 sink.flags[k] = fab.ptrs["flags"][k]

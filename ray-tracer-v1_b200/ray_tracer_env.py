@@ -158,6 +158,7 @@ class BatchedRayTracerEnv:
         if self.handle is not None and desc_key != self._desc_key:
             nat.load_symbols().rt_env_destroy(self.handle)
             self.handle = None
+            self._graph = None                         # a captured step launch holds the old handle's pointers
         if self.handle is None:
             d = nat.EnvDesc()
             d.B, d.W, d.H = self.n_envs, int(self.image_width), int(self.image_height)
@@ -221,7 +222,61 @@ class BatchedRayTracerEnv:
             nat.check(rc)
         return self.obs, self.reward, self._flags[0], self._flags[1], dict(self._info)
 
+    # ---- one launch per step: step + restart of finished episodes ------------------------------------------------
+    def _auto_buffers(self):
+        torch = self.torch
+        if getattr(self, "_auto", None) is None:
+            dev, B = self.obs.device, self.n_envs
+            ft = torch.float64 if self.precision == nat.F64 else torch.float32
+            self.actions = torch.zeros((B, 2), dtype=torch.float32, device=dev)       # static: a policy may write it in place
+            self.reward_auto = torch.zeros(B, dtype=ft, device=dev)
+            self.info_auto = torch.zeros((B, 4), dtype=ft, device=dev)
+            self.final_obs = torch.zeros((B, OBS_DIM), dtype=torch.float32, device=dev)
+            self._auto = True
+            self._auto_info = {"bounce_count": self.info_auto[:, 0], "through_count": self.info_auto[:, 1],
+                               "total_reward": self.info_auto[:, 2], "hit_sun": self.info_auto[:, 3], "reason": self.reason,
+                               "terminal_observation": self.final_obs, "pixels": self.pixels}
+            self._auto_flags = (self.terminated.view(torch.bool), self.truncated.view(torch.bool))
+            self._graph = None
+
+    def _launch_auto(self, stream=None):
+        rc = nat.lib().rt_env_step_auto(self.handle, self.actions.data_ptr(), self.obs.data_ptr(), self.reward_auto.data_ptr(),
+                                        self.terminated.data_ptr(), self.truncated.data_ptr(), self.reason.data_ptr(),
+                                        self.info_auto.data_ptr(), self.final_obs.data_ptr(), self.pixels.data_ptr(),
+                                        self.seed & (2 ** 64 - 1), self.stats.data_ptr(), stream)
+        if rc:
+            nat.check(rc)
+
+    def step_auto(self, actions=None, graph=False):
+        """One step of every episode AND the restart of the finished ones in ONE kernel launch (``rt_env_step_auto``: the
+        VecEnv protocol of Stable-Baselines3).  -> (obs, reward, terminated, truncated, info): ``obs`` [B,18] holds the
+        first observation of the new episode where an episode ended (its last one is in
+        ``info['terminal_observation']``), reward is float32 for the FP32 env.  ``actions=None`` steps on
+        ``self.actions`` as it stands (a policy network can write its output there in place).  ``graph=True`` replays
+        the launch from a CUDA graph captured at the first call (nothing in the launch changes from step to step: new
+        start pixels are keyed by the per-env episode counter on the device)."""
+        torch = self.torch
+        if self.handle is None:
+            raise RuntimeError("reset() first")
+        self._auto_buffers()
+        if actions is not None:
+            if not (isinstance(actions, torch.Tensor) and actions.data_ptr() == self.actions.data_ptr()):
+                self.actions.copy_(self._dev_tensor(actions, torch.float32, (self.n_envs, 2)))
+        if graph:
+            if self._graph is None:
+                side = torch.cuda.Stream(device=self.obs.device)
+                side.wait_stream(torch.cuda.current_stream(self.obs.device))
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    self._launch_auto(torch.cuda.current_stream(self.obs.device).cuda_stream)
+                self._graph = g
+            self._graph.replay()
+        else:
+            self._launch_auto(None)
+        return self.obs, self.reward_auto, self._auto_flags[0], self._auto_flags[1], self._auto_info
+
     def close(self):
+        self._graph = None
         if self.handle is not None:
             try:
                 nat.load_symbols().rt_env_destroy(self.handle)
@@ -445,34 +500,32 @@ class RayTracerVecEnv(_VecEnvBase):
     def step_wait(self):
         import time
         torch = self.env.torch
-        obs, rew, term, trunc, binfo = self.env.step(self._actions)
+        # ONE launch: the step and the restart of the finished episodes (their new first observation comes back in obs,
+        # the last one of the old episode in info['terminal_observation'])
+        obs, rew, term, trunc, binfo = self.env.step_auto(self._actions)
         dones = term | trunc
-        rew = rew.clone()
-        last_obs = obs.clone()
         # SB3's DummyVecEnv sets TimeLimit.truncated = truncated and not terminated; the reference env returns
         # terminated = truncated = True at max_bounces (RL/ray_tracer_env.py:384-392), so the flag is False there and
         # SB3 does not bootstrap the value at those ends -- exactly as when it trains on the reference env
-        time_limit = (trunc & ~term).clone()
-        reason = binfo["reason"].clone()
-        total = binfo["total_reward"].clone()
+        time_limit = trunc & ~term
         self._ep_len += 1
         ep_len = self._ep_len.clone()
-        if bool(dones.any()):
-            obs, _ = self.env.reset(mask=dones.to(torch.uint8))            # only the finished episodes restart
-            self._ep_len.masked_fill_(dones, 0)
+        self._ep_len.masked_fill_(dones, 0)
         if self.as_torch:
-            infos = {"terminal_observation": last_obs, "TimeLimit.truncated": time_limit, "reason": reason,
-                     "total_reward": total, "done": dones, "episode_length": ep_len}
-            return obs.clone(), rew.to(torch.float32), dones, infos
+            infos = {"terminal_observation": binfo["terminal_observation"].clone(), "TimeLimit.truncated": time_limit,
+                     "reason": binfo["reason"].clone(), "total_reward": binfo["total_reward"].clone(), "done": dones.clone(),
+                     "episode_length": ep_len}
+            return obs.clone(), rew.to(torch.float32).clone(), dones.clone(), infos
         d = dones.cpu().numpy()
-        lo, tn, rs, tt, ln = (last_obs.cpu().numpy(), time_limit.cpu().numpy(), reason.cpu().numpy(), total.cpu().numpy(),
-                              ep_len.cpu().numpy())
         infos = [{} for _ in range(self.num_envs)]
-        elapsed = round(time.time() - self._t0, 6)
-        for i in np.nonzero(d)[0]:
-            # 'episode' carries what SB3's Monitor writes and its logger reads: return, length, elapsed seconds
-            infos[i] = {"terminal_observation": lo[i].copy(), "TimeLimit.truncated": bool(tn[i]),
-                        "reason": nat.REASONS[int(rs[i])], "episode": {"r": float(tt[i]), "l": int(ln[i]), "t": elapsed}}
+        if d.any():
+            lo, tn, rs, tt, ln = (binfo["terminal_observation"].cpu().numpy(), time_limit.cpu().numpy(),
+                                  binfo["reason"].cpu().numpy(), binfo["total_reward"].cpu().numpy(), ep_len.cpu().numpy())
+            elapsed = round(time.time() - self._t0, 6)
+            for i in np.nonzero(d)[0]:
+                # 'episode' carries what SB3's Monitor writes and its logger reads: return, length, elapsed seconds
+                infos[i] = {"terminal_observation": lo[i].copy(), "TimeLimit.truncated": bool(tn[i]),
+                            "reason": nat.REASONS[int(rs[i])], "episode": {"r": float(tt[i]), "l": int(ln[i]), "t": elapsed}}
         return obs.cpu().numpy().copy(), rew.cpu().numpy().astype(np.float32), d, infos
 
     def step(self, actions):

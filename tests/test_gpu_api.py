@@ -314,3 +314,53 @@ def test_env_descriptor_is_reread_on_reset(rt):
     with pytest.raises(ValueError):
         BatchedRayTracerEnv(spec.spheres, 4, precision="float16")
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("precision,flavour", [("f64", "rl"), ("f32", "rl"), ("f32", "fb")])
+def test_step_auto_equals_step_plus_masked_reset(rt, precision, flavour):
+    """rt_env_step_auto (step + restart of finished episodes in ONE launch) against the two-launch protocol it replaces:
+    rt_env_step, then rt_env_reset(mask = done, pixels = the ones the fused launch drew).  Same observations, rewards,
+    flags, reasons and terminal observations, step after step; replayed from a CUDA graph it gives the same again."""
+    import torch
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    from ray_tracer_v1_b200.ray_tracer_env import BatchedRayTracerEnv
+    if flavour == "fb":
+        spec = scenes.build_balls_in_space(as_rendered=False)
+        fs = flatten_scene(spec.spheres, spec.global_lights, [], spec.background)
+        kw = dict(image_width=320, image_height=240, camera_position=(0, 0, 1), fov=60, max_bounces=5, flavour="fb")
+        lo, hi = (-1.0, -1.0), (1.0, 1.0)
+    else:
+        spec = scenes.build_optimized_env_scene()
+        fs = flatten_scene(spec.spheres, spec.global_lights, spec.point_lights, spec.background)
+        kw = dict(image_width=320, image_height=240, camera_position=(0, 0, 0), fov=80, max_bounces=6, flavour="rl")
+        lo, hi = (0.0, 0.0), (np.pi / 2, 2 * np.pi)
+    B, T = 5000, 14                                  # not a multiple of the CTA size: ragged last block of rows
+    rs = np.random.RandomState(2)
+    acts = rs.uniform(lo, hi, (T, B, 2)).astype(np.float32)
+    fused = BatchedRayTracerEnv(fs, B, precision=precision, seed=9, **kw)
+    graph = BatchedRayTracerEnv(fs, B, precision=precision, seed=9, **kw)
+    plain = BatchedRayTracerEnv(fs, B, precision=precision, seed=9, **kw)
+    o0 = fused.reset(seed=9)[0].clone()
+    graph.reset(seed=9)
+    plain.reset(options={"pixels": fused.pixels.clone()})
+    assert torch.equal(o0, plain.obs) and torch.equal(o0, graph.obs)
+    finished = 0
+    for t in range(T):
+        obs, rew, term, trunc, info = fused.step_auto(acts[t])
+        og, rg, tg, ug, ig = graph.step_auto(acts[t], graph=True)
+        assert torch.equal(obs, og) and torch.equal(rew, rg) and torch.equal(term, tg) and torch.equal(info["reason"], ig["reason"])
+        po, pr, pt, pu, pi = plain.step(acts[t])
+        done = pt | pu
+        assert torch.equal(term, pt) and torch.equal(trunc, pu) and torch.equal(info["reason"], pi["reason"])
+        if precision == "f64":
+            assert torch.equal(rew, pr)
+        else:
+            assert rew.dtype == torch.float32 and torch.equal(rew, pr.to(torch.float32))
+        assert torch.equal(info["terminal_observation"][done], po[done])          # last observation of the old episode
+        assert torch.allclose(info["total_reward"].double(), pi["total_reward"], rtol=1e-6, atol=1e-6)
+        if bool(done.any()):
+            plain.reset(mask=done.to(torch.uint8), options={"pixels": info["pixels"].clone()})
+        assert torch.equal(obs, plain.obs), f"step {t}"
+        finished += int(done.sum())
+    assert finished > B                              # every env restarted at least once inside the fused launches
+    fused.close(); graph.close(); plain.close()

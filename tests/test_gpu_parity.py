@@ -492,7 +492,7 @@ def test_single_launch_frame_protocol(nat, mode):
         for rank in reversed(range(world)):
             p = sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=100 + e)
             sink = nat.PathSink()
-            sink.world, sink.rank, sink.sync, sink.epoch = world, rank, 1, e
+            sink.world, sink.rank, sink.sync, sink.epoch, sink.spp_total = world, rank, 1, e, spp
             sink.go_epoch = e - 1 if rank == 0 else 0
             sink.image = images[buf].data_ptr()
             sink.timed_out, sink.timeout_ms, sink.max_ctas = timed_out.data_ptr(), 4000, 148
