@@ -340,6 +340,9 @@ typedef struct rt_env_desc {
     int32_t reward_mode;    /* RL flavour: 0 = RayTracerEnv._calculate_reward, 1 = AdaptiveRewardRayTracerEnv
                                (RL/train_raytracer_optimized.py:25-61: light / mirror bonuses, short-path penalty) */
     int32_t light_ids[2];   /* reward_mode 1: self.light_ids = [99, 100] (:21) */
+    int32_t env_offset;     /* env-sharded rollouts: global index of this batch's first env.  Device-drawn start pixels
+                               are keyed by the GLOBAL env index, so a shard equals the same rows of the unsharded batch */
+    int32_t reserved_;
 } rt_env_desc;
 int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out);
 int rt_env_destroy(rt_env *env);

@@ -86,7 +86,8 @@ FLAG_WORDS = 64
 class EnvDesc(C.Structure):
     _fields_ = [("B", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("cam", C.c_double * 3),
                 ("cam_angle", C.c_double * 3), ("fov", C.c_double), ("max_bounces", C.c_int32),
-                ("flavour", C.c_int32), ("sun_id", C.c_int32), ("reward_mode", C.c_int32), ("light_ids", C.c_int32 * 2)]
+                ("flavour", C.c_int32), ("sun_id", C.c_int32), ("reward_mode", C.c_int32), ("light_ids", C.c_int32 * 2),
+                ("env_offset", C.c_int32), ("reserved_", C.c_int32)]
 
 
 # every symbol include/rt_b200.h declares: name -> (restype, argtypes)

@@ -1063,6 +1063,7 @@ template <typename T> static void bind_env(EnvDev<T> &e, const rt_env_desc &d, v
     e.consec = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.total_hits = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.adaptive = d.reward_mode == 1; e.light0 = d.light_ids[0]; e.light1 = d.light_ids[1];
+    e.b0 = d.env_offset;
 }
 
 RT_EXPORT int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *desc, rt_env **out) {

@@ -927,38 +927,62 @@ __global__ void __launch_bounds__(256) shade_hits_kernel(SceneDev<T> sc, int m, 
 }
 
 // ------------------------------------------------------------------ batched RayTracerEnv
-template <typename T> RT_DEV void env_load_hit(const EnvDev<T> &e, int b, Hit<T> &h) {
+// One episode's state in registers: loaded once at the top of a step (all loads in flight together), updated in place,
+// stored once at the end; the observation is built from the registers, never re-read from HBM.
+template <typename T> struct EnvReg {
+    int idx;                      // scene index of current_intersection, -1 = None
+    int bounce, through;
+    V3<T> p, n, d;
+    T acc[3];
+    double total;
+    RT_DEV Hit<T> hit() const {
+        Hit<T> h;
+        h.idx = idx; h.p = p; h.n = n; h.t = T(0); h.bounces = 0; h.through = 0;
+        return h;
+    }
+    RT_DEV void set_hit(const Hit<T> &h, V3<T> D) { idx = h.idx; p = h.p; n = h.n; d = D; }
+};
+
+template <typename T> RT_DEV EnvReg<T> env_load(const EnvDev<T> &e, int b) {
     const size_t B = (size_t)e.B;
-    h.idx = e.has_hit[b] ? e.idx[b] : -1;
-    h.p = mk<T>(e.p[b], e.p[B + b], e.p[2 * B + b]);
-    h.n = mk<T>(e.n[b], e.n[B + b], e.n[2 * B + b]);
-    h.t = T(0); h.bounces = 0; h.through = 0;
+    EnvReg<T> s;
+    const int has = e.has_hit[b], idx = e.idx[b];
+    s.bounce = e.bounce[b]; s.through = e.through[b];
+    s.p = mk<T>(e.p[b], e.p[B + b], e.p[2 * B + b]);
+    s.n = mk<T>(e.n[b], e.n[B + b], e.n[2 * B + b]);
+    s.d = mk<T>(e.d[b], e.d[B + b], e.d[2 * B + b]);
+    s.acc[0] = e.acc[b]; s.acc[1] = e.acc[B + b]; s.acc[2] = e.acc[2 * B + b];
+    s.total = e.total[b];
+    s.idx = has ? idx : -1;
+    return s;
 }
 
-template <typename T> RT_DEV void env_store_hit(const EnvDev<T> &e, int b, const Hit<T> &h, V3<T> D) {
+template <typename T> RT_DEV void env_store(const EnvDev<T> &e, int b, const EnvReg<T> &s) {
     const size_t B = (size_t)e.B;
-    e.has_hit[b] = h.idx >= 0; e.idx[b] = h.idx;
-    e.p[b] = h.p.x; e.p[B + b] = h.p.y; e.p[2 * B + b] = h.p.z;
-    e.n[b] = h.n.x; e.n[B + b] = h.n.y; e.n[2 * B + b] = h.n.z;
-    e.d[b] = D.x; e.d[B + b] = D.y; e.d[2 * B + b] = D.z;
+    e.has_hit[b] = s.idx >= 0; e.idx[b] = s.idx;
+    e.bounce[b] = s.bounce; e.through[b] = s.through;
+    e.p[b] = s.p.x; e.p[B + b] = s.p.y; e.p[2 * B + b] = s.p.z;
+    e.n[b] = s.n.x; e.n[B + b] = s.n.y; e.n[2 * B + b] = s.n.z;
+    e.d[b] = s.d.x; e.d[B + b] = s.d.y; e.d[2 * B + b] = s.d.z;
+    e.acc[b] = s.acc[0]; e.acc[B + b] = s.acc[1]; e.acc[2 * B + b] = s.acc[2];
+    e.total[b] = s.total;
 }
 
 // _get_observation (RL/ray_tracer_env.py:184-222): 18 x float32 into the row `o` (a shared-memory staging row: the
 // CTA writes its rows out together, coalesced, see env_flush_obs)
-template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvDev<T> &e, int b, float *o) {
-    const size_t B = (size_t)e.B;
-    if (!e.has_hit[b]) {
+template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvReg<T> &s, float *o) {
+    if (s.idx < 0) {
 #pragma unroll
         for (int k = 0; k < 18; ++k) o[k] = 0.f;
         return;
     }
-    const typename M<T>::v4 m = g.sv.mat[e.idx[b]];
-    o[0] = (float)e.p[b]; o[1] = (float)e.p[B + b]; o[2] = (float)e.p[2 * B + b];
-    o[3] = (float)e.d[b]; o[4] = (float)e.d[B + b]; o[5] = (float)e.d[2 * B + b];
-    o[6] = (float)e.n[b]; o[7] = (float)e.n[B + b]; o[8] = (float)e.n[2 * B + b];
+    const typename M<T>::v4 m = g.sv.mat[s.idx];
+    o[0] = (float)s.p.x; o[1] = (float)s.p.y; o[2] = (float)s.p.z;
+    o[3] = (float)s.d.x; o[4] = (float)s.d.y; o[5] = (float)s.d.z;
+    o[6] = (float)s.n.x; o[7] = (float)s.n.y; o[8] = (float)s.n.z;
     o[9] = (float)m.x; o[10] = (float)m.y; o[11] = (float)m.z; o[12] = (float)m.w;
-    o[13] = (float)(e.acc[b] / T(255)); o[14] = (float)(e.acc[B + b] / T(255)); o[15] = (float)(e.acc[2 * B + b] / T(255));
-    o[16] = (float)e.bounce[b]; o[17] = (float)e.through[b];
+    o[13] = (float)(s.acc[0] / T(255)); o[14] = (float)(s.acc[1] / T(255)); o[15] = (float)(s.acc[2] / T(255));
+    o[16] = (float)s.bounce; o[17] = (float)s.through;
 }
 
 // RL _calculate_reward (RL/ray_tracer_env.py:224-252); FB _calculate_reward (FB/ray_tracer_env.py:241-278)
@@ -1025,7 +1049,9 @@ template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const E
 // Observation rows of a CTA: every thread builds its 18 floats in shared memory (stride 18: two-way bank conflicts on
 // 18 stores), then the CTA copies the block of rows to HBM as consecutive 16-byte stores -- the per-thread rows would
 // be 72-byte strided 4-byte stores, 18 partial sectors per warp instruction.
-#define RT_ENV_BLOCK 128
+#ifndef RT_ENV_BLOCK
+#define RT_ENV_BLOCK 64         /* 65,536 envs = 1,024 CTAs = 6.9 per SM: 1 % imbalance (128: 3.46 per SM, 15 %) */
+#endif
 RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
     __syncthreads();
     const int base = blockIdx.x * RT_ENV_BLOCK;
@@ -1040,8 +1066,7 @@ RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
 // reset of one episode (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142): camera ray through pixel (px, py),
 // first nearestSphereIntersect, zeroed counters.  Shared by env_reset_kernel and the auto-reset of env_step_kernel.
 template <typename T, bool kBvh>
-RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int px, int py, Counters &ct) {
-    const size_t B = (size_t)e.B;
+RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int px, int py, EnvReg<T> &st, Counters &ct) {
     if (e.episode) e.episode[b] += 1;
     const T aspect = T(e.W) / T(e.H);
     const T x = (T(2) * (T(px) + T(0.5)) / T(e.W) - T(1)) * aspect * e.tan_half;
@@ -1051,10 +1076,11 @@ RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int
         d = rotate<T>(d, mk<T>(e.cam_angle[0], e.cam_angle[1], e.cam_angle[2]));
     d = normalise(d);
     Hit<T> h = trace_terminal<T, kBvh>(S.g, mk<T>(e.cam[0], e.cam[1], e.cam[2]), d, RT_NO_ID_DEV, 0, e.max_bounces, 0, ct);
-    env_store_hit<T>(e, b, h, d);
-    e.bounce[b] = 0; e.through[b] = 0; e.consec[b] = 0;
-    e.acc[b] = T(0); e.acc[B + b] = T(0); e.acc[2 * B + b] = T(0);
-    e.total[b] = 0.0;
+    st.set_hit(h, d);
+    st.bounce = 0; st.through = 0;
+    st.acc[0] = T(0); st.acc[1] = T(0); st.acc[2] = T(0);
+    st.total = 0.0;
+    if (e.adaptive) e.consec[b] = 0;
 }
 
 // reset (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142).  pixels == NULL: draw with Philox(seed) keyed by
@@ -1073,13 +1099,15 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         int px, py;
         if (pixels) { px = pixels[2 * b]; py = pixels[2 * b + 1]; }
         else {
-            Philox4 o = philox4x32_10((uint32_t)b, 0u, 0u, 0x52544556u /* "RTEV" */, k0, k1);   // key = per-reset seed
+            Philox4 o = philox4x32_10((uint32_t)(e.b0 + b), 0u, 0u, 0x52544556u /* "RTEV" */, k0, k1);   // key = per-reset seed
             px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
             py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
         }
         if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
-        env_begin_episode<T, kBvh>(S, e, b, px, py, ct);
-        env_obs<T>(S.g, e, b, obs + 18 * (size_t)b);
+        EnvReg<T> st;
+        env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct);
+        env_store<T>(e, b, st);
+        env_obs<T>(S.g, st, obs + 18 * (size_t)b);
     }
     if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
 }
@@ -1104,29 +1132,29 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
     float *row = s_rows + 18 * threadIdx.x;
     Counters ct = {0u, 0u, 0u};
     if (b < e.B) {
-        const size_t B = (size_t)e.B;
-        Hit<T> cur;
-        env_load_hit<T>(e, b, cur);
-        int bc = e.bounce[b];
-        const int through = e.through[b];
+        EnvReg<T> st = env_load<T>(e, b);
+        const float a0 = actions[2 * b], a1 = actions[2 * b + 1];
+        const Hit<T> cur = st.hit();
+        int bc = st.bounce;
+        const int through = st.through;
         int rsn = 0, term = 0, trunc = 0;
         double rw = 0.0, info_total, info_sun = -1.0;
         int info_bounce = bc;
         if (cur.idx < 0) {                                                   // ray already missed, :313-323
-            rsn = 1; rw = -1.0; term = 1; info_total = e.total[b];
+            rsn = 1; rw = -1.0; term = 1; info_total = st.total;
         } else if (bc >= e.max_bounces) {                                    // :325-337
             rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T, kBvh>(S.g, S.la, e, b, cur, bc, ct);
-            e.total[b] += rw; info_total = e.total[b];
+            st.total += rw; info_total = st.total;
             rsn = 3; term = 1; trunc = 1;
         } else if (e.flavour == 1 && S.g.sv.ids[cur.idx] == e.sun_id) {      // FB :417-431 (total_reward not updated)
-            rsn = 5; rw = 10.0; term = 1; info_total = e.total[b] + rw; info_sun = 1.0;
+            rsn = 5; rw = 10.0; term = 1; info_total = st.total + rw; info_sun = 1.0;
         } else {
             // _action_to_direction: RL :144-182, FB :157-198
             T theta, phi;
             if (e.flavour == 1) {
-                theta = (T(actions[2 * b]) + T(1)) * T(3.14159265358979323846) / T(4);
-                phi = T(actions[2 * b + 1]) * T(3.14159265358979323846);
-            } else { theta = T(actions[2 * b]); phi = T(actions[2 * b + 1]); }
+                theta = (T(a0) + T(1)) * T(3.14159265358979323846) / T(4);
+                phi = T(a1) * T(3.14159265358979323846);
+            } else { theta = T(a0); phi = T(a1); }
             T st_, ct_, sp_, cp_;
             M<T>::sincos(theta, &st_, &ct_); M<T>::sincos(phi, &sp_, &cp_);
             const T lx = st_ * cp_, ly = st_ * sp_, lz = ct_;
@@ -1144,13 +1172,13 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
                 if (S.g.sv.ids[nx.idx] == e.sun_id) { rw = 10.0; rsn = 4; term = 1; info_sun = 1.0; }
                 else { rw = env_lighting_reward<T>(S.g, e, nx); info_sun = 0.0; }
             } else { rw = -0.1; rsn = 1; term = 1; }
-            e.total[b] += rw; info_total = e.total[b];
-            env_store_hit<T>(e, b, nx, D);
-            e.bounce[b] = bc; info_bounce = bc;
+            st.total += rw; info_total = st.total;
+            st.set_hit(nx, D);
+            st.bounce = bc; info_bounce = bc;
             if (nx.idx >= 0) {                                               // :373-381
                 T c[3];
                 terminal_rgb<T, kBvh>(S.g, S.la, nx, 0, c, ct);
-                e.acc[b] = e.acc[b] + c[0]; e.acc[B + b] = e.acc[B + b] + c[1]; e.acc[2 * B + b] = e.acc[2 * B + b] + c[2];
+                st.acc[0] = st.acc[0] + c[0]; st.acc[1] = st.acc[1] + c[1]; st.acc[2] = st.acc[2] + c[2];
             }
             if (e.flavour == 0) {
                 if (nx.idx < 0) { term = 1; rsn = 2; }
@@ -1162,7 +1190,7 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
             R *q = info + 4 * (size_t)b;
             q[0] = (R)info_bounce; q[1] = (R)through; q[2] = (R)info_total; q[3] = (R)info_sun;
         }
-        env_obs<T>(S.g, e, b, row);
+        env_obs<T>(S.g, st, row);
         if constexpr (kAuto) {
             if (term | trunc) {
                 if (final_obs) {                         // 72-byte rows: nine 8-byte stores
@@ -1170,14 +1198,15 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
 #pragma unroll
                     for (int k = 0; k < 9; ++k) fo[k] = make_float2(row[2 * k], row[2 * k + 1]);
                 }
-                const Philox4 o = philox4x32_10((uint32_t)b, (uint32_t)e.episode[b], 1u, 0x52544556u /* "RTEV" */, k0, k1);
+                const Philox4 o = philox4x32_10((uint32_t)(e.b0 + b), (uint32_t)e.episode[b], 1u, 0x52544556u /* "RTEV" */, k0, k1);
                 const int px = (int)(((unsigned long long)o.w[0] * (unsigned)e.W) >> 32);
                 const int py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
                 if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
-                env_begin_episode<T, kBvh>(S, e, b, px, py, ct);
-                env_obs<T>(S.g, e, b, row);
+                env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct);
+                env_obs<T>(S.g, st, row);
             }
         }
+        env_store<T>(e, b, st);
     }
     env_flush_obs(s_rows, obs, e.B);
     if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);

