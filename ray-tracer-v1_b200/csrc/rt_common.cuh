@@ -13,6 +13,16 @@
 namespace rt {
 
 #define RT_DEV __device__ __forceinline__
+// RT_CHECKED build (csrc/Makefile target `checked` -> librt_b200_checked.so): device-side bounds / protocol assertions on
+// every indexed access of the kernels.  compute-sanitizer is closed on the pool these kernels are developed on, so the
+// GPU test suite is also run against this library (RT_B200_LIB=...): a violated assertion aborts the launch with
+// cudaErrorAssert and every later call of the test fails loudly.
+#ifdef RT_CHECKED
+#include <assert.h>
+#define RT_ASSERT(cond) assert(cond)
+#else
+#define RT_ASSERT(cond) ((void)0)
+#endif
 #define RT_NO_ID_DEV INT32_MIN
 #define RT_PATH_MAX_DEPTH 32     /* deepest TraditionalRenderer recursion the path kernel unrolls */
 

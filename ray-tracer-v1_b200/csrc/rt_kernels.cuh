@@ -220,6 +220,7 @@ RT_DEV void flag_wait(const unsigned *flag, unsigned epoch, long long timeout_cy
 RT_DEV void flag_post(unsigned *flag, unsigned epoch) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(flag), "r"(epoch) : "memory");
 }
+RT_DEV bool a_count_ok(int spp_total) { return spp_total > 0; }
 #define RT_FLAG_ADDED 0
 #define RT_FLAG_DONE 16
 #define RT_FLAG_GO 32
@@ -327,6 +328,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     for (unsigned unit = ((unsigned)blockIdx.x << 3) + (unsigned)w_; unit < n_units;) {
     unsigned nxt = 0;
     if (lane_ == 0) nxt = first_dyn + atomicAdd(pp.sched, 1u);
+    RT_ASSERT(unit < n_units);
     const int tile = (int)(unit >> 3), wt = (int)(unit & 7u);      // wt: the warp's place in the 4 x 2 warp tile
     const int by = tile / pp.gx, bx = tile - by * pp.gx;
     const int x = (((bx << 2) + (wt & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
@@ -422,6 +424,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                         Hit<T> h;
                         if constexpr (kMode == 3) { h.idx = i; h.t = t; h.p = O + D * t; h.n = (h.p - centre) * inv_r; }
                         else finish_hit<T>(S.g, O, D, i, t, h);
+                        RT_ASSERT(depth >= 0 && depth < RT_PATH_MAX_DEPTH && i < sc.n);
                         if constexpr (kMode != 3) st.idx[depth] = (uint32_t)i;
                         if constexpr (M<T>::exact) st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
                         else if constexpr (kMode == 3)       // one stack word per level: sphere index above the 24 colour bits
@@ -503,6 +506,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     }
     if (has_pixel && ns > 0 && sub == 0) {
         const size_t o = (size_t)y * pp.W + x;
+        RT_ASSERT(x >= 0 && x < pp.W && y >= pp.y0 && y < pp.y1 && y < pp.H);
         bool to_accum = true;
         if constexpr (!M<T>::exact && kIntFold) {
             if (pp.sink == 1) {
@@ -517,6 +521,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 int k = min(pp.world - 1, (int)(((long long)y * pp.world) / pp.H));
                 while (y >= pp.band_y[k + 1]) ++k;
                 while (y < pp.band_y[k]) --k;
+                RT_ASSERT(k >= 0 && k < pp.world && y >= pp.band_y[k] && y < pp.band_y[k + 1]);
                 float4 *dst = pp.peer_accum[k] + o;
                 asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                              :: "l"(dst), "f"((float)a0), "f"((float)a1), "f"((float)a2), "f"((float)ns) : "memory");
@@ -563,7 +568,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 const double spp = (double)pp.spp_total;
                 for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
                     const size_t o = first + i;
+                    RT_ASSERT(o < (size_t)pp.W * pp.H && a_count_ok(pp.spp_total));
                     const float4 a = __ldcg(own + o);                  // L2: where the peers' reductions landed
+                    RT_ASSERT(a.w == (float)pp.spp_total);            // every rank's sums arrived before the flags said so
                     const double r = floor((double)a.x / spp) / 255.0, g = floor((double)a.y / spp) / 255.0, b = floor((double)a.z / spp) / 255.0;
                     float *px = pp.image + 3 * o;
                     px[0] = (float)(r < 1.0 ? r : 1.0); px[1] = (float)(g < 1.0 ? g : 1.0); px[2] = (float)(b < 1.0 ? b : 1.0);
@@ -1133,6 +1140,7 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
     Counters ct = {0u, 0u, 0u};
     if (b < e.B) {
         EnvReg<T> st = env_load<T>(e, b);
+        RT_ASSERT(st.idx >= -1 && st.idx < sc.n && st.bounce >= 0);
         const float a0 = actions[2 * b], a1 = actions[2 * b + 1];
         const Hit<T> cur = st.hit();
         int bc = st.bounce;

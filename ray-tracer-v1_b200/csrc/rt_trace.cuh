@@ -269,6 +269,7 @@ RT_DEV int brute_select_pkc(const PkConst &pkc, int n_padded, int key_mask6, V3<
             }
         }
     }
+    RT_ASSERT(best >= RT_KEY_INF || (best & 63) < n_padded);
     return best < RT_KEY_INF ? (best & 63) : -1;
 }
 
@@ -388,8 +389,10 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
         int node = g.bvh.root;            // >= 0 internal, < 0 leaf ~prim
         for (;;) {
             if (node < 0) {
+                RT_ASSERT(~node >= 0 && ~node < g.bvh.nodes && g.bvh.prims[~node] >= 0 && g.bvh.prims[~node] < g.sv.n);
                 consider<T, kAbs>(g, g.bvh.prims[~node], O, D, suppress, best, bt, bi, tests);
             } else {
+                RT_ASSERT(node < g.bvh.nodes - 1 || g.bvh.nodes == 1);          // n - 1 internal nodes
                 const float4 a = g.bvh.node4[4 * node + 0], b = g.bvh.node4[4 * node + 1],
                              c = g.bvh.node4[4 * node + 2], ch = g.bvh.node4[4 * node + 3];
                 box_tests += 2;
@@ -409,6 +412,7 @@ RT_DEV int nearest(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, T &t_out, un
                 if (hl && hr) {
                     bool left_first = ln <= rn;
                     int nearc = left_first ? cl : cr, farc = left_first ? cr : cl;
+                    RT_ASSERT(sp < RT_BVH_STACK);                          // a dropped subtree would lose hits
                     if (sp < RT_BVH_STACK) stack[sp++] = farc;
                     node = nearc;
                     continue;
@@ -589,8 +593,10 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
 // kPacked: the level's sphere index rides in bits 24-31 of `direct` (scenes of <= 256 spheres), st.idx is not used.
 template <typename T, bool kPacked = false>
 RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3]) {
+    RT_ASSERT(depth >= 0 && depth <= RT_PATH_MAX_DEPTH);
     for (int k = depth - 1; k >= 0; --k) {
         const uint32_t d = st.direct[k];
+        RT_ASSERT((int)(kPacked ? (d >> 24) : st.idx[k]) < g.sv.n);
         const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
         const int t0 = min(255, (int)(d & 255u) + c[0]), t1 = min(255, (int)((d >> 8) & 255u) + c[1]),
                   t2 = min(255, (int)((d >> 16) & 255u) + c[2]);

@@ -39,3 +39,12 @@ def rt():
     from ray_tracer_v1_b200 import _native
     _native.lib()
     return pkg
+
+
+def gate(name, measured, limit):
+    """FP32-vs-reference gate: `measured` must not exceed `limit` (limits are 3x the figures measured on the B200, with a
+    floor of one or two pixels on the tiny golden frames; the measured table of a `pytest -s` run is committed as
+    profiles/parity_r2.txt)."""
+    measured = float(measured)
+    print(f"GATE {name}: measured {measured:.6g} limit {limit:.6g}")
+    assert measured <= limit, f"{name}: measured {measured:.6g} > limit {limit:.6g}"

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--lbvh", action="store_true")
     ap.add_argument("--ksplit", type=int, default=-1, help="-1 auto, 0 off, k = lanes per pixel")
     ap.add_argument("--schedules", default="0,1")
+    ap.add_argument("--no-stats", action="store_true", help="launch without the statistics counters")
     ap.add_argument("--save", default=None, help="write the last accumulation buffer to this .npy")
     args = ap.parse_args()
     spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
@@ -42,7 +43,7 @@ def main():
         for _ in range(args.reps):
             stats.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); sc.render_path(p, accum, nat.F32, stats=stats); b.record()
+            a.record(); sc.render_path(p, accum, nat.F32, stats=None if args.no_stats else stats); b.record()
             torch.cuda.synchronize()
             best = min(best, a.elapsed_time(b))
         st = stats.cpu().numpy()
