@@ -1073,8 +1073,11 @@ RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
 // reset of one episode (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142): camera ray through pixel (px, py),
 // first nearestSphereIntersect, zeroed counters.  Shared by env_reset_kernel and the auto-reset of env_step_kernel.
 template <typename T, bool kBvh>
-RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int px, int py, EnvReg<T> &st, Counters &ct) {
-    if (e.episode) e.episode[b] += 1;
+RT_DEV void env_begin_episode(const Staged<T> &S, const EnvDev<T> &e, int b, int px, int py, EnvReg<T> &st, Counters &ct,
+                              bool first = false) {
+    // episode number since the last reset of the whole batch: the counter the in-launch restarts key their start pixels
+    // by, so reset(seed) followed by the same actions always replays the same rollout
+    if (e.episode) e.episode[b] = first ? 1 : e.episode[b] + 1;
     const T aspect = T(e.W) / T(e.H);
     const T x = (T(2) * (T(px) + T(0.5)) / T(e.W) - T(1)) * aspect * e.tan_half;
     const T y = (T(1) - T(2) * (T(py) + T(0.5)) / T(e.H)) * e.tan_half;
@@ -1112,7 +1115,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         }
         if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
         EnvReg<T> st;
-        env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct);
+        env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct, mask == nullptr);
         env_store<T>(e, b, st);
         env_obs<T>(S.g, st, obs + 18 * (size_t)b);
     }

@@ -68,7 +68,7 @@ def test_batched_env_fp64_equals_oracle_and_fp32_is_close(rt, orc, name):
         ok = alive32
         np.testing.assert_allclose(obs3.cpu().numpy()[ok], obs_r[ok], rtol=2e-3, atol=2e-3)
         np.testing.assert_allclose(rew3.cpu().numpy()[ok], rew_r[ok], rtol=2e-3, atol=6e-3)
-    gate(f"{name} FP32 episodes leaving the FP64 trajectory", 1 - alive32.mean(), 0.1)
+    gate(f"{name} FP32 episodes leaving the FP64 trajectory", 1 - alive32.mean(), 2.5 / B)       # measured 0 of 96 (65,536 envs: 5.5e-4)
     e64.close(); e32.close()
 
 
@@ -186,7 +186,7 @@ def test_render_entry_points(rt, orc):
         exp32 = CustomSceneExperiment(output_dir=tmp, precision="f32")
         exp32.config.update(image_width=320, image_height=240, samples_per_pixel=1, max_bounces=1)
         _, img32 = exp32.render_custom_scene(scenes.build_balls_in_space(as_rendered=False).spheres, "traditional", None)
-        gate("render entry FP32 pixels beyond 1/255", (np.abs(img32 - z["image"]).max(axis=2) > 1.001 / 255).mean(), 2e-3)
+        gate("render entry FP32 pixels beyond 1/255", (np.abs(img32 - z["image"]).max(axis=2) > 1.001 / 255).mean(), 1e-4)      # measured 0
         # render_true_original: 601x601 notebook grid; compare its centre crop rows with the 121-grid golden's geometry
         full = exp.render_true_original(scenes.build_balls_in_space(as_rendered=False).spheres, None)
         assert full.shape == (601, 601, 3) and full.max() <= 1.0 and full.min() >= 0.0

@@ -41,7 +41,7 @@ def test_sphere_discriminant_kat(nat):
         np.testing.assert_allclose(out64[hit, 1:8], rows[hit, 12:19], rtol=1e-9, atol=1e-12)
         out32 = nat.sphere_discriminant(rows[:, 0:6], rows[:, 6:10], point, nat.F32)
         agree = out32[:, 0] == rows[:, 11]
-        gate("sphere_discriminant FP32 hit/miss flips (grazing rays)", 1 - agree.mean(), 0.01)
+        gate("sphere_discriminant FP32 hit/miss flips (grazing rays)", 1 - agree.mean(), 1.5 / agree.size)        # measured 0: one KAT of slack
         both = hit & agree
         np.testing.assert_allclose(out32[both, 1:8], rows[both, 12:19], rtol=2e-3, atol=2e-4)
 
@@ -69,8 +69,8 @@ def test_trace_rays_matches_oracle(nat, orc):
         assert np.array_equal(sc.shade_hits(hits, 0, nat.F64), orc.shade_hits(fs, hits, 0))
         term32, rgb32 = sc.trace_rays(rays, suppress=sup, bounces0=b0, max_bounces=depth, miss=z["miss"], precision=nat.F32)
         same = np.all(term32[:, :2] == term_o[:, :2], axis=1)
-        gate("trace_rays FP32 terminal object differs", 1 - same.mean(), 5e-3)
-        gate("trace_rays FP32 colour beyond 1 level", 1 - (np.abs(quant8(rgb32[same]) - quant8(rgb_o[same])).max(axis=1) <= 1).mean(), 5e-3)
+        gate("trace_rays FP32 terminal object differs", 1 - same.mean(), max(1.5 / same.size, 1e-4))            # measured 0
+        gate("trace_rays FP32 colour beyond 1 level", 1 - (np.abs(quant8(rgb32[same]) - quant8(rgb_o[same])).max(axis=1) <= 1).mean(), max(1.5 / same.size, 1e-4))
         sc.close()
 
 
@@ -104,8 +104,8 @@ def test_whitted_frames_fp32_within_1_of_255(nat, name):
     flipped = hit != z["hit"].astype(np.int32)
     bad = (diff > 1)
     # every pixel whose terminal object agrees must be within one 8-bit level, bar shadow-edge flips
-    gate(f"{name} FP32 pixels beyond 1/255", bad.mean(), 2e-3)
-    gate(f"{name} FP32 hit flips", flipped.mean(), 2e-3)
+    gate(f"{name} FP32 pixels beyond 1/255", bad.mean(), max(1.5 / bad.size, 1e-4))              # measured 0 on all six frames
+    gate(f"{name} FP32 hit flips", flipped.mean(), max(3.5 / bad.size, 1e-4))                    # measured <= 1 pixel of 14,641
     if name == "whitted_c1_balls_320x240":
         # BASELINE config 1, the reference's own render_custom_scene frame: the north star's "within 1/255 per channel
         # after 8-bit quantisation" holds on every one of the 76,800 pixels (measured: 0; one pixel of slack)
@@ -123,7 +123,7 @@ def test_whitted_jittered_spp4(nat):
     image, sums, _, _ = sc.render_whitted_host(p, nat.F64)
     assert np.array_equal(image, z["image"])
     image32, _, _, _ = sc.render_whitted_host(p, nat.F32)
-    gate("whitted spp4 jittered FP32 pixels beyond 1/255", (np.abs(image32 - z["image"]).max(axis=2) > 1.01 / 255).mean(), 5e-3)
+    gate("whitted spp4 jittered FP32 pixels beyond 1/255", (np.abs(image32 - z["image"]).max(axis=2) > 1.01 / 255).mean(), 2.5 / image32[..., 0].size)   # measured 0
     sc.close()
 
 
@@ -142,9 +142,9 @@ def test_path_frames(nat, name):
     # FP32 product path: same Philox stream, so it only departs where FP32 geometry flips a hit or a truncation
     image32, sums32, stats32 = sc.render_path_host(p, nat.F32)
     d = np.abs(sums32[..., :3] / spp - z["sums"] / spp)
-    gate(f"{name} FP32 pixels beyond one level", (d.max(axis=2) > 1.0).mean(), 0.02)
+    gate(f"{name} FP32 pixels beyond one level", (d.max(axis=2) > 1.0).mean(), 6e-3)                     # measured 0 (full size: 2.5e-4 - 7.2e-4)
     rmse = float(np.sqrt(np.mean(d ** 2)))
-    gate(f"{name} FP32 RMSE x sqrt(spp)", rmse * np.sqrt(spp), 4.0)
+    gate(f"{name} FP32 RMSE x sqrt(spp)", rmse * np.sqrt(spp), 1.5)                                   # measured 0.04-0.05 (full size 0.41-0.66)
     assert abs(int(stats32[0]) - int(z["stats"][0])) <= 0.01 * int(z["stats"][0])
     sc.close()
 
@@ -569,7 +569,7 @@ def test_output6_frames_match_reference(nat, orc, name):
     assert [int(st64[0]), int(st64[1])] == list(z["stats"])
     img32, rgb32, st32 = sc.render_simple_host(p, nat.F32)
     d = np.abs(rgb32[..., :3].astype(np.int64) - z["rgb"].astype(np.int64)).max(axis=2)
-    gate(f"{name} (output6) FP32 pixels beyond one level", (d > 1).mean(), 0.02)          # same Philox stream: a few silhouette / int() flips
+    gate(f"{name} (output6) FP32 pixels beyond one level", (d > 1).mean(), 6e-3)          # same Philox stream: a few silhouette / int() flips
     assert abs(int(st32[0]) - int(st64[0])) <= 0.01 * int(st64[0])
     # a larger frame against the oracle (FP64 exact), and the explicit-ray entry against the frame
     q = sc.simple_params(200, 150, max_bounces=depth, seed=seed + 1)
