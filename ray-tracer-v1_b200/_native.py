@@ -38,13 +38,16 @@ class NativeLibraryError(RuntimeError):
 
 
 class SceneDesc(C.Structure):
+    # the array members are `const double *` / `const int32_t *` / `const uint8_t *` in rt_scene_desc; declared as void
+    # pointers here so that make_desc can store raw addresses (a typed ctypes cast costs ~2 us per field, x 20 fields,
+    # on every frame of a 30-us render)
     _fields_ = [
-        ("n", C.c_int32), ("centre", c_dp), ("radius", c_dp), ("material", c_dp), ("colour", c_dp), ("ids", c_ip),
-        ("nG", C.c_int32), ("g_vec", c_dp), ("g_col", c_dp), ("g_strength", c_dp), ("g_max_angle", c_dp), ("g_func", c_ip),
-        ("nP", C.c_int32), ("p_id", c_ip), ("p_pos", c_dp), ("p_col", c_dp), ("p_strength", c_dp), ("p_max_angle", c_dp),
-        ("p_func", c_ip),
+        ("n", C.c_int32), ("centre", vp), ("radius", vp), ("material", vp), ("colour", vp), ("ids", vp),
+        ("nG", C.c_int32), ("g_vec", vp), ("g_col", vp), ("g_strength", vp), ("g_max_angle", vp), ("g_func", vp),
+        ("nP", C.c_int32), ("p_id", vp), ("p_pos", vp), ("p_col", vp), ("p_strength", vp), ("p_max_angle", vp),
+        ("p_func", vp),
         ("bg", C.c_double * 3),
-        ("nL", C.c_int32), ("l_centre", c_dp), ("l_colour", c_dp), ("l_index", c_ip), ("small", c_u8p),
+        ("nL", C.c_int32), ("l_centre", vp), ("l_colour", vp), ("l_index", vp), ("small", vp),
     ]
 
 
@@ -322,24 +325,36 @@ def _i(a):
     return np.ascontiguousarray(a, np.int32)
 
 
+_F64, _I32 = np.dtype(np.float64), np.dtype(np.int32)
+_DESC_F = ("centre", "radius", "material", "colour", "g_vec", "g_col", "g_strength", "g_max_angle", "p_pos", "p_col",
+           "p_strength", "p_max_angle", "l_centre", "l_colour")
+_DESC_I = ("ids", "g_func", "p_id", "p_func", "l_index")
+
+
+def _as(a, dt):
+    """``a`` as a C-contiguous array of dtype ``dt`` (no copy when it already is one: the FlatScene arrays are)."""
+    if type(a) is np.ndarray and a.dtype == dt and a.flags.c_contiguous:
+        return a
+    return np.ascontiguousarray(a, dt)
+
+
 def make_desc(fs):
     """FlatScene (scene.py) -> (SceneDesc, keep-alive dict)."""
-    k = {name: _d(getattr(fs, name)) for name in ("centre", "radius", "material", "colour", "g_vec", "g_col", "g_strength",
-                                                  "g_max_angle", "p_pos", "p_col", "p_strength", "p_max_angle",
-                                                  "l_centre", "l_colour")}
-    k.update({name: _i(getattr(fs, name)) for name in ("ids", "g_func", "p_id", "p_func", "l_index")})
+    k = {}
+    d = SceneDesc()
+    for name in _DESC_F:
+        a = k[name] = _as(getattr(fs, name), _F64)
+        setattr(d, name, a.__array_interface__["data"][0])
+    for name in _DESC_I:
+        a = k[name] = _as(getattr(fs, name), _I32)
+        setattr(d, name, a.__array_interface__["data"][0])
     n = int(k["radius"].shape[0])
     small = getattr(fs, "small", None)
-    k["small"] = np.ascontiguousarray(small if small is not None else np.zeros(n), np.uint8)
-    d = SceneDesc()
+    sm = k["small"] = np.ascontiguousarray(small if small is not None else np.zeros(n), np.uint8)
+    d.small = sm.__array_interface__["data"][0]
     d.n, d.nG, d.nP, d.nL = n, int(k["g_strength"].shape[0]), int(k["p_strength"].shape[0]), int(k["l_index"].shape[0])
-    for name in ("centre", "radius", "material", "colour", "g_vec", "g_col", "g_strength", "g_max_angle", "p_pos", "p_col",
-                 "p_strength", "p_max_angle", "l_centre", "l_colour"):
-        setattr(d, name, k[name].ctypes.data_as(c_dp))
-    for name in ("ids", "g_func", "p_id", "p_func", "l_index"):
-        setattr(d, name, k[name].ctypes.data_as(c_ip))
-    d.small = k["small"].ctypes.data_as(c_u8p)
-    d.bg[:] = [float(x) for x in np.asarray(fs.bg, np.float64).reshape(3)]
+    bg = np.asarray(fs.bg, np.float64).reshape(3)
+    d.bg[0], d.bg[1], d.bg[2] = float(bg[0]), float(bg[1]), float(bg[2])
     return d, k
 
 

@@ -556,7 +556,9 @@ static int render_whitted_t(rt_scene *sc, const SceneDev<T> &view, const rt_whit
     wp.pitch_y = (T)(p->H > 1 ? p->Y[0] - p->Y[1] : 0.0);
     wp.k0 = (uint32_t)p->seed; wp.k1 = (uint32_t)(p->seed >> 32);
     wp.prenorm = p->prenormalise; wp.accumulate = p->accumulate;
-    CU(launch_whitted<T>(view, wp, accum, hit, reinterpret_cast<unsigned long long *>(stats), st));
+    if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
+    unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
+    CU(launch_whitted<T>(view, wp, accum, hit, reinterpret_cast<unsigned long long *>(stats), st, sched));
     return RT_OK;
 }
 

@@ -132,6 +132,11 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #define RT_MODE_DECL constexpr bool kShared = kMode != 2; constexpr bool kBvh = kMode == 1 || kMode == 2
 
 // ------------------------------------------------------------------ Algorithm A frame
+// PERSISTENT WARPS, as in path_kernel: the launch has as many CTAs as the device keeps resident, the scene is staged and
+// the statistics are flushed once per CTA, and every WARP pulls its next 8x4-pixel tile from a device counter (the
+// first tiles are static, the fetch for the next one is issued before the current one is traced, the last warp of the
+// launch re-arms the counter).  A 1280x720 frame is 28,800 warp tiles of which typically > 95 % are sky: with one CTA
+// per 32x8 block the frame cost what 3,600 CTA prologues cost (0.13 ms); now a sky tile costs a few dozen instructions.
 template <typename T, int kMode>
 __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS : 1)) whitted_kernel(SceneDev<T> sc, WhittedDev<T> wp, typename M<T>::v4 *accum,
                                                       int *hit_out, unsigned long long *stats) {
@@ -139,11 +144,19 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
     extern __shared__ __align__(32) unsigned char smem[];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
-    int x, yr;
-    tile_pixel(x, yr);
-    const int y = wp.y0 + yr;
+    const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
     Counters ct = {0u, 0u, 0u};
     unsigned primaries = 0;
+    const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
+    const unsigned n_units = (unsigned)(wp.gx * wp.gy) << 3, first_dyn = (unsigned)gridDim.x << 3;
+    for (unsigned unit = ((unsigned)blockIdx.x << 3) + (unsigned)w_; unit < n_units;) {
+    unsigned nxt = 0;
+    if (lane_ == 0) nxt = first_dyn + atomicAdd(wp.sched, 1u);
+    RT_ASSERT(unit < n_units);
+    const int tile = (int)(unit >> 3), wt = (int)(unit & 7u);          // 32x8-pixel block, the warp's 8x4 tile in it
+    const int by = tile / wp.gx, bx = tile - by * wp.gx;
+    const int x = bx * 32 + (wt & 3) * 8 + (lane_ & 7);
+    const int y = wp.y0 + by * 8 + (wt >> 2) * 4 + (lane_ >> 3);
     // camera rays of this warp's 8x4 pixel tile: the spheres their cone can touch (cone_candidates, rt_trace.cuh), built
     // once for all samples.  Tiles of sky get an empty list and skip the sphere loop altogether; frames are unchanged.
     unsigned long long cand = ~0ull;
@@ -161,15 +174,23 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
             const V3<float> d0 = normalise(mk<float>(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.f));
             const float alpha = sqrtf(ex * ex + ey * ey) * 1.001f + 1e-6f;       // angle <= distance on the z = -1 plane
             cand = cone_candidates(reinterpret_cast<const float4 *>(S.g.sv.sph), S.g.sv.n,
-                                   mk<float>((float)wp.cam[0], (float)wp.cam[1], (float)wp.cam[2]), d0, alpha, threadIdx.x & 31);
+                                   mk<float>((float)wp.cam[0], (float)wp.cam[1], (float)wp.cam[2]), d0, alpha, lane_);
         }
     }
     if (x < wp.W && y < wp.y1) {
-        const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
         const T X0 = wp.X[x], Y0 = wp.Y[y];
         const uint32_t pixel = (uint32_t)(y * wp.W + x);
         T a0 = T(0), a1 = T(0), a2 = T(0);
         int last = -1;
+        if (cand == 0ull) {
+            // No sphere can be touched by ANY ray of this warp tile's cone (the cone includes the jitter margin), so every
+            // sample of every pixel of the tile misses: the sum is the miss colour added s1 - s0 times (the same
+            // additions as the loop below would make, so the frame is unchanged) and neither the Philox jitter nor the
+            // ray is needed.
+            for (int s = wp.s0; s < wp.s1; ++s) { a0 += wp.miss[0]; a1 += wp.miss[1]; a2 += wp.miss[2]; }
+            primaries += (unsigned)(wp.s1 - wp.s0);
+            ct.queries += (unsigned)(wp.s1 - wp.s0);        // one nearestSphereIntersect per sample, over an empty candidate list
+        } else
         for (int s = wp.s0; s < wp.s1; ++s) {
             T Xj = X0, Yj = Y0;
             if (wp.spp > 1) {                                            // output5.py:1463-1470
@@ -188,6 +209,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
             a0 += c[0]; a1 += c[1]; a2 += c[2];
         }
         const size_t o = (size_t)y * wp.W + x;
+        RT_ASSERT(o < (size_t)wp.W * wp.H);
         typename M<T>::v4 out = M<T>::make4(a0, a1, a2, T(wp.s1 - wp.s0));
         if (wp.accumulate) {
             const typename M<T>::v4 old = accum[o];
@@ -195,6 +217,13 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
         }
         accum[o] = out;
         if (hit_out) hit_out[o] = last;
+    }
+    unit = __shfl_sync(0xffffffffu, nxt, 0);
+    }   // warp tiles of this warp
+    if (lane_ == 0) {
+        // every warp of the launch passes here exactly once, after its last fetch: the last one re-arms the counters
+        __threadfence();
+        if (atomicAdd(wp.sched + 1, 1u) == (gridDim.x << 3) - 1u) { wp.sched[0] = 0u; wp.sched[1] = 0u; __threadfence(); }
     }
     if (stats) {
         flush_stats(stats, STAT_QUERIES, ct.queries);
@@ -1254,18 +1283,6 @@ template <typename T> static inline int mode_for(const SceneDev<T> &sc, size_t e
         }                                                                                                       \
     } while (0)
 
-template <typename T>
-cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
-                           unsigned long long *stats, cudaStream_t st) {
-    const int rows = wp.y1 - wp.y0;
-    if (rows <= 0 || wp.W <= 0) return cudaSuccess;
-    dim3 grid((wp.W + 31) / 32, (rows + 7) / 8), block(256);
-    using v4 = typename M<T>::v4;
-    const int mode = mode_for(sc);
-    RT_DISPATCH_MODE(mode, whitted_kernel, grid, block, smem_for(sc), st, sc, wp, (v4 *)accum, hit, stats);
-    return cudaGetLastError();
-}
-
 // CTAs of a persistent launch: what the current device keeps resident for this kernel (occupancy x SM count); the
 // answer is cached per (device, kernel, shared-memory size) so that a launch costs no runtime query
 template <typename K> static unsigned persistent_ctas(K kernel, size_t smem_bytes, long long tiles) {
@@ -1289,6 +1306,33 @@ template <typename K> static unsigned persistent_ctas(K kernel, size_t smem_byte
         cache.push_back(Key{dev, (const void *)kernel, smem_bytes, g});
     }
     return (unsigned)(tiles < g ? (tiles > 0 ? tiles : 1) : g);
+}
+
+template <typename T>
+cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
+                           unsigned long long *stats, cudaStream_t st, unsigned *sched) {
+    const int rows = wp.y1 - wp.y0;
+    if (rows <= 0 || wp.W <= 0) return cudaSuccess;
+    WhittedDev<T> wl = wp;                                        // + the 32x8 block grid the persistent warps walk
+    wl.gx = (wp.W + 31) / 32; wl.gy = (rows + 7) / 8;
+    wl.sched = sched;
+    const long long blocks = (long long)wl.gx * wl.gy;
+    dim3 grid(1), block(256);
+    using v4 = typename M<T>::v4;
+    const int mode = mode_for(sc);
+    const size_t sm = mode != 2 ? smem_for(sc) : 0;
+    cudaError_t e = cudaSuccess;
+    switch (mode) {
+        case 0: e = allow_smem(whitted_kernel<T, 0>, sm); if (e != cudaSuccess) return e;
+                grid.x = persistent_ctas(whitted_kernel<T, 0>, sm, blocks);
+                whitted_kernel<T, 0><<<grid, block, sm, st>>>(sc, wl, (v4 *)accum, hit, stats); break;
+        case 1: e = allow_smem(whitted_kernel<T, 1>, sm); if (e != cudaSuccess) return e;
+                grid.x = persistent_ctas(whitted_kernel<T, 1>, sm, blocks);
+                whitted_kernel<T, 1><<<grid, block, sm, st>>>(sc, wl, (v4 *)accum, hit, stats); break;
+        default: grid.x = persistent_ctas(whitted_kernel<T, 2>, 0, blocks);
+                 whitted_kernel<T, 2><<<grid, block, 0, st>>>(sc, wl, (v4 *)accum, hit, stats); break;
+    }
+    return cudaGetLastError();
 }
 
 template <typename T>
@@ -1441,7 +1485,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
 
 #define RT_INSTANTIATE_LAUNCHERS(T)                                                                                     \
     template cudaError_t launch_whitted<T>(const SceneDev<T> &, const WhittedDev<T> &, void *, int *,                   \
-                                           unsigned long long *, cudaStream_t);                                         \
+                                           unsigned long long *, cudaStream_t, unsigned *);                             \
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
                                         cudaStream_t, const PkConst *, unsigned *);                                     \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \

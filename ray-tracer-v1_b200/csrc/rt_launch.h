@@ -14,6 +14,8 @@ template <typename T> struct WhittedDev {
     T pitch_x, pitch_y;          // X[1]-X[0], Y[0]-Y[1] (output5.py:1465-1466)
     uint32_t k0, k1;             // Philox key
     int prenorm, accumulate;
+    int gx, gy;                  // 32x8-pixel block grid of the launch (set by launch_whitted)
+    unsigned *sched;             // {next warp tile, warps done}: zero between launches (self-resetting)
 };
 
 // Algorithm B frame (rt_path_params)
@@ -79,7 +81,7 @@ template <typename T> struct EnvDev {
 
 template <typename T>
 cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
-                           unsigned long long *stats, cudaStream_t st);
+                           unsigned long long *stats, cudaStream_t st, unsigned *sched);
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
                         cudaStream_t st, const PkConst *pkc, unsigned *sched);

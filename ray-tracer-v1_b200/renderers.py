@@ -215,7 +215,9 @@ class CustomSceneExperiment:
         width, height = self.config['image_width'], self.config['image_height']
         spp = self.config['samples_per_pixel']
         start = time.time()
-        X, Y = custom_scene_grid(width, height)
+        if getattr(self, "_grid_key", None) != (width, height):             # the grid only depends on the frame size
+            self._grid_key, self._grid = (width, height), custom_scene_grid(width, height)
+        X, Y = self._grid
         fs = self._as_rendered(scene_spheres)
         image = render_whitted(fs, (0, 0, 1), X, Y, spp=spp, max_bounces=self.config['max_bounces'], miss=(2, 2, 5),
                                seed=self.seed, prenorm=True, precision=self.precision, device=self.device,
