@@ -61,6 +61,8 @@ struct rt_scene {
         bool settled = false;
     };
     std::vector<Grid> grids;
+    mutable unsigned *heavy_dev = nullptr;   // warp-tile list of two-pass Algorithm-A frames (launch_whitted)
+    mutable size_t heavy_cap = 0;
     // pinned staging area of scene uploads (FP32 blob, FP64 blob, small-light mask): the copies are asynchronous and
     // rt_scene_update never synchronises the stream; the next update waits for `staged` before it repacks the area
     unsigned char *stage = nullptr;
@@ -461,6 +463,7 @@ RT_EXPORT int rt_scene_destroy(rt_scene *scene) {
     if (scene->d.blob) cudaFree(scene->d.blob);
     if (scene->small_dev) cudaFree(scene->small_dev);
     if (scene->sched_dev) cudaFree(scene->sched_dev);
+    if (scene->heavy_dev) cudaFree(scene->heavy_dev);
     if (scene->stage) cudaFreeHost(scene->stage);
     if (scene->staged) cudaEventDestroy(scene->staged);
     for (rt_scene::Grid &g : scene->grids) grid_free(g);
@@ -557,8 +560,32 @@ static int render_whitted_t(rt_scene *sc, const SceneDev<T> &view, const rt_whit
     wp.k0 = (uint32_t)p->seed; wp.k1 = (uint32_t)(p->seed >> 32);
     wp.prenorm = p->prenormalise; wp.accumulate = p->accumulate;
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
-    unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
-    CU(launch_whitted<T>(view, wp, accum, hit, reinterpret_cast<unsigned long long *>(stats), st, sched));
+    const unsigned slot = sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS;
+    unsigned *sched = sc->sched_dev + 4 * slot;
+    // two-pass schedule (pass 1 lists the tiles a sphere can be seen in, pass 2 spreads their samples over the device):
+    // FP32 reductions in no fixed order, so only for integer-valued background / miss colours (sums then exact).  Every
+    // counter slot has its own tile list, so frames in flight on different streams do not share one
+    unsigned *sched2 = nullptr, *heavy = nullptr;
+    static const bool no_split = std::getenv("RT_B200_NO_SPLIT") != nullptr;       // A/B switch for measurements
+    if (sizeof(T) == 4 && !no_split && p->s1 - p->s0 >= 4 && p->s1 - p->s0 <= 4096) {
+        bool ints = true;
+        for (int k = 0; k < 3; ++k) {
+            const double a = p->miss[k], b = (double)view.bg[k];
+            ints = ints && a == std::floor(a) && b == std::floor(b) && std::fabs(a) <= 1024.0 && std::fabs(b) <= 1024.0;
+        }
+        const size_t tiles = (size_t)((p->W + 31) / 32) * (size_t)((p->y1 - p->y0 + 7) / 8) * 8;
+        if (ints && tiles > 0) {
+            if (tiles > sc->heavy_cap) {               // (cudaFree waits for the launches that may still read the old lists)
+                if (sc->heavy_dev) CU(cudaFree(sc->heavy_dev));
+                sc->heavy_dev = nullptr; sc->heavy_cap = 0;
+                CU(cudaMalloc((void **)&sc->heavy_dev, (size_t)RT_SCHED_SLOTS * tiles * sizeof(unsigned)));
+                sc->heavy_cap = tiles;
+            }
+            heavy = sc->heavy_dev + (size_t)slot * sc->heavy_cap;
+            sched2 = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);
+        }
+    }
+    CU(launch_whitted<T>(view, wp, accum, hit, reinterpret_cast<unsigned long long *>(stats), st, sched, sched2, heavy));
     return RT_OK;
 }
 

@@ -132,6 +132,43 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #define RT_MODE_DECL constexpr bool kShared = kMode != 2; constexpr bool kBvh = kMode == 1 || kMode == 2
 
 // ------------------------------------------------------------------ Algorithm A frame
+// camera rays of a warp's 8x4 pixel tile: the spheres their cone can touch (cone_candidates, rt_trace.cuh), built once
+// for all samples.  Tiles of sky get an empty list and skip the sphere loop altogether; frames are unchanged.
+template <typename T> RT_DEV unsigned long long whitted_tile_candidates(const Staged<T> &S, const WhittedDev<T> &wp, int x, int y, int lane) {
+    const float gx = (float)wp.X[min(x, wp.W - 1)], gy = (float)wp.Y[min(y, wp.y1 - 1)];
+    float xlo = gx, xhi = gx, ylo = gy, yhi = gy;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+    const float jx = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_x) : 0.f, jy = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_y) : 0.f;
+    const float ex = 0.5f * (xhi - xlo) + jx, ey = 0.5f * (yhi - ylo) + jy;
+    const V3<float> d0 = normalise(mk<float>(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.f));
+    const float alpha = sqrtf(ex * ex + ey * ey) * 1.001f + 1e-6f;       // angle <= distance on the z = -1 plane
+    return cone_candidates(reinterpret_cast<const float4 *>(S.g.sv.sph), S.g.sv.n,
+                           mk<float>((float)wp.cam[0], (float)wp.cam[1], (float)wp.cam[2]), d0, alpha, lane);
+}
+
+// one sample of one pixel: jittered camera ray (output5.py:1463-1470), nearestSphereIntersect, terminalRGB -> c[3]
+template <typename T, bool kBvh>
+RT_DEV int whitted_sample(const Staged<T> &S, const WhittedDev<T> &wp, V3<T> cam, T X0, T Y0, uint32_t pixel, int s,
+                          unsigned long long cand, Counters &ct, T c[3]) {
+    T Xj = X0, Yj = Y0;
+    if (wp.spp > 1) {
+        Philox4 o = philox4x32_10(pixel, (uint32_t)s, 0u, RT_PHILOX_TAG, wp.k0, wp.k1);
+        Xj = X0 + (u01<T>(o.w[0]) - T(0.5)) * wp.pitch_x;
+        Yj = Y0 + (u01<T>(o.w[1]) - T(0.5)) * wp.pitch_y;
+    }
+    V3<T> d = mk<T>(Xj, Yj, T(-1));
+    if constexpr (M<T>::exact) { if (wp.prenorm) d = normalise(d); }
+    d = normalise(d);                                            // Ray.__init__, ray.py:69-71
+    Hit<T> h = trace_terminal<T, kBvh>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct, cand);
+    if (h.idx >= 0) { terminal_rgb<T, kBvh>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); return h.idx; }
+    c[0] = wp.miss[0]; c[1] = wp.miss[1]; c[2] = wp.miss[2];
+    return -1;
+}
+
 // PERSISTENT WARPS, as in path_kernel: the launch has as many CTAs as the device keeps resident, the scene is staged and
 // the statistics are flushed once per CTA, and every WARP pulls its next 8x4-pixel tile from a device counter (the
 // first tiles are static, the fetch for the next one is issued before the current one is traced, the last warp of the
@@ -161,23 +198,19 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
     // once for all samples.  Tiles of sky get an empty list and skip the sphere loop altogether; frames are unchanged.
     unsigned long long cand = ~0ull;
     if constexpr (!M<T>::exact && kMode == 0) {
-        if (sc.n <= 64 && wp.W > 0 && wp.y1 > wp.y0) {
-            const float gx = (float)wp.X[min(x, wp.W - 1)], gy = (float)wp.Y[min(y, wp.y1 - 1)];
-            float xlo = gx, xhi = gx, ylo = gy, yhi = gy;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                xlo = fminf(xlo, __shfl_xor_sync(0xffffffffu, xlo, o)); xhi = fmaxf(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
-                ylo = fminf(ylo, __shfl_xor_sync(0xffffffffu, ylo, o)); yhi = fmaxf(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
-            }
-            const float jx = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_x) : 0.f, jy = wp.spp > 1 ? 0.5f * fabsf((float)wp.pitch_y) : 0.f;
-            const float ex = 0.5f * (xhi - xlo) + jx, ey = 0.5f * (yhi - ylo) + jy;
-            const V3<float> d0 = normalise(mk<float>(0.5f * (xlo + xhi), 0.5f * (ylo + yhi), -1.f));
-            const float alpha = sqrtf(ex * ex + ey * ey) * 1.001f + 1e-6f;       // angle <= distance on the z = -1 plane
-            cand = cone_candidates(reinterpret_cast<const float4 *>(S.g.sv.sph), S.g.sv.n,
-                                   mk<float>((float)wp.cam[0], (float)wp.cam[1], (float)wp.cam[2]), d0, alpha, lane_);
+        if (sc.n <= 64 && wp.W > 0 && wp.y1 > wp.y0) cand = whitted_tile_candidates<T>(S, wp, x, y, lane_);
+    }
+    bool listed = false;
+    if constexpr (!M<T>::exact && kMode == 0) {
+        // two-pass frame: a tile some sphere can be seen in is only LISTED here (and its pixels zeroed); pass 2 traces it,
+        // one (tile, sample) unit per warp, on every warp of the device
+        if (wp.split && cand != 0ull) {
+            listed = true;
+            if (lane_ == 0) wp.heavy[atomicAdd(wp.sched + 2, 1u)] = unit;
+            if (!wp.accumulate && x < wp.W && y < wp.y1) accum[(size_t)y * wp.W + x] = M<T>::make4(T(0), T(0), T(0), T(0));
         }
     }
-    if (x < wp.W && y < wp.y1) {
+    if (!listed && x < wp.W && y < wp.y1) {
         const T X0 = wp.X[x], Y0 = wp.Y[y];
         const uint32_t pixel = (uint32_t)(y * wp.W + x);
         T a0 = T(0), a1 = T(0), a2 = T(0);
@@ -192,20 +225,9 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
             ct.queries += (unsigned)(wp.s1 - wp.s0);        // one nearestSphereIntersect per sample, over an empty candidate list
         } else
         for (int s = wp.s0; s < wp.s1; ++s) {
-            T Xj = X0, Yj = Y0;
-            if (wp.spp > 1) {                                            // output5.py:1463-1470
-                Philox4 o = philox4x32_10(pixel, (uint32_t)s, 0u, RT_PHILOX_TAG, wp.k0, wp.k1);
-                Xj = X0 + (u01<T>(o.w[0]) - T(0.5)) * wp.pitch_x;
-                Yj = Y0 + (u01<T>(o.w[1]) - T(0.5)) * wp.pitch_y;
-            }
-            V3<T> d = mk<T>(Xj, Yj, T(-1));
-            if constexpr (M<T>::exact) { if (wp.prenorm) d = normalise(d); }
-            d = normalise(d);                                            // Ray.__init__, ray.py:69-71
-            Hit<T> h = trace_terminal<T, kBvh>(S.g, cam, d, RT_NO_ID_DEV, 0, wp.max_bounces, 0, ct, cand);
-            primaries++;
             T c[3];
-            if (h.idx >= 0) { terminal_rgb<T, kBvh>(S.g, S.la, h, wp.shadow_max_bounces, c, ct); last = h.idx; }
-            else { c[0] = wp.miss[0]; c[1] = wp.miss[1]; c[2] = wp.miss[2]; last = -1; }
+            last = whitted_sample<T, kBvh>(S, wp, cam, X0, Y0, pixel, s, cand, ct, c);
+            primaries++;
             a0 += c[0]; a1 += c[1]; a2 += c[2];
         }
         const size_t o = (size_t)y * wp.W + x;
@@ -224,6 +246,62 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
         // every warp of the launch passes here exactly once, after its last fetch: the last one re-arms the counters
         __threadfence();
         if (atomicAdd(wp.sched + 1, 1u) == (gridDim.x << 3) - 1u) { wp.sched[0] = 0u; wp.sched[1] = 0u; __threadfence(); }
+    }
+    if (stats) {
+        flush_stats(stats, STAT_QUERIES, ct.queries);
+        flush_stats(stats, STAT_RAYS, primaries);
+        flush_stats(stats, STAT_SPHERE_TESTS, ct.tests);
+        flush_stats(stats, STAT_AABB_TESTS, ct.boxes);
+    }
+}
+
+// Pass 2 of a two-pass Algorithm-A frame (FP32): the listed tiles x the samples of the launch are (tile, sample) units
+// pulled by every warp of the device from a counter; a unit traces ONE sample of the tile's 32 pixels and adds
+// (r, g, b, 1) to the pixel with one 16-byte reduction (sums of integer-valued colours are exact in FP32, so the frame
+// does not depend on the order; the API only selects this schedule when background and miss colour are integers).
+// A frame whose spheres cover 1 % of the view had all its work in the few warps that own those tiles -- the frame took
+// as long as ONE warp needs for 16 samples of a tile (~0.1 ms); spread over all warps it takes a fraction of that.
+template <int kMode>
+__global__ void __launch_bounds__(256, RT_WHITTED_MIN_BLOCKS) whitted_heavy_kernel(SceneDev<float> sc, WhittedDev<float> wp, float4 *accum,
+                                                                                  int *hit_out, unsigned long long *stats) {
+    using T = float;
+    RT_MODE_DECL;
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+    Counters ct = {0u, 0u, 0u};
+    unsigned primaries = 0;
+    const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
+    const unsigned ns = (unsigned)(wp.s1 - wp.s0);
+    const unsigned n_units = __ldcg(wp.sched + 2) * ns, first_dyn = (unsigned)gridDim.x << 3;     // pass 1 has finished (stream order)
+    for (unsigned unit = ((unsigned)blockIdx.x << 3) + (unsigned)w_; unit < n_units;) {
+        unsigned nxt = 0;
+        if (lane_ == 0) nxt = first_dyn + atomicAdd(wp.sched2, 1u);
+        const unsigned tu = wp.heavy[unit / ns];
+        const int s = wp.s0 + (int)(unit % ns);
+        const int tile = (int)(tu >> 3), wt = (int)(tu & 7u);
+        const int by = tile / wp.gx, bx = tile - by * wp.gx;
+        const int x = bx * 32 + (wt & 3) * 8 + (lane_ & 7);
+        const int y = wp.y0 + by * 8 + (wt >> 2) * 4 + (lane_ >> 3);
+        const unsigned long long cand = whitted_tile_candidates<T>(S, wp, x, y, lane_);
+        if (x < wp.W && y < wp.y1) {
+            T c[3];
+            const int last = whitted_sample<T, kBvh>(S, wp, cam, wp.X[x], wp.Y[y], (uint32_t)(y * wp.W + x), s, cand, ct, c);
+            primaries++;
+            const size_t o = (size_t)y * wp.W + x;
+            RT_ASSERT(o < (size_t)wp.W * wp.H);
+            asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                         :: "l"(accum + o), "f"(c[0]), "f"(c[1]), "f"(c[2]), "f"(1.f) : "memory");
+            if (hit_out && s == wp.s1 - 1) hit_out[o] = last;
+        }
+        unit = __shfl_sync(0xffffffffu, nxt, 0);
+    }
+    if (lane_ == 0) {
+        __threadfence();
+        if (atomicAdd(wp.sched2 + 1, 1u) == (gridDim.x << 3) - 1u) {      // last warp: re-arm both passes' counters
+            wp.sched2[0] = 0u; wp.sched2[1] = 0u; wp.sched[2] = 0u; __threadfence();
+        }
     }
     if (stats) {
         flush_stats(stats, STAT_QUERIES, ct.queries);
@@ -1310,18 +1388,32 @@ template <typename K> static unsigned persistent_ctas(K kernel, size_t smem_byte
 
 template <typename T>
 cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
-                           unsigned long long *stats, cudaStream_t st, unsigned *sched) {
+                           unsigned long long *stats, cudaStream_t st, unsigned *sched, unsigned *sched2, unsigned *heavy) {
     const int rows = wp.y1 - wp.y0;
     if (rows <= 0 || wp.W <= 0) return cudaSuccess;
     WhittedDev<T> wl = wp;                                        // + the 32x8 block grid the persistent warps walk
     wl.gx = (wp.W + 31) / 32; wl.gy = (rows + 7) / 8;
-    wl.sched = sched;
+    wl.sched = sched; wl.sched2 = sched2; wl.heavy = heavy; wl.split = 0;
     const long long blocks = (long long)wl.gx * wl.gy;
     dim3 grid(1), block(256);
     using v4 = typename M<T>::v4;
     const int mode = mode_for(sc);
     const size_t sm = mode != 2 ? smem_for(sc) : 0;
     cudaError_t e = cudaSuccess;
+    if constexpr (sizeof(T) == 4) {
+        // two-pass schedule: small brute-force scenes (the candidate lists need <= 64 spheres), a few samples per pixel
+        if (mode == 0 && sched2 && heavy && sc.n <= 64 && wp.s1 - wp.s0 >= 4) {
+            wl.split = 1;
+            e = allow_smem(whitted_kernel<T, 0>, sm); if (e != cudaSuccess) return e;
+            e = allow_smem(whitted_heavy_kernel<0>, sm); if (e != cudaSuccess) return e;
+            grid.x = persistent_ctas(whitted_kernel<T, 0>, sm, blocks);
+            whitted_kernel<T, 0><<<grid, block, sm, st>>>(sc, wl, (v4 *)accum, hit, stats);
+            e = cudaGetLastError(); if (e != cudaSuccess) return e;
+            grid.x = persistent_ctas(whitted_heavy_kernel<0>, sm, blocks * 8);
+            whitted_heavy_kernel<0><<<grid, block, sm, st>>>(sc, wl, (float4 *)accum, hit, stats);
+            return cudaGetLastError();
+        }
+    }
     switch (mode) {
         case 0: e = allow_smem(whitted_kernel<T, 0>, sm); if (e != cudaSuccess) return e;
                 grid.x = persistent_ctas(whitted_kernel<T, 0>, sm, blocks);
@@ -1485,7 +1577,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
 
 #define RT_INSTANTIATE_LAUNCHERS(T)                                                                                     \
     template cudaError_t launch_whitted<T>(const SceneDev<T> &, const WhittedDev<T> &, void *, int *,                   \
-                                           unsigned long long *, cudaStream_t, unsigned *);                             \
+                                           unsigned long long *, cudaStream_t, unsigned *, unsigned *, unsigned *);     \
     template cudaError_t launch_path<T>(const SceneDev<T> &, const PathDev<T> &, void *, unsigned long long *,          \
                                         cudaStream_t, const PkConst *, unsigned *);                                     \
     template cudaError_t launch_resolve<T>(const void *, int, int, int, int, float *, cudaStream_t);                    \

@@ -15,7 +15,12 @@ template <typename T> struct WhittedDev {
     uint32_t k0, k1;             // Philox key
     int prenorm, accumulate;
     int gx, gy;                  // 32x8-pixel block grid of the launch (set by launch_whitted)
-    unsigned *sched;             // {next warp tile, warps done}: zero between launches (self-resetting)
+    unsigned *sched;             // {next warp tile, warps done, heavy tiles, -}: zero between launches (self-resetting)
+    // two-pass frames (FP32, small scenes, >= 4 samples): pass 1 fills the sky tiles and LISTS the tiles whose cone of
+    // camera rays can touch a sphere; pass 2 spreads (listed tile, sample) units over all warps of the device
+    int split;
+    unsigned *heavy;             // [gx * gy * 8] warp-tile indices listed by pass 1
+    unsigned *sched2;            // pass 2: {next unit, warps done}
 };
 
 // Algorithm B frame (rt_path_params)
@@ -81,7 +86,10 @@ template <typename T> struct EnvDev {
 
 template <typename T>
 cudaError_t launch_whitted(const SceneDev<T> &sc, const WhittedDev<T> &wp, void *accum, int *hit,
-                           unsigned long long *stats, cudaStream_t st, unsigned *sched);
+                           unsigned long long *stats, cudaStream_t st, unsigned *sched, unsigned *sched2 = nullptr,
+                           unsigned *heavy = nullptr);
+// sched2 / heavy non-NULL: the caller allows the two-pass schedule (exact only for integer-valued colours: it adds the
+// samples of a pixel with FP32 reductions in no fixed order)
 template <typename T>
 cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum, unsigned long long *stats,
                         cudaStream_t st, const PkConst *pkc, unsigned *sched);

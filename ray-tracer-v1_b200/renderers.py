@@ -134,6 +134,19 @@ class TraditionalRenderer:
         return flatten_scene(self.scene, background_colour=Colour(2, 2, 5), light_sources=self.light_sources,
                              small_lights=self.small_lights)
 
+    def generate_camera_ray(self, x, y, sample_x=0.5, sample_y=0.5):
+        """The camera ray of pixel (x, y) at sub-pixel position (sample_x, sample_y) as the reference builds it
+        (FB/fb_vs_traditional_chandelier.py:417-429: the aspect ratio enters the x coordinate TWICE) -> ``Ray``.
+        ``render`` generates the same rays on the device (``path_camera_ray``); needs ``set_render_settings`` first."""
+        from .ray import Ray
+        half_height = np.tan(np.radians(self.fov) / 2)
+        half_width = half_height * self.aspect_ratio
+        ndc_x = (x + sample_x) / self.image_width
+        ndc_y = (y + sample_y) / self.image_height
+        screen_x = (2 * ndc_x - 1) * self.aspect_ratio * half_width
+        screen_y = (1 - 2 * ndc_y) * half_height
+        return Ray(self.camera_position, Vector(screen_x, screen_y, -1).normalise())
+
     def render(self, width=200, height=150, samples_per_pixel=4, max_bounces=3):
         self.set_render_settings(width, height, max_bounces, samples_per_pixel)
         self.stats = {k: 0 for k in self.stats}
@@ -197,6 +210,31 @@ class CustomSceneExperiment:
                           max_angle=np.radians(90), func=0)]
         pl = [PointLight(id=sun.id, position=sun.centre, colour=sun.colour, strength=1, max_angle=np.radians(90), func=-1)]
         return flatten_scene(spheres, gl, pl, Colour(2, 2, 5))
+
+    def _trace_custom_traditional(self, ray, spheres, scene_id=None):
+        """One ray through the traditional path (RL/output5.py:535-607) -> (Colour, stats, strategies): the sun id 7 is
+        swapped for the id-0 sun, ``ray.nearestSphereIntersect(all_spheres, max_bounces=config['max_bounces'])`` then
+        ``terminalRGB`` with the fixed light set -- both evaluated on the GPU (batches of one through ``rt_trace_rays`` /
+        ``rt_terminal_rgb``, FP64 parity build).  The reference's except-branch (a heuristic "enhanced" tracer, SURVEY
+        section 2 row 12) is outside the hot path: errors propagate instead."""
+        stats = {'reward': 0, 'light_hits': 0, 'steps': 0}
+        strategies = ['traditional_mimic']
+        sun = Sphere(id=0, centre=Vector(-0.6, 0.2, 6), radius=0.1, material=Material(emitive=True),
+                     colour=Colour(255, 255, 204))
+        all_spheres = [s for s in spheres if not (hasattr(s, 'id') and s.id == 7)]
+        all_spheres.append(sun)
+        gl = [GlobalLight(vector=Vector(3, 1, -0.75), colour=Colour(20, 20, 255), strength=1, max_angle=np.radians(90), func=0)]
+        pl = [PointLight(id=sun.id, position=sun.centre, colour=sun.colour, strength=1, max_angle=np.radians(90), func=-1)]
+        background_colour = Colour(2, 2, 5)
+        terminal = ray.nearestSphereIntersect(all_spheres, max_bounces=self.config['max_bounces'])
+        if terminal is None:
+            return background_colour, stats, strategies
+        color = terminal.terminalRGB(spheres=all_spheres, background_colour=background_colour, global_light_sources=gl,
+                                     point_light_sources=pl)
+        if (color.r + color.g + color.b) / 3 > 10:
+            stats['light_hits'] = 1
+            stats['reward'] = 10.0
+        return color, stats, strategies
 
     def render_true_original(self, scene_spheres, save_path=None):
         """601x601 notebook grid, depth 5, direction NOT pre-normalised (RL/output5.py:416-533) -> image."""

@@ -187,6 +187,14 @@ def test_render_entry_points(rt, orc):
         exp32.config.update(image_width=320, image_height=240, samples_per_pixel=1, max_bounces=1)
         _, img32 = exp32.render_custom_scene(scenes.build_balls_in_space(as_rendered=False).spheres, "traditional", None)
         gate("render entry FP32 pixels beyond 1/255", (np.abs(img32 - z["image"]).max(axis=2) > 1.001 / 255).mean(), 1e-4)      # measured 0
+        # the scalar helper behind the frame (RL/output5.py:535-607): the same pixels of the reference's image, one ray each
+        from ray_tracer_v1_b200 import Ray
+        balls = scenes.build_balls_in_space(as_rendered=False).spheres
+        for (yi, xi) in ((120, 160), (60, 100), (200, 250), (10, 10), (150, 40)):
+            ray = Ray(Vector(0, 0, 1), Vector(float(z["X"][xi]), float(z["Y"][yi]), -1).normalise())
+            colour, stats, strategies = exp._trace_custom_traditional(ray, balls, 0)
+            assert colour.getList() == [float(v) for v in z["rgb"][yi, xi]] and strategies == ['traditional_mimic']
+            assert stats['light_hits'] == int(sum(colour.getList()) / 3 > 10)
         # render_true_original: 601x601 notebook grid; compare its centre crop rows with the 121-grid golden's geometry
         full = exp.render_true_original(scenes.build_balls_in_space(as_rendered=False).spheres, None)
         assert full.shape == (601, 601, 3) and full.max() <= 1.0 and full.min() >= 0.0
@@ -201,6 +209,11 @@ def test_render_entry_points(rt, orc):
     sums, st = orc.render_path(r.flat_scene(), (0, 2, 0), 64, 36, 3, 8, 0.0, seed=5)
     assert np.array_equal(img, orc.resolve(sums, 3))
     assert r.stats["total_rays"] == st["total_rays"] and r.stats["light_hits"] == st["light_hits"]
+    # generate_camera_ray: the reference's camera (aspect applied twice on x), same direction as the device generates
+    ray = r.generate_camera_ray(10, 20, 0.5, 0.5)
+    hh = np.tan(np.radians(60) / 2)
+    d = np.array([(2 * 10.5 / 64 - 1) * (64 / 36) * hh * (64 / 36), (1 - 2 * 20.5 / 36) * hh, -1.0])
+    np.testing.assert_allclose(ray.D.getXYZ(), d / np.linalg.norm(d), rtol=1e-12)
     assert r.stats["rays_per_second"] > 0 and set(r.stats) == {'total_rays', 'total_intersections', 'light_hits',
                                                               'small_light_hits', 'render_time', 'rays_per_second'}
     spec.spheres[10].centre = Vector(0.3, 3.0, 7.0)          # scenes are mutable: the next render must see the change

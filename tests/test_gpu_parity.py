@@ -804,3 +804,58 @@ def test_concurrent_launches_are_deterministic(nat):
         first = out if first is None else first
         assert torch.equal(out, first)
     sb.close(); sc.close()
+
+
+def test_two_pass_whitted_frames_equal_single_pass(nat):
+    """Algorithm-A frames of >= 4 samples take the two-pass schedule (pass 1 fills the sky tiles and lists the others,
+    pass 2 spreads (tile, sample) units over the device and adds them with FP32 reductions).  With integer colours the
+    sums are exact, so the frame equals the single-pass frame (rows x sample ranges accumulated: no list, every pixel
+    traced by its own thread) bit for bit -- also with frames in flight on three streams at once, in accumulate mode,
+    and with a non-integer miss colour (which must fall back to the single pass)."""
+    import torch
+    from ray_tracer_v1_b200 import scenes, flatten_scene
+    for spec, W, H in ((scenes.build_planets2(), 640, 360), (scenes.build_marbles4(), 333, 187)):
+        fs = flatten_scene(spec.spheres, spec.global_lights, spec.point_lights, spec.background)
+        sc = nat.DeviceScene(fs)
+        k = 640 * spec.ray_step
+        X, Y = np.linspace(-k * 16 / 9, k * 16 / 9, W), np.linspace(k, -k, H)
+        miss = [spec.miss.r, spec.miss.g, spec.miss.b]
+        spp = 12
+        # single pass: sample ranges of fewer than 4 samples never split
+        single = torch.zeros((H, W, 4), dtype=torch.float32, device="cuda")
+        for i, s0 in enumerate(range(0, spp, 3)):
+            sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=8, samples=(s0, s0 + 3),
+                                                accumulate=i > 0), single, nat.F32)
+        st = torch.zeros(8, dtype=torch.int64, device="cuda")
+        st1 = torch.zeros(8, dtype=torch.int64, device="cuda")
+        sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=8, samples=(0, 3)), torch.zeros_like(single), nat.F32, stats=st1)
+        p = sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=8)
+        two = torch.zeros_like(single)
+        sc.render_whitted(p, two, nat.F32, stats=st)
+        torch.cuda.synchronize()
+        assert torch.equal(two, single)
+        assert int(st[0]) == W * H * spp and int(st1[0]) == W * H * 3
+        # frames in flight on three streams share nothing but the scene
+        streams = [torch.cuda.Stream() for _ in range(3)]
+        bufs = [torch.zeros_like(single) for _ in range(9)]
+        torch.cuda.synchronize()
+        for i, b in enumerate(bufs):
+            sc.render_whitted(p, b, nat.F32, stream=streams[i % 3].cuda_stream)
+        torch.cuda.synchronize()
+        assert all(torch.equal(b, single) for b in bufs)
+        # accumulate mode: two halves of the samples, both through the two-pass schedule
+        acc = torch.zeros_like(single)
+        sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=8, samples=(0, 6)), acc, nat.F32)
+        sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=8, samples=(6, 12), accumulate=True), acc, nat.F32)
+        torch.cuda.synchronize()
+        assert torch.equal(acc, single)
+        # non-integer miss colour: single pass, same per-pixel addition order as the sample-range reference
+        m2 = [miss[0] + 0.25, miss[1], miss[2]]
+        a = torch.zeros_like(single); b = torch.zeros_like(single)
+        sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=m2, seed=8), a, nat.F32)
+        for i, s0 in enumerate(range(0, spp, 3)):
+            sc.render_whitted(sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=m2, seed=8, samples=(s0, s0 + 3),
+                                                accumulate=i > 0), b, nat.F32)
+        torch.cuda.synchronize()
+        assert torch.allclose(a, b, rtol=1e-6, atol=1e-3)
+        sc.close()
