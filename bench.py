@@ -191,8 +191,8 @@ def _sum_over_ranks(torch, dist, world, values):
 def extras(torch, dist, rank, world, local, fused_ok, peak, reps=3):
     """Every BASELINE shape at this GPU count (north_star: 'throughput on synthetic scenes of each named shape is reported
     at 1, 2, 4 and 8 GPUs'), device-timed, max over ranks:
-      C3 tiles    the headline frame TILE-sharded (BASELINE config 3): fused stripes (path-kernel stores over NVLink) and
-                  contiguous bands + one NCCL gather
+      C3          the headline frame back to back (no flush): tile-sharded (BASELINE config 3) as fused stripes (path-kernel
+                  stores over NVLink) and as contiguous bands + one NCCL gather; sample-sharded (fused reduce-scatter / NCCL)
       C4          chandelier 1920x1080 64 spp, sample-range sharded (fused reduce-scatter; NCCL reduce beside it)
       C5          65,536 envs env-sharded (no collective): steady-state env-steps/s through rt_env_step_auto graph replay,
                   and each shard checked against the same rows of the unsharded batch
@@ -243,8 +243,8 @@ def extras(torch, dist, rank, world, local, fused_ok, peak, reps=3):
         return leg
 
     # ---- C3: the headline frame, tile-sharded
-    modes = [("tiles", "fused"), ("tiles", "nccl")] if world > 1 else [("tiles", "nccl")]
-    out["C3_complex_1920x1080_spp64_tiles"] = path_leg(scenes.build_complex(), SPP, DEPTH, THRESHOLD, modes)
+    modes = [("tiles", "fused"), ("tiles", "nccl"), ("samples", "fused"), ("samples", "nccl")] if world > 1 else [("tiles", "nccl")]
+    out["C3_complex_1920x1080_spp64"] = path_leg(scenes.build_complex(), SPP, DEPTH, THRESHOLD, modes)
     # ---- C4: chandelier, sample-range sharded
     modes = [("samples", "fused"), ("samples", "nccl")] if world > 1 else [("samples", "nccl")]
     out["C4_chandelier_1920x1080_spp64_samples"] = path_leg(scenes.build_chandelier(), 64, 8, 0.0, modes)
@@ -344,8 +344,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="auto", choices=["auto", "tiles", "samples"],
-                    help="auto: tiles at N=1 (one band = the frame), sample ranges at N>1 (every rank works on every pixel: "
-                         "perfect load balance); the tile split is timed beside it under extra")
+                    help="auto = tiles: at N=1 one band is the frame; at N>1 every rank renders interleaved 8-row stripes "
+                         "(BASELINE config 3 is tile-sharded); the sample-range split is timed beside it under extra")
     ap.add_argument("--collective", default="fused", choices=["fused", "nccl", "chain"],
                     help="N>1: fused = ONE path-kernel launch per rank and frame, its stores/reductions and the epoch protocol "
                          "over NVLink peer memory; chain = the round-1 launch chain around the kernel; nccl = gather/reduce")
@@ -357,7 +357,7 @@ def main():
         return run_reference_arm(args)
     args.warmup = max(args.warmup, 3)
     if args.mode == "auto":
-        args.mode = "tiles" if int(os.environ.get("WORLD_SIZE", "1")) == 1 else "samples"
+        args.mode = "tiles"          # BASELINE config 3: "tile-sharded at 2/4/8 GPUs" (the sample split is timed under extra)
 
     import torch
     import torch.distributed as dist
@@ -421,8 +421,9 @@ def main():
     launches = 0
     barrier()
     for i in range(args.steps):
+        # L2 flush between the timed steps (untimed: outside the step's event pair).  The K steps are bracketed by a
+        # barrier + synchronize on both sides, not individually: inside, the frame protocol itself keeps the ranks together
         flush.zero_()
-        barrier()
         ev[i][0].record()
         # the step, with the dominant kernel bracketed separately for the roofline
         if fused:
@@ -570,7 +571,10 @@ def main():
                 barrier()
                 res[name] = _max_over_ranks(torch, dist, world, [a.elapsed_time(b) / 5])[0]
             # NVLink payload of the fused sample reduce: every pixel's (r, g, b, n) goes to its owner as one 16-byte red
-            res["nvlink_bytes_per_frame"] = int(W * H * 16 * (world - 1)) if args.mode == "samples" else int(W * H * 12 * (world - 1) / world)
+            # NVLink payload per frame: samples = every rank's (r,g,b,n) of every pixel to its owner (one 16-byte red each)
+            # + the resolved bands to rank 0; tiles = the resolved float32 stripes of ranks 1.. to rank 0
+            res["nvlink_bytes_per_frame"] = int(W * H * 16 * (world - 1) + W * H * 12 * (world - 1) / world) if args.mode == "samples" \
+                else int(W * H * 12 * (world - 1) / world)
             extra["C3_fused_protocol"] = res
 
     if rank == 0:

@@ -160,8 +160,26 @@ def bench_env(name, spec, flavour, B, W, H, fov, depth, cam, reps, cpu_B):
     a.record(); busy(200); b.record()
     torch.cuda.synchronize()
     t = a.elapsed_time(b)
+    out["steady_state_two_launches"] = {"us_per_step_with_auto_reset": 1e3 * t / 200, "env_steps_per_s": B * 200 / (t * 1e-3)}
+    # the same steady state through rt_env_step_auto: step + restart of the finished episodes in ONE launch, replayed from
+    # a CUDA graph, actions written in place
+    env.reset(seed=1)
+    for k in range(20):
+        env.step_auto(acts[k % len(acts)])
+    env.actions.copy_(acts[0])
+    for k in range(10):
+        env.step_auto(None, graph=True)
+    torch.cuda.synchronize()
+    env.stats.zero_()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for k in range(200):
+        env.step_auto(None, graph=True)
+    b.record()
+    torch.cuda.synchronize()
+    t = a.elapsed_time(b)
     out["steady_state"] = {"us_per_step_with_auto_reset": 1e3 * t / 200, "env_steps_per_s": B * 200 / (t * 1e-3),
-                           "Mrays_per_s": int(env.stats.cpu()[4]) / t / 1e3}
+                           "Mrays_per_s": int(env.stats.cpu()[4]) / t / 1e3, "launches_per_step": 1}
     env.close()
     if cpu_B:
         from oracle import oracle as orc
