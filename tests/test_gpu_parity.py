@@ -519,6 +519,55 @@ def test_single_launch_frame_protocol(nat, mode):
     sc.close()
 
 
+def test_frame_buffer_is_not_reused_before_its_consumer_ran(nat):
+    """ADVICE r1 (distributed.py): in tile mode a peer could start frame e + 2 -- which stores into the image buffer of
+    frame e -- before rank 0's consumer of frame e had run.  The "consumed" signal is now published by rank 0's NEXT
+    launch on its stream, i.e. after whatever the caller queued on the image.  Here rank 0's stream sleeps 40 ms and only
+    then copies frame e out, while the peers' launches of frames e + 1 and e + 2 are already queued on their streams: the
+    copy must still be frame e."""
+    import torch
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import scenes
+    spec = scenes.build_complex()
+    fs = pkg.flatten_scene(spec.spheres, background_colour=spec.background)
+    sc = nat.DeviceScene(fs)
+    W, H, spp, world = 256, 144, 4, 3
+    dev = torch.device("cuda", 0)
+    images = [torch.zeros((H, W, 3), dtype=torch.float32, device=dev) for _ in (0, 1)]
+    flags = [torch.zeros(nat.FLAG_WORDS, dtype=torch.int32, device=dev) for _ in range(world)]
+    timed_out = torch.zeros(1, dtype=torch.int32, device=dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    refs = {e: sc.render_path_host(sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=300 + e), nat.F32)[0] for e in range(1, 5)}
+    snaps = {}
+    torch.cuda.synchronize()
+
+    def launch(rank, e):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step = nat.SINK_IMAGE, rank, world
+        sink.world, sink.rank, sink.sync, sink.epoch = world, rank, 1, e
+        sink.go_epoch = e - 1 if rank == 0 else 0
+        sink.image = images[e & 1].data_ptr()
+        sink.timed_out, sink.timeout_ms, sink.max_ctas = timed_out.data_ptr(), 8000, 148
+        for k in range(world):
+            sink.flags[k] = flags[k].data_ptr()
+        sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=300 + e), sink, stream=streams[rank].cuda_stream)
+
+    for rank in (1, 2):                      # the peers queue all four frames at once
+        for e in range(1, 5):
+            launch(rank, e)
+    cycles = int(0.04 * 1.9e9)
+    for e in range(1, 5):                    # rank 0: frame, a slow consumer, then the next frame
+        launch(0, e)
+        with torch.cuda.stream(streams[0]):
+            torch.cuda._sleep(cycles)
+            snaps[e] = images[e & 1].clone()
+    torch.cuda.synchronize()
+    assert int(timed_out.item()) == 0
+    for e in range(1, 5):
+        assert np.array_equal(snaps[e].cpu().numpy(), refs[e]), f"frame {e} was overwritten before its consumer ran"
+    sc.close()
+
+
 def test_sample_split_gives_the_same_frame(nat):
     """ksplit: 1..32 lanes sharing a pixel's samples (butterfly-summed) render the frame of one thread per pixel, for
     ragged sizes, row bands, sample ranges that do not divide by k, both schedules and the image sink."""
