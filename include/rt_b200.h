@@ -296,7 +296,9 @@ typedef struct rt_path_sink {
  *            and the last CTA sets done[rank] on rank 0
  *   collect  rank 0 only: the launch ends after done[0..world) have reached the epoch, i.e. kernel completion = frame
  *            complete in `image`.
- * The launches of all ranks must be able to run concurrently (one per GPU; tests: max_ctas). */
+ * The launches of all ranks must be able to run concurrently (one per GPU; tests: max_ctas).  When several ranks share
+ * ONE device (tests), a launch that waits on a flag must be issued after the launch that sets it: streams of a process
+ * share hardware queues, and a kernel issued later can be held behind a spinning one. */
 /* FP32 product path only.  p->y0/y1 are ignored for RT_SINK_IMAGE (the tiles say which rows); p->s0/s1 must be the
  * full [0, spp) range there. */
 int rt_render_path_sink(rt_scene *scene, const rt_path_params *p, const rt_path_sink *sink, uint64_t *stats_dev,

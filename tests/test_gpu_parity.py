@@ -552,15 +552,22 @@ def test_frame_buffer_is_not_reused_before_its_consumer_ran(nat):
             sink.flags[k] = flags[k].data_ptr()
         sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 5, 0.9, seed=300 + e), sink, stream=streams[rank].cuda_stream)
 
-    for rank in (1, 2):                      # the peers queue all four frames at once
-        for e in range(1, 5):
-            launch(rank, e)
+    # Issue order matters on ONE device: a launch that spins on a flag must have been issued AFTER the launch that will
+    # set it (streams of one process share hardware queues, a later-issued kernel can be held behind a spinning one).
+    # Across GPUs -- the real deployment -- every rank has its own queues and this constraint does not exist.
     cycles = int(0.04 * 1.9e9)
-    for e in range(1, 5):                    # rank 0: frame, a slow consumer, then the next frame
-        launch(0, e)
-        with torch.cuda.stream(streams[0]):
+    for rank in (1, 2):
+        launch(rank, 1); launch(rank, 2)
+    launch(0, 1)
+    for e in range(1, 5):
+        with torch.cuda.stream(streams[0]):  # rank 0: a slow consumer of frame e ...
             torch.cuda._sleep(cycles)
             snaps[e] = images[e & 1].clone()
+        if e + 1 <= 4:
+            launch(0, e + 1)                 # ... then its next frame, whose prologue publishes "frame e consumed"
+        if e + 2 <= 4:
+            for rank in (1, 2):
+                launch(rank, e + 2)          # the peers' frame e + 2 (same buffer as e) is queued while the consumer sleeps
     torch.cuda.synchronize()
     assert int(timed_out.item()) == 0
     for e in range(1, 5):
