@@ -174,6 +174,14 @@ typedef struct rt_path_params {
  * [5] sphere tests, [6] AABB tests (LBVH only). */
 int rt_render_path(rt_scene *scene, int precision, const rt_path_params *p, void *accum_dev, uint64_t *stats_dev,
                    void *stream);
+/* TraditionalRenderer.trace_ray_traditional(ray, bounce_count) (FB/fb_vs_traditional_chandelier.py:431-521) for n
+ * explicit rays at once: rays_dev [n,6] doubles = origin, direction AS GIVEN (Ray() has normalised it); the path starts
+ * at recursion depth bounce_count (a call with bounce_count >= max_bounces returns (2,2,5)); ray i draws its bounce
+ * directions from the Philox stream of pixel ray_ids_dev[i] (NULL: i) and sample s, so a camera ray generated on the
+ * host reproduces the frame's sample exactly.  accum_dev [n,4] as rt_render_path (sum over samples [s0,s1) + count).
+ * p->cam / W / H / fov / y0 / y1 are ignored. */
+int rt_trace_paths(rt_scene *scene, int precision, const rt_path_params *p, int32_t n, const double *rays_dev,
+                   const int32_t *ray_ids_dev, int32_t bounce_count, void *accum_dev, uint64_t *stats_dev, void *stream);
 
 /* accum [H,W,4] -> image [H,W,3] float32 = min(1, floor(sum/spp)/255) (chandelier.py:540-549; output5.py:1500-1512).
  * rows [y0,y1) only. */

@@ -119,6 +119,7 @@ SIGNATURES = {
     "rt_terminal_rgb": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, vp, vp]),
     "rt_render_whitted": (C.c_int, [vp, C.c_int, C.POINTER(WhittedParams), vp, vp, vp, vp]),
     "rt_render_path": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), vp, vp, vp]),
+    "rt_trace_paths": (C.c_int, [vp, C.c_int, C.POINTER(PathParams), C.c_int32, vp, vp, C.c_int32, vp, vp, vp]),
     "rt_resolve": (C.c_int, [C.c_int, C.c_int, vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, vp]),
     "rt_wf_create": (C.c_int, [vp, C.c_int, C.c_int32, C.c_int32, C.POINTER(vp)]),
     "rt_wf_destroy": (C.c_int, [vp]),
@@ -426,6 +427,21 @@ class DeviceScene:
 
     def render_path(self, params, accum, precision=F32, stats=None, stream=None):
         check(lib().rt_render_path(self.handle, precision, C.byref(params), _ptr(accum), _ptr(stats), stream))
+
+    def trace_paths(self, rays, max_bounces, mirror_threshold, bounce_count=0, seed=0, ray_ids=None, samples=(0, 1),
+                    precision=F64):
+        """``trace_ray_traditional(ray, bounce_count)`` for explicit rays [m,6] (origin, unit direction) ->
+        (sums [m,4] = r, g, b summed over the sample range + count, stats u64[8])."""
+        rays = _d(rays).reshape(-1, 6)
+        m = rays.shape[0]
+        r = DeviceBuffer.from_host(rays, np.float64, self.device)
+        ids = None if ray_ids is None else DeviceBuffer.from_host(np.asarray(ray_ids).reshape(m), np.int32, self.device)
+        ft = np.float64 if precision == F64 else np.float32
+        acc = DeviceBuffer((m, 4), ft, self.device)
+        st = DeviceBuffer(8, np.uint64, self.device)
+        p = self.path_params((0, 0, 0), max(m, 1), 1, samples[1], max_bounces, mirror_threshold, seed=seed, samples=samples)
+        check(lib().rt_trace_paths(self.handle, precision, C.byref(p), m, r.ptr, _ptr(ids), int(bounce_count), acc.ptr, st.ptr, None))
+        return acc.download(), st.download()
 
     def render_path_sink(self, params, sink, stats=None, stream=None):
         """FP32 path kernel with a fused multi-GPU sink (``PathSink``: image store / scatter-add over peer memory)."""

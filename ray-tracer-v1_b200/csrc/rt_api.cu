@@ -610,11 +610,14 @@ RT_EXPORT int rt_render_whitted(rt_scene *scene, int precision, const rt_whitted
 }
 
 // ------------------------------------------------------------------ Algorithm B frame
+struct ExplicitRays { const double *rays; const int32_t *ids; int depth0; };
+
 template <typename T>
 static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_path_params *p, void *accum, uint64_t *stats,
-                         cudaStream_t st, const rt_path_sink *sink = nullptr) {
+                         cudaStream_t st, const rt_path_sink *sink = nullptr, const ExplicitRays *xr = nullptr) {
     PathDev<T> pp;
     std::memset(&pp, 0, sizeof pp);
+    if (xr) { pp.rays = xr->rays; pp.ray_ids = xr->ids; pp.depth0 = xr->depth0; }
     pp.cam[0] = (T)p->cam[0]; pp.cam[1] = (T)p->cam[1]; pp.cam[2] = (T)p->cam[2];
     pp.W = p->W; pp.H = p->H; pp.y0 = p->y0; pp.y1 = p->y1; pp.s0 = p->s0; pp.s1 = p->s1; pp.max_bounces = p->max_bounces;
     // chandelier.py:412-415: aspect = W/H; half_height = tan(radians(fov)/2); half_width = half_height*aspect
@@ -680,7 +683,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     // sample split (automatic): k lanes per pixel so that a lane keeps about 8 samples -- measured best at 8, 16, 32 and
     // 64 samples per launch (k = 1, 2, 4, 8: tighter camera-ray cones against per-unit overhead) -- and, for small frames,
     // more lanes per pixel until there are ~4 warp tiles per resident warp (every lane keeps >= 2 samples)
-    if (pp.int_fold && p->ksplit != 0) {
+    if (pp.int_fold && p->ksplit != 0 && !xr) {
         static int sm_cache[64] = {0};
         int sms = sc->device >= 0 && sc->device < 64 ? sm_cache[sc->device] : 0;
         if (sms == 0) {
@@ -704,7 +707,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
     unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);      // {next unit, warps done, CTAs resolved, -}
     CU(launch_path<T>(view, pp, accum, reinterpret_cast<unsigned long long *>(stats), st,
-                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 && !(p->schedule & 4) ? &sc->pkc : nullptr, sched));
+                      sizeof(T) == 4 && sc->pkc_ok && view.bvh.nodes == 0 && !(p->schedule & 4) && !xr ? &sc->pkc : nullptr, sched));
     return RT_OK;
 }
 
@@ -717,6 +720,22 @@ RT_EXPORT int rt_render_path(rt_scene *scene, int precision, const rt_path_param
     CU(cudaSetDevice(scene->device));
     if (precision == RT_F64) return render_path_t<double>(scene, scene->d.view, p, accum_dev, stats_dev, S(stream));
     if (precision == RT_F32) return render_path_t<float>(scene, scene->f.view, p, accum_dev, stats_dev, S(stream));
+    return fail(RT_ERR_INVALID, "unknown precision");
+}
+
+RT_EXPORT int rt_trace_paths(rt_scene *scene, int precision, const rt_path_params *p, int32_t n, const double *rays_dev,
+                             const int32_t *ray_ids_dev, int32_t bounce_count, void *accum_dev, uint64_t *stats_dev, void *stream) {
+    if (!scene || !p || !accum_dev || (n > 0 && !rays_dev)) return fail(RT_ERR_INVALID, "NULL argument");
+    if (n < 0 || bounce_count < 0) return fail(RT_ERR_INVALID, "negative count");
+    if (n == 0) return RT_OK;
+    if (p->s0 < 0 || p->s0 > p->s1) return fail(RT_ERR_INVALID, "bad sample range");
+    if (p->max_bounces > RT_PATH_MAX_DEPTH) return fail(RT_ERR_UNSUPPORTED, "max_bounces above 32 is not supported by the path kernel");
+    CU(cudaSetDevice(scene->device));
+    rt_path_params q = *p;
+    q.W = n; q.H = 1; q.y0 = 0; q.y1 = 1; q.accumulate = 0;
+    const ExplicitRays xr = {rays_dev, ray_ids_dev, bounce_count};
+    if (precision == RT_F64) return render_path_t<double>(scene, scene->d.view, &q, accum_dev, stats_dev, S(stream), nullptr, &xr);
+    if (precision == RT_F32) return render_path_t<float>(scene, scene->f.view, &q, accum_dev, stats_dev, S(stream), nullptr, &xr);
     return fail(RT_ERR_INVALID, "unknown precision");
 }
 

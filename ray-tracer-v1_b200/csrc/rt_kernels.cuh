@@ -459,7 +459,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         cand = cone_candidates(S.g.sv.sph, S.g.sv.n, cam, d0, alpha, lane_);
     }
 
-    if (pp.max_bounces <= 0) {                        // degenerate: every call returns (2,2,5) at the depth check
+    bool none = pp.max_bounces <= 0;                  // degenerate: every call returns (2,2,5) at the depth check
+    if constexpr (kMode != 3) none = none || (pp.rays && pp.depth0 >= pp.max_bounces);
+    if (none) {
         const int mine = has_pixel ? (ns - sub + kk - 1) >> lk : 0;      // samples of this lane
         n_rays += (unsigned)mine;
         a0 = 2 * mine; a1 = 2 * mine; a2 = 5 * mine;
@@ -476,12 +478,24 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         auto start_sample = [&](int smp) {
             depth = 0; O = cam;
             leaf0 = 2; leaf1 = 2; leaf2 = 5; lf0 = 2.0; lf1 = 2.0; lf2 = 5.0; pend = true;
+            if constexpr (kMode != 3) {
+                if (pp.rays) {                        // explicit ray (rt_trace_paths): as given, from recursion depth depth0
+                    const double *r = pp.rays + 6 * (size_t)pixel;
+                    O = mk<T>(T(r[0]), T(r[1]), T(r[2])); D = mk<T>(T(r[3]), T(r[4]), T(r[5]));
+                    depth = pp.depth0;
+                    rng.begin(pp.ray_ids ? (uint32_t)pp.ray_ids[pixel] : pixel, (uint32_t)smp, pp.k0, pp.k1);
+                    n_rays++;
+                    return;
+                }
+            }
             rng.begin(pixel, (uint32_t)smp, pp.k0, pp.k1);
             uint32_t wa, wb;
             if (RT_PHILOX_RK) rng.pair_rk(0u, wa, wb, pp.rk); else rng.pair(0u, wa, wb);
             D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
             n_rays++;                                 // trace_ray_traditional call count, chandelier.py:432
         };
+        int fold_from = 0;                            // deepest-first fold stops at the level the path started on
+        if constexpr (kMode != 3) fold_from = pp.rays ? pp.depth0 : 0;
         if (alive) start_sample(s);
         first_trip = true;
         for (;;) {
@@ -565,11 +579,11 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     pend = false;
                     if constexpr (kIntFold) {
                         int c[3] = {leaf0, leaf1, leaf2};
-                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c);
+                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from);
                         a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                     } else {
                         double c[3] = {lf0, lf1, lf2};
-                        fold_path<T, kMode == 3>(S.g, st, depth, c);
+                        fold_path<T, kMode == 3>(S.g, st, depth, c, fold_from);
                         a0 += c[0]; a1 += c[1]; a2 += c[2];
                     }
                 }
@@ -583,11 +597,11 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 alive = false;
                 if constexpr (kIntFold) {
                     int c[3] = {leaf0, leaf1, leaf2};
-                    fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c);
+                    fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from);
                     a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                 } else {
                     double c[3] = {lf0, lf1, lf2};
-                    fold_path<T, kMode == 3>(S.g, st, depth, c);
+                    fold_path<T, kMode == 3>(S.g, st, depth, c, fold_from);
                     a0 += c[0]; a1 += c[1]; a2 += c[2];
                 }
                 if constexpr (kRegen) {

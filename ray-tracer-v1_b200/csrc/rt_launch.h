@@ -50,6 +50,12 @@ template <typename T> struct PathDev {
     int *timed_out;
     long long timeout_cycles;
     int max_ctas;
+    // explicit rays (rt_trace_paths: TraditionalRenderer.trace_ray_traditional(ray, bounce_count) for n rays at once):
+    // ray i = (origin, direction as given -- Ray() has normalised it) starts at recursion depth depth0 and draws from
+    // the Philox stream of pixel ray_ids[i] (or i).  W = n, H = 1.  Not available in the parameter-block kernel (kMode 3).
+    const double *rays;
+    const int *ray_ids;
+    int depth0;
 };
 
 // "Algorithm C" frame (rt_simple_params)

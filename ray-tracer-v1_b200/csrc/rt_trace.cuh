@@ -575,8 +575,8 @@ struct PathStack {
 // final = int(albedo * (min(255, direct + indirect) / 255.0)) per channel, folded from the leaf back to the camera
 // (chandelier.py:509-521).  Always evaluated in double: the truncation must see the reference's rounding.
 template <typename T, bool kPacked = false>
-RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[3]) {
-    for (int k = depth - 1; k >= 0; --k) {
+RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[3], int k0 = 0) {
+    for (int k = depth - 1; k >= k0; --k) {
         const uint32_t d = st.direct[k];
         const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
         double t0 = (double)(d & 255u) + c[0], t1 = (double)((d >> 8) & 255u) + c[1], t2 = (double)((d >> 16) & 255u) + c[2];
@@ -592,9 +592,9 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
 // the division) and the running colour stays an int.  Still a double multiply: the truncation sees the same product.
 // kPacked: the level's sphere index rides in bits 24-31 of `direct` (scenes of <= 256 spheres), st.idx is not used.
 template <typename T, bool kPacked = false>
-RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3]) {
+RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3], int k0 = 0) {
     RT_ASSERT(depth >= 0 && depth <= RT_PATH_MAX_DEPTH);
-    for (int k = depth - 1; k >= 0; --k) {
+    for (int k = depth - 1; k >= k0; --k) {
         const uint32_t d = st.direct[k];
         RT_ASSERT((int)(kPacked ? (d >> 24) : st.idx[k]) < g.sv.n);
         const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];

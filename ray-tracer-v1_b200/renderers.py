@@ -134,6 +134,25 @@ class TraditionalRenderer:
         return flatten_scene(self.scene, background_colour=Colour(2, 2, 5), light_sources=self.light_sources,
                              small_lights=self.small_lights)
 
+    def trace_ray_traditional(self, ray, bounce_count=0, pixel=0, sample=0):
+        """One call of the reference's recursive tracer (FB/fb_vs_traditional_chandelier.py:431-521) -> ``Colour``: nearest
+        hit, unshadowed direct light from every light sphere, one mirror / cosine-weighted bounce per level, integer
+        truncation at every level -- on the GPU, a batch of one through ``rt_trace_paths`` (the frame kernel, fed an
+        explicit ray).  The reference draws its bounce directions from global ``np.random``; here they come from the
+        Philox stream of (``self.seed``; pixel, sample), the one ``render`` uses for that pixel sample, so
+        ``trace_ray_traditional(generate_camera_ray(x, y, .5 + jx, .5 + jy), pixel=y * W + x, sample=s)`` is exactly that
+        sample of the frame.  Updates ``stats`` like the reference's counters."""
+        seed = self.seed if self.seed is not None else 0
+        if self._ctx is None:
+            self._ctx = FrameContext(self.device)
+        sc = self._ctx.set_scene(self.flat_scene())
+        o, d = _xyz(ray.origin), _xyz(ray.D)
+        sums, st = sc.trace_paths([[*o, *d]], self.max_bounces, self.mirror_threshold, bounce_count=bounce_count, seed=seed,
+                                  ray_ids=[int(pixel)], samples=(int(sample), int(sample) + 1), precision=_precision(self.precision))
+        for i, k in enumerate(('total_rays', 'total_intersections', 'light_hits', 'small_light_hits')):
+            self.stats[k] = self.stats.get(k, 0) + int(st[i])
+        return Colour(float(sums[0, 0]), float(sums[0, 1]), float(sums[0, 2]))
+
     def generate_camera_ray(self, x, y, sample_x=0.5, sample_y=0.5):
         """The camera ray of pixel (x, y) at sub-pixel position (sample_x, sample_y) as the reference builds it
         (FB/fb_vs_traditional_chandelier.py:417-429: the aspect ratio enters the x coordinate TWICE) -> ``Ray``.

@@ -209,6 +209,17 @@ def test_render_entry_points(rt, orc):
     sums, st = orc.render_path(r.flat_scene(), (0, 2, 0), 64, 36, 3, 8, 0.0, seed=5)
     assert np.array_equal(img, orc.resolve(sums, 3))
     assert r.stats["total_rays"] == st["total_rays"] and r.stats["light_hits"] == st["light_hits"]
+    # trace_ray_traditional (the scalar recursive tracer, FB/fb_vs_traditional_chandelier.py:431-521) through
+    # rt_trace_paths: fed the camera ray of a pixel sample (jitter = the Philox numbers render() uses) it reproduces that
+    # sample, so the samples of a pixel add up to the frame's sum -- exactly, in the FP64 build
+    for (x, y) in ((10, 20), (33, 5), (63, 35), (0, 0)):
+        tot = np.zeros(3)
+        for smp in range(3):
+            u0, u1 = orc.rng_pair(5, y * 64 + x, smp, 0)
+            ray = r.generate_camera_ray(x, y, 0.5 + (u0 - 0.5), 0.5 + (u1 - 0.5))
+            tot += r.trace_ray_traditional(ray, 0, pixel=y * 64 + x, sample=smp).getList()
+        assert np.array_equal(tot, sums[y, x]), (x, y, tot, sums[y, x])
+    assert r.trace_ray_traditional(ray, bounce_count=8).getList() == [2.0, 2.0, 5.0]      # at the depth limit: Colour(2, 2, 5)
     # generate_camera_ray: the reference's camera (aspect applied twice on x), same direction as the device generates
     ray = r.generate_camera_ray(10, 20, 0.5, 0.5)
     hh = np.tan(np.radians(60) / 2)
