@@ -624,6 +624,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     const double aspect = (double)p->W / (double)p->H;
     const double half_h = std::tan((p->fov_deg * (M_PI / 180.0)) / 2), half_w = half_h * aspect;
     pp.aspect = (T)aspect; pp.half_w = (T)half_w; pp.half_h = (T)half_h;
+    pp.inv_W = (T)(1.0 / (double)p->W); pp.inv_H = (T)(1.0 / (double)p->H);
     pp.mirror_threshold = (T)p->mirror_threshold;
     pp.k0 = (uint32_t)p->seed; pp.k1 = (uint32_t)(p->seed >> 32);
     for (uint32_t r = 0; r < 10; ++r) { pp.rk[2 * r] = pp.k0 + r * 0x9E3779B9u; pp.rk[2 * r + 1] = pp.k1 + r * 0xBB67AE85u; }
@@ -962,6 +963,7 @@ static int wf_begin_t(rt_wavefront *wf, WaveDev<T> &w, PathDev<T> &pp, const rt_
     for (int k = 0; k < 3; ++k) { w.cam[k] = (T)p->cam[k]; pp.cam[k] = (T)p->cam[k]; }
     w.aspect = pp.aspect = (T)aspect; w.half_w = pp.half_w = (T)half_w; w.half_h = pp.half_h = (T)half_h;
     pp.W = p->W; pp.H = p->H;
+    pp.inv_W = (T)(1.0 / (double)p->W); pp.inv_H = (T)(1.0 / (double)p->H);
     w.mirror_threshold = (T)p->mirror_threshold; w.fb_prob = (T)fb_prob;
     w.k0 = (uint32_t)p->seed; w.k1 = (uint32_t)(p->seed >> 32);
     CU(launch_wf_begin<T>(w, pp, reinterpret_cast<unsigned long long *>(stats), st));

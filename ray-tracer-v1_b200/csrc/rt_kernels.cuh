@@ -332,11 +332,24 @@ RT_DEV bool a_count_ok(int spp_total) { return spp_total > 0; }
 #define RT_FLAG_DONE 16
 #define RT_FLAG_GO 32
 
+// explicit shared-memory loads off a 32-bit shared-window address (see path_kernel, kMode 3)
+RT_DEV float4 lds_v4(unsigned addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+template <int kStride> RT_DEV void lds_v4x2(unsigned addr, float4 &a, float4 &b) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr), "n"(kStride));
+}
+
 // ------------------------------------------------------------------ Algorithm B frame
 // TraditionalRenderer.generate_camera_ray (chandelier.py:417-429): aspect is applied twice on x.
 template <typename T> RT_DEV V3<T> path_camera_ray(const PathDev<T> &pp, int x, int y, T u0, T u1) {
     T sx = T(0.5) + (u0 - T(0.5)), sy = T(0.5) + (u1 - T(0.5));         // 0.5 + jitter, chandelier.py:534-536
-    T ndc_x = (T(x) + sx) / T(pp.W), ndc_y = (T(y) + sy) / T(pp.H);
+    T ndc_x, ndc_y;
+    if constexpr (M<T>::exact) { ndc_x = (T(x) + sx) / T(pp.W); ndc_y = (T(y) + sy) / T(pp.H); }
+    else { ndc_x = (T(x) + sx) * pp.inv_W; ndc_y = (T(y) + sy) * pp.inv_H; }      // two multiplies instead of two divisions
     T scx = T(2) * ndc_x - T(1), scy = T(1) - T(2) * ndc_y;
     scx *= pp.aspect; scx *= pp.half_w; scy *= pp.half_h;
     V3<T> d = normalise(mk<T>(scx, scy, T(-1)));
@@ -362,11 +375,17 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     Staged<T> S;
     double *div255;                                                    // [256] k / 255.0, correctly rounded
     const float4 *hitrec = nullptr;                                    // kMode 3: (1/r, reflective, emissive, -) per sphere
+    unsigned s_base = 0;                                               // kMode 3: shared-window address of the static block
     if constexpr (kMode == 3) {
         // <= RT_PKC_MAX spheres: STATIC shared arrays at fixed offsets, so every per-hit fetch is one LDS with an
         // immediate base (the dynamic layout costs ~8 address instructions per fetch, its offsets depend on n)
-        __shared__ __align__(16) float4 s_sph[RT_PKC_MAX], s_hit[RT_PKC_MAX], s_col[RT_PKC_MAX], s_cw[RT_PKC_MAX];
+        // ONE block (sph | hit | col | cw at 1 KB strides) read with explicit ld.shared off a 32-bit base kept in a
+        // register: the compiler's own addressing of static shared arrays re-derives the cluster window base (S2R
+        // CgaCtaId, MOV, IADD3, LEA) at every site, 6 instructions per winner fetch
+        __shared__ __align__(16) float4 s_all[4 * RT_PKC_MAX];
         __shared__ __align__(16) double s_div255[256];
+        float4 *const s_sph = s_all, *const s_hit = s_all + RT_PKC_MAX, *const s_col = s_all + 2 * RT_PKC_MAX, *const s_cw = s_all + 3 * RT_PKC_MAX;
+        s_base = (unsigned)__cvta_generic_to_shared(s_all);
         const int n_pad = (sc.n + 7) & ~7;
         const float *pkf = reinterpret_cast<const float *>(sc.pk);       // pair j: cx0 cx1 cy0 cy1 | cz0 cz1 w0 w1
         for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
@@ -522,7 +541,8 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) n_tests += (unsigned)__popcll(cand);
                     else n_tests += (unsigned)S.g.sv.n;
                     if (i >= 0) {
-                        const float4 w = S.g.sv.sph[i], hr = hitrec[i];
+                        float4 w, hr;
+                        lds_v4x2<16 * RT_PKC_MAX>(s_base + 16u * (unsigned)i, w, hr);      // (centre, r) and (1/r, reflective, emissive)
                         t = winner_distance(w, O, D);
                         centre = mk<T>(w.x, w.y, w.z); inv_r = hr.x;
                         m.x = hr.y; m.y = T(0); m.z = hr.z; m.w = T(1);
@@ -537,7 +557,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     if (m.z != T(0)) {                                               // emissive: its own colour
                         n_light++;
                         if (sc.small && sc.small[i]) n_small++;
-                        const typename M<T>::v4 col = S.g.sv.col[i];
+                        typename M<T>::v4 col;
+                        if constexpr (kMode == 3) col = lds_v4(s_base + 32u * RT_PKC_MAX + 16u * (unsigned)i);
+                        else col = S.g.sv.col[i];
                         if constexpr (kIntFold) { leaf0 = (int)col.x; leaf1 = (int)col.y; leaf2 = (int)col.z; }
                         else { lf0 = (double)col.x; lf1 = (double)col.y; lf2 = (double)col.z; }
                         ended = true;
@@ -559,6 +581,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                         if (!RT_SKIP_LAST_BOUNCE || !ended) {
                             const bool mirror = m.x > pp.mirror_threshold;
                             T r1 = T(0), r2 = T(0);
+                            // (measured: letting mirror lanes fill the two-slot Philox cache at even depths, so that they
+                            // need not recompute the block alone one trip later, gains 0.4 % on the complex scene and
+                            // LOSES 3.5 % on the chandelier, where most surfaces mirror and the rounds would run for nobody)
                             if (!mirror) {
                                 uint32_t wa, wb;
                                 if (RT_PHILOX_RK) rng.pair_rk((uint32_t)depth, wa, wb, pp.rk); else rng.pair((uint32_t)depth, wa, wb);
@@ -579,7 +604,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     pend = false;
                     if constexpr (kIntFold) {
                         int c[3] = {leaf0, leaf1, leaf2};
-                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from);
+                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from, s_base + 32u * RT_PKC_MAX);
                         a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                     } else {
                         double c[3] = {lf0, lf1, lf2};
@@ -597,7 +622,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 alive = false;
                 if constexpr (kIntFold) {
                     int c[3] = {leaf0, leaf1, leaf2};
-                    fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from);
+                    fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from, s_base + 32u * RT_PKC_MAX);
                     a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                 } else {
                     double c[3] = {lf0, lf1, lf2};

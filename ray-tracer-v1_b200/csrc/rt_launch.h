@@ -28,6 +28,7 @@ template <typename T> struct PathDev {
     T cam[3];
     int W, H, y0, y1, s0, s1, max_bounces;
     T aspect, half_w, half_h;    // W/H, tan(fov/2)*aspect, tan(fov/2)   (chandelier.py:412-415)
+    T inv_W, inv_H;              // product build: 1/W, 1/H (the parity build divides like the reference)
     T mirror_threshold;
     int gx, gy;                          // tile grid of the launch (set by launch_path)
     unsigned *sched;                     // {next work unit, warps done}: zero between launches (self-resetting)

@@ -592,12 +592,17 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
 // the division) and the running colour stays an int.  Still a double multiply: the truncation sees the same product.
 // kPacked: the level's sphere index rides in bits 24-31 of `direct` (scenes of <= 256 spheres), st.idx is not used.
 template <typename T, bool kPacked = false>
-RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3], int k0 = 0) {
+RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3], int k0 = 0,
+                          unsigned col_base = 0) {            // kPacked: shared-window address of the colour array
     RT_ASSERT(depth >= 0 && depth <= RT_PATH_MAX_DEPTH);
     for (int k = depth - 1; k >= k0; --k) {
         const uint32_t d = st.direct[k];
         RT_ASSERT((int)(kPacked ? (d >> 24) : st.idx[k]) < g.sv.n);
-        const typename M<T>::v4 col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
+        typename M<T>::v4 col;
+        if constexpr (kPacked && !M<T>::exact) {
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(col.x), "=f"(col.y), "=f"(col.z), "=f"(col.w)
+                         : "r"(col_base + 16u * (d >> 24)));
+        } else col = g.sv.col[kPacked ? (d >> 24) : st.idx[k]];
         const int t0 = min(255, (int)(d & 255u) + c[0]), t1 = min(255, (int)((d >> 8) & 255u) + c[1]),
                   t2 = min(255, (int)((d >> 16) & 255u) + c[2]);
         c[0] = __double2int_rz(__dmul_rn((double)col.x, div255[t0]));
