@@ -218,17 +218,22 @@ class CustomSceneExperiment:
             self._ctx = FrameContext(self.device)
         return self._ctx
 
-    @staticmethod
-    def _as_rendered(scene_spheres):
+    # the constants of RL/output5.py:447-486 / :543-578 (the reference rebuilds them on every call; their values never change)
+    _SUN = Sphere(id=0, centre=Vector(-0.6, 0.2, 6), radius=0.1, material=Material(emitive=True), colour=Colour(255, 255, 204))
+    _GLOBAL = [GlobalLight(vector=Vector(3, 1, -0.75), colour=Colour(20, 20, 255), strength=1, max_angle=np.radians(90), func=0)]
+    _POINT = [PointLight(id=0, position=Vector(-0.6, 0.2, 6), colour=Colour(255, 255, 204), strength=1,
+                         max_angle=np.radians(90), func=-1)]
+    _BACKGROUND = Colour(2, 2, 5)
+    _LIGHTS = None
+
+    @classmethod
+    def _as_rendered(cls, scene_spheres):
         """RL/output5.py:447-486 / :543-578: sun id 7 replaced by an id-0 sun appended last, fixed light set."""
-        sun = Sphere(id=0, centre=Vector(-0.6, 0.2, 6), radius=0.1, material=Material(emitive=True),
-                     colour=Colour(255, 255, 204))
         spheres = [s for s in scene_spheres if not (hasattr(s, 'id') and s.id == 7)]
-        spheres.append(sun)
-        gl = [GlobalLight(vector=Vector(3, 1, -0.75), colour=Colour(20, 20, 255), strength=1,
-                          max_angle=np.radians(90), func=0)]
-        pl = [PointLight(id=sun.id, position=sun.centre, colour=sun.colour, strength=1, max_angle=np.radians(90), func=-1)]
-        return flatten_scene(spheres, gl, pl, Colour(2, 2, 5))
+        spheres.append(cls._SUN)
+        if cls._LIGHTS is None:               # the constant light set, flattened once
+            cls._LIGHTS = flatten_scene([], cls._GLOBAL, cls._POINT, cls._BACKGROUND, path_lights=False)
+        return flatten_scene(spheres, path_lights=False, lights_like=cls._LIGHTS)
 
     def _trace_custom_traditional(self, ray, spheres, scene_id=None):
         """One ray through the traditional path (RL/output5.py:535-607) -> (Colour, stats, strategies): the sun id 7 is

@@ -66,7 +66,7 @@ class FlatScene:
 
 
 def flatten_scene(spheres, global_light_sources=None, point_light_sources=None, background_colour=None,
-                  light_sources=None, small_lights=None):
+                  light_sources=None, small_lights=None, path_lights=True, lights_like=None):
     """Flatten a scene graph.
 
     spheres               list of Sphere-like (``.centre .radius .material .colour .id``)
@@ -77,17 +77,31 @@ def flatten_scene(spheres, global_light_sources=None, point_light_sources=None, 
                           (``TraditionalRenderer.light_sources``); default = the emissive spheres, in scene
                           order, as the reference's drivers build it (FB/fb_vs_traditional_chandelier.py:801)
     small_lights          Algorithm B: spheres counted in ``small_light_hits``; default radius < 0.5 lights
+    lights_like           a FlatScene whose (already flattened) global / point light arrays and background are reused
+                          as they are: for callers whose lights are constants (the output5 entries)
+    path_lights           False: skip the Algorithm-B light arrays (callers that only run Algorithm A / the env; a
+                          sub-millisecond frame should not pay for them on every call)
     """
     spheres = list(spheres)
     n = len(spheres)
-    centre = np.array([_xyz(s.centre) for s in spheres], _F).reshape(n, 3)
-    radius = np.array([float(s.radius) for s in spheres], _F).reshape(n)
-    material = np.array([(float(s.material.reflective), float(s.material.transparent), float(s.material.emitive),
-                          float(s.material.refractive_index)) for s in spheres], _F).reshape(n, 4)
-    colour = np.array([_rgb(s.colour) for s in spheres], _F).reshape(n, 3)
+    # one pass over the objects, one array construction: this runs on EVERY render / reset (scenes are mutable lists)
+    rows = []
+    for s in spheres:
+        c, m, k = s.centre, s.material, s.colour
+        rows.append((c.x, c.y, c.z, s.radius, m.reflective, m.transparent, m.emitive, m.refractive_index, k.r, k.g, k.b))
+    a = np.array(rows, _F).reshape(n, 11)
+    centre = np.ascontiguousarray(a[:, 0:3])
+    radius = np.ascontiguousarray(a[:, 3])
+    material = np.ascontiguousarray(a[:, 4:8])
+    colour = np.ascontiguousarray(a[:, 8:11])
     ids = np.array([int(s.id) for s in spheres], _I).reshape(n)
     fs = FlatScene(centre, radius, material, colour, ids)
 
+    if lights_like is not None:
+        for name in ("g_vec", "g_col", "g_strength", "g_max_angle", "g_func", "p_id", "p_pos", "p_col", "p_strength",
+                     "p_max_angle", "p_func", "bg"):
+            setattr(fs, name, getattr(lights_like, name))
+        global_light_sources = point_light_sources = background_colour = None
     gl = list(global_light_sources or [])
     if gl:
         fs.g_vec = np.array([_xyz(g.vector) for g in gl], _F)
@@ -106,6 +120,9 @@ def flatten_scene(spheres, global_light_sources=None, point_light_sources=None, 
     if background_colour is not None:
         fs.bg = np.array(_rgb(background_colour), _F)
 
+    if not path_lights:
+        fs.small = np.zeros(n, np.uint8)
+        return fs
     if light_sources is None:
         light_sources = [s for s in spheres if s.material.emitive]
     light_sources = list(light_sources)
