@@ -14,6 +14,7 @@
 Every call re-flattens the scene (the reference's scenes are mutable lists) and uploads it; frames are rendered and
 resolved on the GPU and only the float32 image (plus, on request, the raw sums) comes back to the host.
 """
+import ctypes as C
 import time
 from pathlib import Path
 
@@ -332,6 +333,27 @@ class SimplifiedFBRenderer:
                              sun_col=self.sun_color.getList(), sun_id=7, max_bounces=self.max_bounces, seed=seed)
         return sc, p
 
+    def _render_frame(self, sc, p, width, height):
+        """One frame through ``rt_render_simple`` into buffers this renderer keeps (HBM rgb / image / stats + pinned host
+        copies): no allocation and one synchronisation per frame (``rt_render_simple_host`` allocates and frees four
+        device buffers per call, which cost more than the 400x300 frame itself)."""
+        L, dev = nat.lib(), self.device
+        if getattr(self, "_buf_key", None) != (width, height):
+            for b in getattr(self, "_bufs", ()):
+                b.free()
+            n = width * height
+            self._bufs = (nat.DeviceBuffer((n, 4), np.int32, dev), nat.DeviceBuffer((height, width, 3), np.float32, dev),
+                          nat.DeviceBuffer(8, np.uint64, dev), nat.PinnedArray((height, width, 3), np.float32),
+                          nat.PinnedArray(8, np.uint64))
+            self._buf_key = (width, height)
+        rgb, img, st, h_img, h_st = self._bufs
+        st.fill(0)
+        nat.check(L.rt_render_simple(sc.handle, _precision(self.precision), C.byref(p), rgb.ptr, img.ptr, st.ptr, None))
+        nat.check(L.rt_memcpy_d2h(dev, h_img.ptr, img.ptr, img.nbytes, None))
+        nat.check(L.rt_memcpy_d2h(dev, h_st.ptr, st.ptr, 64, None))
+        nat.check(L.rt_stream_sync(dev, None))
+        return h_img.array.copy(), h_st.array.copy()
+
     def trace_ray_simple(self, ray):
         """One ray -> accumulated ``Colour`` (output6.py:434-577); a batch of one through the same kernel."""
         sc, p = self._scene_and_params(1, 1)
@@ -349,7 +371,7 @@ class SimplifiedFBRenderer:
         self.stats = {'total_rays': 0, 'sun_hits': 0, 'fb_used': 0, 'fb_success': 0, 'render_time': 0}
         start = time.time()
         sc, p = self._scene_and_params(width, height)
-        image, _, st = sc.render_simple_host(p, _precision(self.precision))
+        image, st = self._render_frame(sc, p, width, height)
         self.stats['total_rays'], self.stats['sun_hits'] = int(st[0]), int(st[1])
         self.stats['render_time'] = time.time() - start
         if output_path:
