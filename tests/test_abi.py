@@ -3,6 +3,7 @@ include/rt_b200.h declares (no compute calls -- there is no GPU here), and fails
 import os
 import re
 
+import numpy as np
 import pytest
 
 from conftest import ROOT
@@ -59,3 +60,31 @@ def test_no_cpu_fallback(native):
                   for f in os.listdir(os.path.join(ROOT, "ray-tracer-v1_b200")) if f.endswith(".py"))
     assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "").replace("CPU oracle", ""), \
         "the product package must not import the oracle"
+
+
+def test_scene_descriptor_marshalling_is_faithful():
+    """make_desc packs the float64 / int32 arrays of a FlatScene into two buffers and hands the C ABI offsets into them:
+    every pointer must read back exactly the array it stands for, for scenes with and without lights, and the
+    cached-constant-lights path of the output5 entries must flatten to the same scene as the plain path."""
+    import ctypes as C
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import _native as native, scenes
+    from ray_tracer_v1_b200.renderers import CustomSceneExperiment
+    balls = scenes.build_balls_in_space(as_rendered=True)
+    plain = pkg.flatten_scene(balls.spheres, balls.global_lights, balls.point_lights, balls.background)
+    fast = CustomSceneExperiment._as_rendered(scenes.build_balls_in_space(as_rendered=False).spheres)
+    for name in native._DESC_F + native._DESC_I + ("bg",):
+        if not name.startswith("l_"):
+            assert np.array_equal(getattr(fast, name), getattr(plain, name)), name
+    cases = [plain, fast, pkg.flatten_scene(scenes.build_chandelier().spheres),
+             pkg.flatten_scene([], background_colour=balls.background)]
+    for fs in cases:
+        d, keep = native.make_desc(fs)
+        assert (d.n, d.nG, d.nP, d.nL) == (fs.radius.shape[0], fs.g_strength.shape[0], fs.p_strength.shape[0], fs.l_index.shape[0])
+        for names, ct, dt in ((native._DESC_F, C.c_double, np.float64), (native._DESC_I, C.c_int32, np.int32)):
+            for name in names:
+                want = np.ascontiguousarray(getattr(fs, name), dt).reshape(-1)
+                if want.size:
+                    got = np.ctypeslib.as_array(C.cast(getattr(d, name), C.POINTER(ct)), shape=(want.size,))
+                    assert np.array_equal(got, want), name
+        assert [d.bg[0], d.bg[1], d.bg[2]] == [float(v) for v in np.asarray(fs.bg).reshape(3)]
