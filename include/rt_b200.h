@@ -202,7 +202,9 @@ typedef struct rt_simple_params {
     int32_t max_bounces;     /* self.max_bounces = 5 */
     uint64_t seed;           /* Philox key; slot bounce+1 of (pixel, sample 0): glass draws word 0, diffuse words 0,1 */
     int32_t m;               /* number of explicit rays when rays_dev != NULL */
-    int32_t reserved_;
+    int32_t lighting_only;   /* != 0: rays_dev holds m INTERSECTIONS [m,7] = point, normal, scene index of the sphere;
+                              * rgb = calculate_lighting_exact_original(intersection) (output6.py:197-306), nothing is
+                              * traced but the sun's shadow test; rgb[.,3] = 0 */
     const double *rays_dev;  /* optional [m,6] origin + raw direction (scalar trace_ray_simple = a batch of one) */
 } rt_simple_params;
 /* rgb_dev [n,4] int32 = accumulated r, g, b, bounce_count (n = W*H or m); image_dev (optional) [n,3] float32 =
@@ -210,7 +212,7 @@ typedef struct rt_simple_params {
  * (nearest-hit + shadow tests). */
 int rt_render_simple(rt_scene *scene, int precision, const rt_simple_params *p, int32_t *rgb_dev, float *image_dev,
                      uint64_t *stats_dev, void *stream);
-/* host buffers; rays_host replaces p->rays_dev when not NULL.  Synchronous. */
+/* host buffers; rays_host ([m,6], or [m,7] with p->lighting_only) replaces p->rays_dev when not NULL.  Synchronous. */
 int rt_render_simple_host(rt_scene *scene, int precision, const rt_simple_params *p, const double *rays_host,
                           int32_t *rgb_host, float *image_host, uint64_t *stats_host);
 

@@ -417,7 +417,12 @@ def gen_simple(ref):
         def calculate_lighting_exact_original(self, intersection):     # once per bounce, before any draw
             ctl.bounce += 1
             ctl.word = 0
-            return super().calculate_lighting_exact_original(intersection)
+            out = super().calculate_lighting_exact_original(intersection)
+            if len(lit) < 4096:          # the helper on its own: (intersection -> Colour) pairs of the reference
+                k = next(j for j, sph in enumerate(self.scene) if sph is intersection.object)
+                p_, n_ = intersection.point, intersection.normal
+                lit.append([p_.x, p_.y, p_.z, n_.x, n_.y, n_.z, float(k), out.r, out.g, out.b])
+            return out
 
     def fake_random():
         w = ctl.word
@@ -425,6 +430,7 @@ def gen_simple(ref):
         assert w < 2
         return orc.rng_pair(seed, ctl.pixel, 0, ctl.bounce + 1)[w]
 
+    lit = []
     for tag, W, H, seed, depth in (("a", 64, 48, 21, 5), ("b", 40, 30, 22, 8)):
         colours = []
         ctl.pixel = -1
@@ -443,6 +449,10 @@ def gen_simple(ref):
         np.savez_compressed(OUT / f"simple_balls_{tag}_{W}x{H}.npz", image=img, rgb=rgb.astype(np.float32), stats=stats,
                             W=W, H=H, seed=seed, max_bounces=depth, **flat_dict(rtb.flatten_scene(spec.spheres)))
         print(f"simple_balls_{tag}", stats, "mean", rgb.mean(axis=(0, 1)))
+    lit = np.array(lit, np.float64)
+    np.savez_compressed(OUT / "simple_lighting_balls.npz", hits=lit[:, :7], rgb=lit[:, 7:].astype(np.float32),
+                        **flat_dict(rtb.flatten_scene(spec.spheres)))
+    print("simple_lighting", lit.shape, "sun rows", int((lit[:, 6] == 7).sum()), "mean", lit[:, 7:].mean(axis=0))
 
 
 # ----------------------------------------------------------------- FB-guided Algorithm B (f-4)

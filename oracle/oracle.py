@@ -82,6 +82,9 @@ def lib():
         _lib.orc_env_reset.argtypes = [C.POINTER(_Scene), C.POINTER(_EnvCfg), C.c_int, c_ip, C.c_void_p, c_fp]
         _lib.orc_env_step.argtypes = [C.POINTER(_Scene), C.POINTER(_EnvCfg), C.c_int, c_fp, C.c_void_p, c_fp, c_dp,
                                       c_u8p, c_u8p, c_ip]
+        _lib.orc_simple_lighting.argtypes = [C.POINTER(_Scene), C.POINTER(_SimpleCfg), C.c_int, c_dp, c_dp,
+                                             C.POINTER(C.c_uint64)]
+        _lib.orc_simple_lighting.restype = None
         _lib.orc_render_simple.argtypes = [C.POINTER(_Scene), C.POINTER(_SimpleCfg), C.c_int, C.c_int, C.c_uint64, c_dp, c_dp,
                                            c_u64p, C.c_int]
         _lib.orc_generate_trajectories.argtypes = [C.POINTER(_Scene), C.c_int, C.c_int, C.c_int, C.c_uint64, c_fp, c_fp, c_fp,
@@ -249,6 +252,21 @@ def render_simple(fs, W, H, cam=(0, 0, 1), fov=np.pi / 3, sun_pos=(-0.6, 0.2, 6)
     st = (C.c_uint64 * 2)()
     lib().orc_render_simple(sc.ref, C.byref(cfg), int(W), int(H), int(seed), rp, _p(out, c_dp), st, int(nthreads))
     return out, {"total_rays": int(st[0]), "sun_hits": int(st[1])}
+
+
+def simple_lighting(fs, hits, sun_pos=(-0.6, 0.2, 6), sun_col=(255, 255, 204), sun_id=7):
+    """FB/output6.py ``calculate_lighting_exact_original`` on given intersections: hits [m,7] = point, normal, scene
+    index -> (rgb [m,3] f64 integer-valued, sun_hits)."""
+    sc = _scene(fs)
+    cfg = _SimpleCfg()
+    cfg.sun_pos[:] = [float(x) for x in sun_pos]
+    cfg.sun_col[:] = [float(x) for x in sun_col]
+    cfg.sun_id = int(sun_id)
+    hits = _d(hits).reshape(-1, 7)
+    out = np.zeros((hits.shape[0], 3))
+    st = (C.c_uint64 * 2)()
+    lib().orc_simple_lighting(sc.ref, C.byref(cfg), int(hits.shape[0]), _p(hits, c_dp), _p(out, c_dp), st)
+    return out, int(st[1])
 
 
 def generate_trajectories(fs, n_traj, max_steps=8, max_bounces=8, seed=0):

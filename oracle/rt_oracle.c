@@ -668,6 +668,24 @@ static void trace_simple(const orc_scene *s, const orc_simple_cfg *c, v3 O, v3 D
 /* render_original_style: FB/output6.py:579-635.  rgb_out [H,W,3] integer-valued colours (image = min(1, c/255));
    rays != NULL: m explicit rays [m,6] (origin + raw direction) instead of the camera grid, W = m, H = 1.
    stats2 = total_rays, sun_hits. */
+/* calculate_lighting_exact_original on m given intersections: hits [m,7] = point, normal, scene index -> out [m,3];
+   st[1] += sun hits */
+ORC_API void orc_simple_lighting(const orc_scene *s, const orc_simple_cfg *c, int m, const double *hits, double *out,
+                                 uint64_t *st) {
+    uint64_t sh = 0;
+    for (int i = 0; i < m; ++i) {
+        const double *r = hits + 7 * (size_t)i;
+        isect h;
+        memset(&h, 0, sizeof h);
+        h.hit = 1; h.idx = (int)r[6];
+        h.p = V(r[0], r[1], r[2]); h.n = V(r[3], r[4], r[5]);
+        int64_t li[3] = {0, 0, 0};
+        if (h.idx >= 0 && h.idx < s->n) simple_lighting(s, c, &h, li, &sh);
+        for (int k = 0; k < 3; ++k) out[3 * (size_t)i + k] = (double)li[k];
+    }
+    if (st) st[1] += sh;
+}
+
 ORC_API void orc_render_simple(const orc_scene *s, const orc_simple_cfg *c, int W, int H, uint64_t seed,
                                const double *rays, double *rgb_out, uint64_t *stats2, int nthreads) {
     uint64_t R = 0, S = 0;

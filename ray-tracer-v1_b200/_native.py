@@ -68,7 +68,7 @@ class PathParams(C.Structure):
 class SimpleParams(C.Structure):
     _fields_ = [("cam", C.c_double * 3), ("W", C.c_int32), ("H", C.c_int32), ("fov_rad", C.c_double),
                 ("sun_pos", C.c_double * 3), ("sun_col", C.c_double * 3), ("sun_id", C.c_int32), ("max_bounces", C.c_int32),
-                ("seed", C.c_uint64), ("m", C.c_int32), ("reserved_", C.c_int32), ("rays_dev", C.c_void_p)]
+                ("seed", C.c_uint64), ("m", C.c_int32), ("lighting_only", C.c_int32), ("rays_dev", C.c_void_p)]
 
 
 RT_MAX_PEERS, IPC_HANDLE_BYTES = 16, 64
@@ -492,10 +492,17 @@ class DeviceScene:
         p.sun_id, p.max_bounces, p.seed = int(sun_id), int(max_bounces), int(seed)
         return p
 
-    def render_simple_host(self, params, precision=F32, rays=None, want_image=True):
+    def render_simple_host(self, params, precision=F32, rays=None, want_image=True, hits=None):
         """FB/output6.py ``render_original_style`` (or ``trace_ray_simple`` on explicit rays [m,6]) ->
-        (image [H,W,3] f32 | None, rgb [H,W,4] int32 = r, g, b, bounce_count, stats u64[8])."""
-        if rays is not None:
+        (image [H,W,3] f32 | None, rgb [H,W,4] int32 = r, g, b, bounce_count, stats u64[8]).
+        ``hits`` [m,7] = (point, normal, scene index): ``calculate_lighting_exact_original`` of those intersections
+        (output6.py:197-306), rgb [1,m,4]."""
+        params.lighting_only = 0
+        if hits is not None:
+            rays = _d(hits).reshape(-1, 7)
+            params.m, params.lighting_only = int(rays.shape[0]), 1
+            shape, want_image = (1, params.m), False
+        elif rays is not None:
             rays = _d(rays).reshape(-1, 6)
             params.m = int(rays.shape[0])
             shape = (1, params.m)

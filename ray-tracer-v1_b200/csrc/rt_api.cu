@@ -1048,6 +1048,7 @@ static int render_simple_t(const SceneDev<T> &view, const rt_simple_params *p, i
     sp.W = p->W; sp.H = p->H; sp.sun_id = p->sun_id; sp.max_bounces = p->max_bounces;
     sp.k0 = (uint32_t)p->seed; sp.k1 = (uint32_t)(p->seed >> 32);
     sp.rays = p->rays_dev;
+    sp.lighting_only = p->lighting_only != 0;
     sp.n = p->rays_dev ? p->m : p->W * p->H;
     CU(launch_simple<T>(view, sp, reinterpret_cast<int4 *>(rgb), image, reinterpret_cast<unsigned long long *>(stats), st));
     return RT_OK;
@@ -1058,6 +1059,7 @@ RT_EXPORT int rt_render_simple(rt_scene *scene, int precision, const rt_simple_p
     if (!scene || !p || !rgb_dev) return fail(RT_ERR_INVALID, "NULL argument");
     if (p->rays_dev ? p->m < 0 : (p->W <= 0 || p->H <= 0 || (long long)p->W * p->H > 0x7fffffffLL))
         return fail(RT_ERR_INVALID, "bad frame size / ray count");
+    if (p->lighting_only && (!p->rays_dev || image_dev)) return fail(RT_ERR_INVALID, "lighting_only needs intersections and no image");
     CU(cudaSetDevice(scene->device));
     if (precision == RT_F64) return render_simple_t<double>(scene->d.view, p, rgb_dev, image_dev, stats_dev, S(stream));
     if (precision == RT_F32) return render_simple_t<float>(scene->f.view, p, rgb_dev, image_dev, stats_dev, S(stream));
@@ -1072,8 +1074,9 @@ RT_EXPORT int rt_render_simple_host(rt_scene *scene, int precision, const rt_sim
     DevTmp rays, rgb, image, stats;
     if (rays_host) {
         if (q.m < 0) return fail(RT_ERR_INVALID, "negative ray count");
-        CU(cudaMalloc(&rays.p, sizeof(double) * 6 * (size_t)(q.m > 0 ? q.m : 1)));
-        CU(cudaMemcpyAsync(rays.p, rays_host, sizeof(double) * 6 * (size_t)q.m, cudaMemcpyHostToDevice, nullptr));
+        const size_t row = q.lighting_only ? 7 : 6;
+        CU(cudaMalloc(&rays.p, sizeof(double) * row * (size_t)(q.m > 0 ? q.m : 1)));
+        CU(cudaMemcpyAsync(rays.p, rays_host, sizeof(double) * row * (size_t)q.m, cudaMemcpyHostToDevice, nullptr));
         q.rays_dev = (const double *)rays.p;
     }
     const size_t n = q.rays_dev ? (size_t)q.m : (size_t)q.W * (size_t)q.H;

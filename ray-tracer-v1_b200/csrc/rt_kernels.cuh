@@ -817,7 +817,15 @@ __global__ void __launch_bounds__(256) simple_kernel(SceneDev<T> sc, SimpleDev<T
         i = y * sp.W + x;
     }
     unsigned n_rays = 0, n_sun = 0, n_query = 0, n_tests = 0, n_boxes = 0;
-    if (active) {
+    if (active && sp.lighting_only) {                 // calculate_lighting_exact_original on a given intersection
+        const double *r = sp.rays + 7 * (size_t)i;
+        Hit<T> h;
+        h.idx = (int)r[6]; h.t = T(0); h.bounces = 0; h.through = 0;
+        h.p = mk<T>(T(r[0]), T(r[1]), T(r[2])); h.n = mk<T>(T(r[3]), T(r[4]), T(r[5]));
+        int li[3] = {0, 0, 0};
+        if (h.idx >= 0 && h.idx < S.g.sv.n) { simple_lighting<T>(S.g, sp, h, li, n_sun, n_tests); n_query++; }
+        rgb[i] = make_int4(li[0], li[1], li[2], 0);
+    } else if (active) {
         V3<T> O, D;
         if (sp.rays) {
             const double *r = sp.rays + 6 * (size_t)i;
@@ -1203,17 +1211,24 @@ template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const E
 // 18 stores), then the CTA copies the block of rows to HBM as consecutive 16-byte stores -- the per-thread rows would
 // be 72-byte strided 4-byte stores, 18 partial sectors per warp instruction.
 #ifndef RT_ENV_BLOCK
-#define RT_ENV_BLOCK 64         /* 65,536 envs = 1,024 CTAs = 6.9 per SM: 1 % imbalance (128: 3.46 per SM, 15 %) */
+#define RT_ENV_BLOCK 64         /* envs per CTA.  65,536 envs = 1,024 CTAs = 6.9 per SM: 1 % imbalance (128: 3.46 per SM, 15 %) */
 #endif
+// Envs per warp.  The step is latency-bound, not issue-bound (65,536 envs are 3.5 full warps per scheduler, issue slots
+// 27 % busy, and every divergent branch of a warp runs one after the other), so a warp carries RT_ENV_LANES envs in its
+// low lanes and leaves the others idle: more warps per scheduler to hide latency, fewer distinct paths per warp.
+#ifndef RT_ENV_LANES
+#define RT_ENV_LANES 32
+#endif
+#define RT_ENV_THREADS (RT_ENV_BLOCK / RT_ENV_LANES * 32)
 RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
     __syncthreads();
     const int base = blockIdx.x * RT_ENV_BLOCK;
     const int n = min(RT_ENV_BLOCK, B - base) * 18;                      // floats of this CTA's rows
-    float *dst = obs + (size_t)base * 18;                                // 128 * 72 bytes per CTA: 16-byte aligned
+    float *dst = obs + (size_t)base * 18;                                // 64 * 72 bytes per CTA: 16-byte aligned
     const int n4 = (((uintptr_t)obs & 15u) == 0) ? n >> 2 : 0;
-    for (int j = threadIdx.x; j < n4; j += RT_ENV_BLOCK)
+    for (int j = threadIdx.x; j < n4; j += RT_ENV_THREADS)
         reinterpret_cast<float4 *>(dst)[j] = reinterpret_cast<const float4 *>(rows)[j];
-    for (int j = 4 * n4 + threadIdx.x; j < n; j += RT_ENV_BLOCK) dst[j] = rows[j];
+    for (int j = 4 * n4 + threadIdx.x; j < n; j += RT_ENV_THREADS) dst[j] = rows[j];
 }
 
 // reset of one episode (RL/ray_tracer_env.py:254-293, _get_initial_ray :121-142): camera ray through pixel (px, py),
@@ -1275,7 +1290,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
 // Philox(env, episode number) under the key (k0, k1) -- no host round trip and no second launch per step, and the
 // lanes of finished episodes go straight back to work.
 template <typename T, int kMode, typename R, bool kAuto>
-__global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
+__global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
                                                                 R *reward, uint8_t *terminated, uint8_t *truncated,
                                                                 int *reason, R *info, float *final_obs, int *pixels_out,
                                                                 uint32_t k0, uint32_t k1, unsigned long long *stats) {
@@ -1284,10 +1299,11 @@ __global__ void __launch_bounds__(RT_ENV_BLOCK) env_step_kernel(SceneDev<T> sc, 
     __shared__ __align__(16) float s_rows[RT_ENV_BLOCK * 18];
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    float *row = s_rows + 18 * threadIdx.x;
+    const int slot = RT_ENV_LANES == 32 ? (int)threadIdx.x : (int)(threadIdx.x >> 5) * RT_ENV_LANES + (int)(threadIdx.x & 31u);
+    const int b = blockIdx.x * RT_ENV_BLOCK + slot;
+    float *row = s_rows + 18 * slot;
     Counters ct = {0u, 0u, 0u};
-    if (b < e.B) {
+    if ((RT_ENV_LANES == 32 || (threadIdx.x & 31u) < RT_ENV_LANES) && b < e.B) {
         EnvReg<T> st = env_load<T>(e, b);
         RT_ASSERT(st.idx >= -1 && st.idx < sc.n && st.bounce >= 0);
         const float a0 = actions[2 * b], a1 = actions[2 * b + 1];
@@ -1598,7 +1614,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
                             uint8_t *terminated, uint8_t *truncated, int *reason, R *info, float *final_obs, int *pixels_out,
                             uint64_t seed, unsigned long long *stats, cudaStream_t st) {
     if (e.B <= 0) return cudaSuccess;
-    const int block = RT_ENV_BLOCK, grid = (e.B + block - 1) / block;
+    const int block = RT_ENV_THREADS, grid = (e.B + RT_ENV_BLOCK - 1) / RT_ENV_BLOCK;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     const size_t rows = RT_ENV_BLOCK * 18 * sizeof(float);                 // static shared rows on top of the staged scene
     const int mode = mode_for(sc, rows);

@@ -65,6 +65,7 @@ template <typename T> struct SimpleDev {
     int W, H, n, sun_id, max_bounces;
     uint32_t k0, k1;
     const double *rays;
+    int lighting_only;                    // rays = [n,7] intersections (point, normal, scene index): lighting alone
 };
 
 // wavefront form of Algorithm B (rt_wavefront.cuh): SoA path state, one slot per (pixel, sample)

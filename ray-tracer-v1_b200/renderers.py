@@ -364,6 +364,23 @@ class SimplifiedFBRenderer:
         self.stats['sun_hits'] += int(st[1])
         return Colour(int(rgb[0, 0, 0]), int(rgb[0, 0, 1]), int(rgb[0, 0, 2]))
 
+    def calculate_lighting_exact_original(self, intersection):
+        """Lighting ``Colour`` at one intersection (output6.py:197-306): the sun's colour on the sun, else
+        int(colour * min(255, global + shadowed sun) / 255).  ``intersection`` carries ``object`` (a sphere of
+        ``self.scene``), ``point`` and ``normal`` like ``ray.Intersection``; a batch of one through the frame kernel's
+        own lighting function (``rt_simple_params.lighting_only``)."""
+        sc, p = self._scene_and_params(1, 1)
+        obj = intersection.object
+        idx = next((k for k, s in enumerate(self.scene) if s is obj), None)
+        if idx is None:
+            idx = next((k for k, s in enumerate(self.scene) if s.id == obj.id), None)
+        if idx is None:
+            raise ValueError("intersection.object is not a sphere of this renderer's scene")
+        row = np.array([[*_xyz(intersection.point), *_xyz(intersection.normal), float(idx)]], np.float64)
+        _, rgb, st = sc.render_simple_host(p, _precision(self.precision), hits=row)
+        self.stats['sun_hits'] = self.stats.get('sun_hits', 0) + int(st[1])
+        return Colour(int(rgb[0, 0, 0]), int(rgb[0, 0, 1]), int(rgb[0, 0, 2]))
+
     def render_original_style(self, width=400, height=300, output_path=None):
         """-> (image [H,W,3] float32 in [0,1], output_path) (output6.py:579-654)."""
         if output_path is None:

@@ -9,6 +9,7 @@ Tolerances (north_star):
     within RMSE <= 4/sqrt(spp) levels (it is far smaller in practice).
 """
 import numpy as np
+from types import SimpleNamespace
 import pytest
 
 from conftest import gate, load_golden
@@ -633,6 +634,32 @@ def test_output6_frames_match_reference(nat, orc, name):
     ref, sto = orc.render_simple(fs, 200, 150, seed=seed + 1, max_bounces=depth)
     assert np.array_equal(big64[..., :3], ref.astype(np.int32)) and int(stb[0]) == sto["total_rays"] and int(stb[1]) == sto["sun_hits"]
     sc.close()
+
+
+def test_output6_lighting_helper_matches_reference(nat, rt, orc):
+    """calculate_lighting_exact_original on its own (rt_simple_params.lighting_only): the reference's own (intersection
+    -> Colour) pairs exactly in FP64, within one level in FP32 but for a few shadow / int() flips; then the class
+    method."""
+    z, fs = load_golden("simple_lighting_balls")
+    sc = nat.DeviceScene(fs)
+    p = sc.simple_params(1, 1)
+    _, rgb64, st = sc.render_simple_host(p, nat.F64, hits=z["hits"])
+    assert np.array_equal(rgb64[0, :, :3], z["rgb"].astype(np.int32)) and int(st[1]) == 0
+    _, rgb32, _ = sc.render_simple_host(p, nat.F32, hits=z["hits"])
+    d = np.abs(rgb32[0, :, :3].astype(np.int64) - z["rgb"].astype(np.int64)).max(axis=1)
+    gate("output6 lighting helper FP32 rows beyond one level", (d > 1).mean(), 6e-3)
+    sc.close()
+    r = rt.SimplifiedFBRenderer(precision="f64", seed=5)
+    sph = r.scene[2]
+    n = rt.Vector(0.0, 0.6, 0.8)
+    pt = sph.centre.addVector(n.scaleByLength(sph.radius))
+    it = SimpleNamespace(object=sph, point=pt, normal=n)
+    c = r.calculate_lighting_exact_original(it)
+    want, _ = orc.simple_lighting(rt.flatten_scene(r.scene), [[pt.x, pt.y, pt.z, n.x, n.y, n.z, 2.0]])
+    assert (c.r, c.g, c.b) == tuple(int(v) for v in want[0])
+    sun = next(s for s in r.scene if s.id == 7)
+    c = r.calculate_lighting_exact_original(SimpleNamespace(object=sun, point=sun.centre, normal=n))
+    assert (c.r, c.g, c.b) == (255, 255, 204) and r.stats["sun_hits"] == 1
 
 
 def test_output6_dropin_class(rt, orc):

@@ -152,6 +152,19 @@ def test_output6_frames(orc, name):
     assert (rgb2.reshape(H, W, 3) != rgb).any(axis=2).mean() < 0.002      # vnorm in numpy vs C: last-ulp flips only
 
 
+def test_output6_lighting_helper(orc):
+    """FB/output6.py calculate_lighting_exact_original on its own: 2,920 (intersection -> Colour) pairs recorded from the
+    reference's own calls while it rendered the two frames above."""
+    z, fs = load_golden("simple_lighting_balls")
+    rgb, sun_hits = orc.simple_lighting(fs, z["hits"])
+    assert np.array_equal(rgb, z["rgb"]) and sun_hits == 0
+    # on the sun sphere (id 7) the helper returns the sun's colour and counts the hit (output6.py:204-206)
+    sun = int(np.nonzero(fs.ids == 7)[0][0])
+    row = np.array([[0, 0, 0, 0, 0, 1, sun]], float)
+    rgb, sun_hits = orc.simple_lighting(fs, row)
+    assert rgb.tolist() == [[255, 255, 204]] and sun_hits == 1
+
+
 def test_fb_trajectories(orc):
     """FB/train_complex_only.py generate_trajectory run by the reference itself (random.* patched to the Philox
     stream): 256 random walks on the complex scene, every transition bit for bit."""
