@@ -26,8 +26,13 @@ def main():
     ap.add_argument("--no-stats", action="store_true", help="launch without the statistics counters")
     ap.add_argument("--save", default=None, help="write the last accumulation buffer to this .npy")
     args = ap.parse_args()
-    spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
-    fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
+    if args.scene.startswith("scaled"):           # scaled1000 / scaled10000 / scaled100000: SURVEY 8d's LBVH variant of C4
+        spec = scenes.build_chandelier()
+        fs = scenes.build_many_spheres_flat(int(args.scene[6:]), seed=0)
+        args.lbvh = True
+    else:
+        spec = scenes.build_complex() if args.scene == "complex" else scenes.build_chandelier()
+        fs = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
     sc = nat.DeviceScene(fs)
     if args.lbvh:
         sc.build_lbvh(50.0)
