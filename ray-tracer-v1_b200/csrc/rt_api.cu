@@ -44,6 +44,7 @@ template <typename T> struct SceneBufs {
 struct rt_scene {
     int device = 0;
     int n = 0, nG = 0, nP = 0, nL = 0;
+    unsigned long long version = 0;            // bumped by every upload (rt_scene_create / rt_scene_update)
     SceneBufs<float> f;
     SceneBufs<double> d;
     uint8_t *small_dev = nullptr;
@@ -83,6 +84,7 @@ struct rt_env {
     void *blob = nullptr;
     EnvDev<float> f;
     EnvDev<double> d;
+    unsigned long long shaded_version = 0;      // rt_scene::version the cached shading (EnvDev::rgb) was computed with
 };
 
 template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
@@ -219,6 +221,7 @@ static int validate_desc(const rt_scene_desc *s) {
 
 static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
     CU(cudaSetDevice(sc->device));
+    sc->version++;
     const bool same = sc->n == s->n && sc->nG == s->nG && sc->nP == s->nP && sc->nL == s->nL && sc->f.blob;
     if (!same) {
         if (sc->f.blob) CU(cudaFree(sc->f.blob));
@@ -1108,6 +1111,7 @@ template <typename T> static void bind_env(EnvDev<T> &e, const rt_env_desc &d, v
     e.n = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
     e.d = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
     e.acc = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
+    e.rgb = reinterpret_cast<T *>(p); p += 3 * B * sizeof(T);
     e.has_hit = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.idx = reinterpret_cast<int *>(p); p += B * sizeof(int);
     e.bounce = reinterpret_cast<int *>(p); p += B * sizeof(int);
@@ -1130,13 +1134,14 @@ RT_EXPORT int rt_env_create(rt_scene *scene, int precision, const rt_env_desc *d
     if (!env) return fail(RT_ERR_NOMEM, "host allocation failed");
     env->scene = scene; env->precision = precision; env->desc = *desc;
     const size_t B = (size_t)desc->B, el = precision == RT_F64 ? sizeof(double) : sizeof(float);
-    const size_t bytes = B * sizeof(double) + 12 * B * el + 7 * B * sizeof(int);
+    const size_t bytes = B * sizeof(double) + 15 * B * el + 7 * B * sizeof(int);
     cudaError_t e = cudaMalloc(&env->blob, bytes);
     if (e != cudaSuccess) { delete env; cudaGetLastError(); return e == cudaErrorMemoryAllocation ? fail(RT_ERR_NOMEM, "out of device memory") : cuda_fail(e, "cudaMalloc"); }
     e = cudaMemset(env->blob, 0, bytes);
     if (e != cudaSuccess) { cudaFree(env->blob); delete env; return cuda_fail(e, "cudaMemset"); }
     if (precision == RT_F64) bind_env<double>(env->d, *desc, env->blob);
     else bind_env<float>(env->f, *desc, env->blob);
+    env->shaded_version = scene->version;
     *out = env;
     return RT_OK;
 }
@@ -1146,6 +1151,16 @@ RT_EXPORT int rt_env_destroy(rt_env *env) {
     cudaSetDevice(env->scene->device);
     if (env->blob) cudaFree(env->blob);
     delete env;
+    return RT_OK;
+}
+
+// The RL flavour keeps terminalRGB of every episode's current hit (EnvDev::rgb).  If the scene was re-uploaded since
+// those were computed, shade the running episodes' hits again before the next step reads them.
+static int env_reshade_if_stale(rt_env *env, cudaStream_t st) {
+    if (env->shaded_version == env->scene->version) return RT_OK;
+    if (env->precision == RT_F64) CU(launch_env_reshade<double>(env->scene->d.view, env->d, st));
+    else CU(launch_env_reshade<float>(env->scene->f.view, env->f, st));
+    env->shaded_version = env->scene->version;
     return RT_OK;
 }
 
@@ -1165,6 +1180,7 @@ RT_EXPORT int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev,
     if (!env || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev || !reason_dev)
         return fail(RT_ERR_INVALID, "NULL argument");
     CU(cudaSetDevice(env->scene->device));
+    if (int rc = env_reshade_if_stale(env, S(stream))) return rc;
     unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
     if (env->precision == RT_F64)
         CU((launch_env_step<double, double, false>(env->scene->d.view, env->d, actions_dev, obs_dev, reward_dev, terminated_dev,
@@ -1182,6 +1198,7 @@ RT_EXPORT int rt_env_step_auto(rt_env *env, const float *actions_dev, float *obs
         return fail(RT_ERR_INVALID, "NULL argument");
     if (((uintptr_t)final_obs_dev) & 7u) return fail(RT_ERR_INVALID, "final_obs must be 8-byte aligned");
     CU(cudaSetDevice(env->scene->device));
+    if (int rc = env_reshade_if_stale(env, S(stream))) return rc;
     unsigned long long *st = reinterpret_cast<unsigned long long *>(stats_dev);
     if (env->precision == RT_F64)
         CU((launch_env_step<double, double, true>(env->scene->d.view, env->d, actions_dev, obs_dev, (double *)reward_dev,

@@ -1095,6 +1095,7 @@ template <typename T> struct EnvReg {
     int bounce, through;
     V3<T> p, n, d;
     T acc[3];
+    T c[3];                       // RL flavour: terminalRGB of the current hit, computed when the hit was made (see env_step_kernel)
     double total;
     RT_DEV Hit<T> hit() const {
         Hit<T> h;
@@ -1115,6 +1116,8 @@ template <typename T> RT_DEV EnvReg<T> env_load(const EnvDev<T> &e, int b) {
     s.acc[0] = e.acc[b]; s.acc[1] = e.acc[B + b]; s.acc[2] = e.acc[2 * B + b];
     s.total = e.total[b];
     s.idx = has ? idx : -1;
+    if (e.flavour == 0) { s.c[0] = e.rgb[b]; s.c[1] = e.rgb[B + b]; s.c[2] = e.rgb[2 * B + b]; }
+    else s.c[0] = s.c[1] = s.c[2] = T(0);
     return s;
 }
 
@@ -1127,6 +1130,7 @@ template <typename T> RT_DEV void env_store(const EnvDev<T> &e, int b, const Env
     e.d[b] = s.d.x; e.d[B + b] = s.d.y; e.d[2 * B + b] = s.d.z;
     e.acc[b] = s.acc[0]; e.acc[B + b] = s.acc[1]; e.acc[2 * B + b] = s.acc[2];
     e.total[b] = s.total;
+    if (e.flavour == 0) { e.rgb[b] = s.c[0]; e.rgb[B + b] = s.c[1]; e.rgb[2 * B + b] = s.c[2]; }
 }
 
 // _get_observation (RL/ray_tracer_env.py:184-222): 18 x float32 into the row `o` (a shared-memory staging row: the
@@ -1147,13 +1151,12 @@ template <typename T> RT_DEV void env_obs(const Geo<T> &g, const EnvReg<T> &s, f
 }
 
 // RL _calculate_reward (RL/ray_tracer_env.py:224-252); FB _calculate_reward (FB/ray_tracer_env.py:241-278)
-template <typename T, bool kBvh>
-RT_DEV double env_reward_base(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, const Hit<T> &h, int bounce_count,
-                              Counters &ct) {
+// `c` = terminalRGB(h) (ray.py:37-65): the step kernel keeps it with the hit instead of shading the same point twice
+// (once for the accumulated colour when the hit is made, once for the next step's reward)
+template <typename T>
+RT_DEV double env_reward_base(const Geo<T> &g, const EnvDev<T> &e, const Hit<T> &h, int bounce_count, const T *c) {
     if (h.idx < 0) return -0.1;
     if (e.flavour == 1 && g.sv.ids[h.idx] == e.sun_id) return 10.0;
-    T c[3];
-    terminal_rgb<T, kBvh>(g, la, h, 0, c, ct);
     if constexpr (M<T>::exact) {
         double brightness = (c[0] + c[1] + c[2]) / (3 * 255);
         double pen = -0.01 * bounce_count;
@@ -1163,12 +1166,11 @@ RT_DEV double env_reward_base(const Geo<T> &g, const LightsA<T> &la, const EnvDe
     }
 }
 // + AdaptiveRewardRayTracerEnv._calculate_reward (RL/train_raytracer_optimized.py:25-61) when e.adaptive
-template <typename T, bool kBvh>
-RT_DEV double env_reward(const Geo<T> &g, const LightsA<T> &la, const EnvDev<T> &e, int b, const Hit<T> &h, int bounce_count,
-                         Counters &ct) {
-    if (!e.adaptive) return env_reward_base<T, kBvh>(g, la, e, h, bounce_count, ct);
+template <typename T>
+RT_DEV double env_reward(const Geo<T> &g, const EnvDev<T> &e, int b, const Hit<T> &h, int bounce_count, const T *c) {
+    if (!e.adaptive) return env_reward_base<T>(g, e, h, bounce_count, c);
     if (h.idx < 0) return -0.5;
-    const double base = env_reward_base<T, kBvh>(g, la, e, h, bounce_count, ct);
+    const double base = env_reward_base<T>(g, e, h, bounce_count, c);
     double light_bonus = 0.0, reflective_bonus = 0.0, path_length_penalty = 0.0;
     const int id = g.sv.ids[h.idx];
     if (id == e.light0 || id == e.light1) {
@@ -1220,6 +1222,11 @@ template <typename T> RT_DEV double env_lighting_reward(const Geo<T> &g, const E
 #define RT_ENV_LANES 32
 #endif
 #define RT_ENV_THREADS (RT_ENV_BLOCK / RT_ENV_LANES * 32)
+// register budget of the step kernel: left to itself ptxas settles on 80 registers and spills 64 bytes; the launch
+// never has more than 14 warps per SM to place (65,536 episodes / 148 SMs), so registers are free
+#ifndef RT_ENV_REGS
+#define RT_ENV_REGS 128
+#endif
 RT_DEV void env_flush_obs(const float *rows, float *obs, int B) {
     __syncthreads();
     const int base = blockIdx.x * RT_ENV_BLOCK;
@@ -1277,10 +1284,29 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
         EnvReg<T> st;
         env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct, mask == nullptr);
+        st.c[0] = st.c[1] = st.c[2] = T(0);
+        if (e.flavour == 0 && st.idx >= 0) terminal_rgb<T, kBvh>(S.g, S.la, st.hit(), 0, st.c, ct);
         env_store<T>(e, b, st);
         env_obs<T>(S.g, st, obs + 18 * (size_t)b);
     }
     if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
+}
+
+// The scene changed under running episodes (rt_scene_update): shade the current hits again
+template <typename T, int kMode>
+__global__ void __launch_bounds__(256) env_reshade_kernel(SceneDev<T> sc, EnvDev<T> e) {
+    RT_MODE_DECL;
+    extern __shared__ __align__(32) unsigned char smem[];
+    Staged<T> S;
+    stage_scene<T, kShared>(sc, smem, S);
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    Counters ct = {0u, 0u, 0u};
+    if (b < e.B && e.flavour == 0 && e.has_hit[b] && e.idx[b] >= 0 && e.idx[b] < sc.n) {
+        EnvReg<T> st = env_load<T>(e, b);
+        terminal_rgb<T, kBvh>(S.g, S.la, st.hit(), 0, st.c, ct);
+        const size_t B = (size_t)e.B;
+        e.rgb[b] = st.c[0]; e.rgb[B + b] = st.c[1]; e.rgb[2 * B + b] = st.c[2];
+    }
 }
 
 // step (RL/ray_tracer_env.py:295-401, FB/ray_tracer_env.py:378-514)
@@ -1290,7 +1316,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
 // Philox(env, episode number) under the key (k0, k1) -- no host round trip and no second launch per step, and the
 // lanes of finished episodes go straight back to work.
 template <typename T, int kMode, typename R, bool kAuto>
-__global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
+__global__ void __maxnreg__(RT_ENV_REGS) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
                                                                 R *reward, uint8_t *terminated, uint8_t *truncated,
                                                                 int *reason, R *info, float *final_obs, int *pixels_out,
                                                                 uint32_t k0, uint32_t k1, unsigned long long *stats) {
@@ -1304,6 +1330,7 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
     float *row = s_rows + 18 * slot;
     Counters ct = {0u, 0u, 0u};
     if ((RT_ENV_LANES == 32 || (threadIdx.x & 31u) < RT_ENV_LANES) && b < e.B) {
+        const unsigned live = __activemask();       // the lanes of this warp that carry an episode (converged here)
         EnvReg<T> st = env_load<T>(e, b);
         RT_ASSERT(st.idx >= -1 && st.idx < sc.n && st.bounce >= 0);
         const float a0 = actions[2 * b], a1 = actions[2 * b + 1];
@@ -1311,12 +1338,13 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
         int bc = st.bounce;
         const int through = st.through;
         int rsn = 0, term = 0, trunc = 0;
+        bool shade = false;                       // the step made a new hit: accumulated colour += terminalRGB(hit)
         double rw = 0.0, info_total, info_sun = -1.0;
         int info_bounce = bc;
         if (cur.idx < 0) {                                                   // ray already missed, :313-323
             rsn = 1; rw = -1.0; term = 1; info_total = st.total;
         } else if (bc >= e.max_bounces) {                                    // :325-337
-            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T, kBvh>(S.g, S.la, e, b, cur, bc, ct);
+            rw = e.flavour == 1 ? env_lighting_reward<T>(S.g, e, cur) : env_reward<T>(S.g, e, b, cur, bc, st.c);
             st.total += rw; info_total = st.total;
             rsn = 3; term = 1; trunc = 1;
         } else if (e.flavour == 1 && S.g.sv.ids[cur.idx] == e.sun_id) {      // FB :417-431 (total_reward not updated)
@@ -1340,7 +1368,7 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
             if constexpr (M<T>::exact) D = normalise(D);                      // Ray() normalises again
             bc += 1;
             Hit<T> nx = trace_terminal<T, kBvh>(S.g, cur.p, D, S.g.sv.ids[cur.idx], bc, e.max_bounces, through, ct);
-            if (e.flavour == 0) rw = env_reward<T, kBvh>(S.g, S.la, e, b, cur, bc, ct);    // reward at the PRE-update hit, :362
+            if (e.flavour == 0) rw = env_reward<T>(S.g, e, b, cur, bc, st.c);             // reward at the PRE-update hit, :362
             else if (nx.idx >= 0) {
                 if (S.g.sv.ids[nx.idx] == e.sun_id) { rw = 10.0; rsn = 4; term = 1; info_sun = 1.0; }
                 else { rw = env_lighting_reward<T>(S.g, e, nx); info_sun = 0.0; }
@@ -1348,11 +1376,7 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
             st.total += rw; info_total = st.total;
             st.set_hit(nx, D);
             st.bounce = bc; info_bounce = bc;
-            if (nx.idx >= 0) {                                               // :373-381
-                T c[3];
-                terminal_rgb<T, kBvh>(S.g, S.la, nx, 0, c, ct);
-                st.acc[0] = st.acc[0] + c[0]; st.acc[1] = st.acc[1] + c[1]; st.acc[2] = st.acc[2] + c[2];
-            }
+            shade = nx.idx >= 0;                                             // :373-381, done below
             if (e.flavour == 0) {
                 if (nx.idx < 0) { term = 1; rsn = 2; }
                 else if (bc >= e.max_bounces) { term = 1; trunc = 1; rsn = 3; }
@@ -1363,9 +1387,22 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
             R *q = info + 4 * (size_t)b;
             q[0] = (R)info_bounce; q[1] = (R)through; q[2] = (R)info_total; q[3] = (R)info_sun;
         }
-        env_obs<T>(S.g, st, row);
+        // ONE shading site for the whole step.  A hit is shaded when it is made: the colour goes into the accumulated
+        // colour of the observation (:373-381) and stays with the hit (EnvReg::c) as the RL flavour's reward of the NEXT
+        // step (:362 shades the pre-update hit again: same point, same scene, same value).  An episode that restarts in
+        // this launch shades its first hit here too, so the lanes of continuing and of restarted episodes share the
+        // code; only an episode that ENDS on a hit (bounce limit) needs its colour before the restart, for final_obs.
+        bool restarted = false;
+        __syncwarp(live);       // the four outcomes of the step above meet again before the restarts
         if constexpr (kAuto) {
             if (term | trunc) {
+                restarted = true;
+                if (shade && final_obs) {
+                    T c[3];
+                    terminal_rgb<T, kBvh>(S.g, S.la, st.hit(), 0, c, ct);
+                    st.acc[0] = st.acc[0] + c[0]; st.acc[1] = st.acc[1] + c[1]; st.acc[2] = st.acc[2] + c[2];
+                }
+                env_obs<T>(S.g, st, row);
                 if (final_obs) {                         // 72-byte rows: nine 8-byte stores
                     float2 *fo = reinterpret_cast<float2 *>(final_obs + 18 * (size_t)b);
 #pragma unroll
@@ -1376,9 +1413,16 @@ __global__ void __launch_bounds__(RT_ENV_THREADS) env_step_kernel(SceneDev<T> sc
                 const int py = (int)(((unsigned long long)o.w[1] * (unsigned)e.H) >> 32);
                 if (pixels_out) { pixels_out[2 * b] = px; pixels_out[2 * b + 1] = py; }
                 env_begin_episode<T, kBvh>(S, e, b, px, py, st, ct);
-                env_obs<T>(S.g, st, row);
+                shade = e.flavour == 0 && st.idx >= 0;
             }
         }
+        __syncwarp(live);       // continuing and restarted episodes enter the shading TOGETHER (else the compiler threads
+                                // the two paths into the block separately and the warp runs it twice)
+        if (shade) {
+            terminal_rgb<T, kBvh>(S.g, S.la, st.hit(), 0, st.c, ct);
+            if (!restarted) { st.acc[0] = st.acc[0] + st.c[0]; st.acc[1] = st.acc[1] + st.c[1]; st.acc[2] = st.acc[2] + st.c[2]; }
+        }
+        env_obs<T>(S.g, st, row);
         env_store<T>(e, b, st);
     }
     env_flush_obs(s_rows, obs, e.B);
@@ -1608,6 +1652,15 @@ cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const in
     return cudaGetLastError();
 }
 
+template <typename T>
+cudaError_t launch_env_reshade(const SceneDev<T> &sc, const EnvDev<T> &e, cudaStream_t st) {
+    if (e.B <= 0 || e.flavour != 0) return cudaSuccess;
+    const int block = 128, grid = (e.B + block - 1) / block;
+    const int mode = mode_for(sc);
+    RT_DISPATCH_MODE(mode, env_reshade_kernel, grid, block, smem_for(sc), st, sc, e);
+    return cudaGetLastError();
+}
+
 // kAuto = false: plain step (rt_env_step); true: step + in-launch restart of finished episodes (rt_env_step_auto)
 template <typename T, typename R, bool kAuto>
 cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, R *reward,
@@ -1647,6 +1700,7 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     template cudaError_t launch_shade_hits<T>(const SceneDev<T> &, int, const double *, int, double *, cudaStream_t);    \
     template cudaError_t launch_env_reset<T>(const SceneDev<T> &, const EnvDev<T> &, const int *, const uint8_t *,      \
                                              uint64_t, float *, int *, unsigned long long *, cudaStream_t);             \
+    template cudaError_t launch_env_reshade<T>(const SceneDev<T> &, const EnvDev<T> &, cudaStream_t);                   \
     template cudaError_t launch_env_step<T, double, false>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, double *, \
                                             uint8_t *, uint8_t *, int *, double *, float *, int *, uint64_t, unsigned long long *, cudaStream_t); \
     template cudaError_t launch_env_step<T, T, true>(const SceneDev<T> &, const EnvDev<T> &, const float *, float *, T *,   \

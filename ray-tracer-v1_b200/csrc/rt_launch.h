@@ -89,6 +89,7 @@ template <typename T> struct EnvDev {
     int b0;                                          // global index of env 0 of this batch (rt_env_desc::env_offset)
     int *has_hit, *idx, *bounce, *through, *episode, *consec, *total_hits;
     T *p, *n, *d, *acc;
+    T *rgb;                                          // [3][B] RL flavour: terminalRGB of the current hit (shaded once, used twice)
     double *total;
 };
 
@@ -129,6 +130,8 @@ cudaError_t launch_shade_hits(const SceneDev<T> &sc, int m, const double *hits, 
 template <typename T>
 cudaError_t launch_env_reset(const SceneDev<T> &sc, const EnvDev<T> &e, const int *pixels, const uint8_t *mask,
                              uint64_t seed, float *obs, int *pixels_out, unsigned long long *stats, cudaStream_t st);
+// shade the current hits again after the scene changed under running episodes (EnvDev::rgb)
+template <typename T> cudaError_t launch_env_reshade(const SceneDev<T> &sc, const EnvDev<T> &e, cudaStream_t st);
 template <typename T, typename R, bool kAuto>
 cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const float *actions, float *obs, R *reward,
                             uint8_t *terminated, uint8_t *truncated, int *reason, R *info, float *final_obs, int *pixels_out,
