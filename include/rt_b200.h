@@ -139,8 +139,10 @@ typedef struct rt_whitted_params {
 } rt_whitted_params;
 /* accum_dev: [H,W,4] float (RT_F32) or double (RT_F64): sum r,g,b over the sample range + sample count.
  * hit_dev (optional) [H,W] int32 terminal scene index of the last sample (-1 miss).
- * stats_dev (optional) uint64[8]: [0] primary rays, [4] nearest-hit/occlusion queries, [5] sphere tests,
- * [6] AABB tests (LBVH only).
+ * stats_dev (optional) uint64[8]: [0] primary rays, [4] nearest-hit/occlusion queries traced, [5] sphere tests,
+ * [6] AABB tests (LBVH only), [7] continuation queries NOT traced: behind a mirror / through glass with the bounce
+ * limit already spent the reference still casts the ray and discards what it finds (ray.py:170-174), so
+ * [4] + [7] = the reference's own query count.
  * X / Y are HOST arrays; the scene keeps their device copies resident (keyed by value), so only the first frame with
  * a given grid uploads it (asynchronously, from a pinned copy) and later frames are a pure stream-ordered kernel
  * launch: no copy, no synchronisation, graph-capturable, and safe from any number of streams.  A handle is not
@@ -365,7 +367,9 @@ int rt_env_reset(rt_env *env, const int32_t *pixels_dev, const uint8_t *mask_dev
                  int32_t *pixels_out_dev, void *stream);
 /* step(): actions_dev [B,2] float32 -> obs [B,18] f32, reward [B] f64, terminated/truncated [B] u8,
  * reason [B] int32 (RT_REASON_*), info_dev (optional) [B,4] f64 = bounce_count, through_count, total_reward,
- * hit_sun.  stats_dev (optional) uint64[8]: [0] nearest-hit/occlusion queries. */
+ * hit_sun.  stats_dev (optional) uint64[8]: [4] nearest-hit/occlusion queries traced, [7] discarded continuation
+ * queries not traced (see rt_render_whitted).  The RL flavour shades every hit once, when it is made, and keeps the
+ * colour with the episode for the next step's reward (the reference shades the same point again one step later). */
 int rt_env_step(rt_env *env, const float *actions_dev, float *obs_dev, double *reward_dev, uint8_t *terminated_dev,
                 uint8_t *truncated_dev, int32_t *reason_dev, double *info_dev, uint64_t *stats_dev, void *stream);
 /* step() with the restart of finished episodes IN THE SAME LAUNCH (the VecEnv protocol of Stable-Baselines3, which the

@@ -213,7 +213,7 @@ template <typename T> struct SphereView {
 };
 
 enum : int { STAT_RAYS = 0, STAT_INTER = 1, STAT_LIGHT = 2, STAT_SMALL = 3, STAT_QUERIES = 4, STAT_SPHERE_TESTS = 5,
-             STAT_AABB_TESTS = 6, STAT_COUNT = 8 };
+             STAT_AABB_TESTS = 6, STAT_DEAD_QUERIES = 7, STAT_COUNT = 8 };
 
 RT_DEV unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll

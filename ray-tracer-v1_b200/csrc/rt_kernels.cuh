@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
     const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     unsigned primaries = 0;
     const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
     const unsigned n_units = (unsigned)(wp.gx * wp.gy) << 3, first_dyn = (unsigned)gridDim.x << 3;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256, (sizeof(T) == 4 ? RT_WHITTED_MIN_BLOCKS :
         if (atomicAdd(wp.sched + 1, 1u) == (gridDim.x << 3) - 1u) { wp.sched[0] = 0u; wp.sched[1] = 0u; __threadfence(); }
     }
     if (stats) {
-        flush_stats(stats, STAT_QUERIES, ct.queries);
+        flush_stats(stats, STAT_QUERIES, ct.queries); flush_stats(stats, STAT_DEAD_QUERIES, ct.dead);
         flush_stats(stats, STAT_RAYS, primaries);
         flush_stats(stats, STAT_SPHERE_TESTS, ct.tests);
         flush_stats(stats, STAT_AABB_TESTS, ct.boxes);
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256, RT_WHITTED_MIN_BLOCKS) whitted_heavy_kern
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
     const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     unsigned primaries = 0;
     const V3<T> cam = mk<T>(wp.cam[0], wp.cam[1], wp.cam[2]);
     const unsigned ns = (unsigned)(wp.s1 - wp.s0);
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(256, RT_WHITTED_MIN_BLOCKS) whitted_heavy_kern
         }
     }
     if (stats) {
-        flush_stats(stats, STAT_QUERIES, ct.queries);
+        flush_stats(stats, STAT_QUERIES, ct.queries); flush_stats(stats, STAT_DEAD_QUERIES, ct.dead);
         flush_stats(stats, STAT_RAYS, primaries);
         flush_stats(stats, STAT_SPHERE_TESTS, ct.tests);
         flush_stats(stats, STAT_AABB_TESTS, ct.boxes);
@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(256) trace_rays_kernel(SceneDev<T> sc, int m, 
     const double *r = rays + 6 * (size_t)i;
     V3<T> O = mk<T>(T(r[0]), T(r[1]), T(r[2]));
     V3<T> D = normalise(mk<T>(T(r[3]), T(r[4]), T(r[5])));
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     Hit<T> h = trace_terminal<T, kBvh>(S.g, O, D, suppress ? suppress[i] : RT_NO_ID_DEV, bounces0 ? bounces0[i] : 0,
                                  max_bounces, through0 ? through0[i] : 0, ct);
     double *t = term + 11 * (size_t)i;
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256) shade_hits_kernel(SceneDev<T> sc, int m, 
     h.n = mk<T>(T(q[4]), T(q[5]), T(q[6]));
     double *c = rgb + 3 * (size_t)i;
     if (h.idx < 0 || h.idx >= sc.n) { c[0] = c[1] = c[2] = 0.0; return; }
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     T o[3];
     terminal_rgb<T, kBvh>(S.g, S.la, h, shadow_max_bounces, o, ct);
     c[0] = (double)o[0]; c[1] = (double)o[1]; c[2] = (double)o[2];
@@ -1272,7 +1272,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     if (b < e.B && (!mask || mask[b])) {
         int px, py;
         if (pixels) { px = pixels[2 * b]; py = pixels[2 * b + 1]; }
@@ -1289,7 +1289,7 @@ __global__ void __launch_bounds__(256) env_reset_kernel(SceneDev<T> sc, EnvDev<T
         env_store<T>(e, b, st);
         env_obs<T>(S.g, st, obs + 18 * (size_t)b);
     }
-    if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
+    if (stats) { flush_stats(stats, STAT_QUERIES, ct.queries); flush_stats(stats, STAT_DEAD_QUERIES, ct.dead); }
 }
 
 // The scene changed under running episodes (rt_scene_update): shade the current hits again
@@ -1300,7 +1300,7 @@ __global__ void __launch_bounds__(256) env_reshade_kernel(SceneDev<T> sc, EnvDev
     Staged<T> S;
     stage_scene<T, kShared>(sc, smem, S);
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     if (b < e.B && e.flavour == 0 && e.has_hit[b] && e.idx[b] >= 0 && e.idx[b] < sc.n) {
         EnvReg<T> st = env_load<T>(e, b);
         terminal_rgb<T, kBvh>(S.g, S.la, st.hit(), 0, st.c, ct);
@@ -1328,7 +1328,7 @@ __global__ void __maxnreg__(RT_ENV_REGS) env_step_kernel(SceneDev<T> sc, EnvDev<
     const int slot = RT_ENV_LANES == 32 ? (int)threadIdx.x : (int)(threadIdx.x >> 5) * RT_ENV_LANES + (int)(threadIdx.x & 31u);
     const int b = blockIdx.x * RT_ENV_BLOCK + slot;
     float *row = s_rows + 18 * slot;
-    Counters ct = {0u, 0u, 0u};
+    Counters ct = {0u, 0u, 0u, 0u};
     if ((RT_ENV_LANES == 32 || (threadIdx.x & 31u) < RT_ENV_LANES) && b < e.B) {
         const unsigned live = __activemask();       // the lanes of this warp that carry an episode (converged here)
         EnvReg<T> st = env_load<T>(e, b);
@@ -1426,7 +1426,7 @@ __global__ void __maxnreg__(RT_ENV_REGS) env_step_kernel(SceneDev<T> sc, EnvDev<
         env_store<T>(e, b, st);
     }
     env_flush_obs(s_rows, obs, e.B);
-    if (stats) flush_stats(stats, STAT_QUERIES, ct.queries);
+    if (stats) { flush_stats(stats, STAT_QUERIES, ct.queries); flush_stats(stats, STAT_DEAD_QUERIES, ct.dead); }
 }
 
 // ------------------------------------------------------------------ launchers

@@ -464,7 +464,7 @@ RT_DEV bool sphere_exit_ray(V3<T> D, typename M<T>::v4 sph, T ior, const Hit<T> 
     return true;
 }
 
-struct Counters { unsigned queries, tests, boxes; };
+struct Counters { unsigned queries, tests, boxes, dead; };      // dead: queries the reference casts and then discards (skipped)
 
 // Ray.nearestSphereIntersect (ray.py:160-231) with the recursion unrolled: a mirror that finds nothing returns
 // ITSELF (ray.py:198-201), glass that finds nothing returns None (ray.py:226-229), so a dead-ended chain yields the
@@ -492,6 +492,9 @@ RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, in
             D = M<T>::exact ? normalise(r) : r;               // Ray() normalises again
             O = h.p;
             bounces += 1; suppress = g.sv.ids[i];
+            // the reference casts the mirrored ray even when the bounce limit is spent and then discards what it finds
+            // (ray.py:170-174: both exits return the mirror itself): do not trace it
+            if (bounces > max_bounces) { ct.dead++; return fallback; }
             continue;
         }
         if (m.y == T(1)) {                                    // material.transparent == True, ray.py:204
@@ -499,6 +502,7 @@ RT_DEV Hit<T> trace_terminal(const Geo<T> &g, V3<T> O, V3<T> D, int suppress, in
             if (!sphere_exit_ray<T>(D, g.sv.sph[i], m.w, h, eo, ed)) return fallback;
             O = eo; D = ed;
             bounces += 1; through += 1; suppress = g.sv.ids[i];
+            if (bounces > max_bounces) { ct.dead++; return fallback; }      // as above: the exit ray's result is discarded
             continue;
         }
         return h;

@@ -59,7 +59,9 @@ def test_c2_full_size_equals_oracle(nat, orc, scene, spp):
     p = sc.whitted_params(spec.camera, X, Y, spp=spp, max_bounces=4, miss=miss, seed=3)
     _, s64, hit64, st64 = sc.render_whitted_host(p, nat.F64)
     assert np.array_equal(s64[..., :3], sum_o), "FP64 whitted kernel differs from the oracle at 1280x720"
-    assert np.array_equal(hit64, hit_o) and int(st64[4]) == q_o
+    # stats[7]: continuation queries the reference casts with the bounce limit already spent (their result is
+    # discarded, ray.py:170-174); the kernel counts them without tracing them
+    assert np.array_equal(hit64, hit_o) and int(st64[4]) + int(st64[7]) == q_o
     _, s32, hit32, _ = sc.render_whitted_host(p, nat.F32)
     bad = np.abs(quant8(s32[..., :3] / spp) - quant8(s64[..., :3] / spp)).max(axis=2) > 1
     gate(f"C2 {scene} 1280x720 spp {spp} FP32 pixels beyond 1/255", bad.mean(), GATE_A_PIXELS)
