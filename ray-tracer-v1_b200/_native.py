@@ -366,6 +366,15 @@ def make_desc(fs):
     return d, {"f": fbuf, "i": ibuf, "small": sm}
 
 
+def scene_signature(fs):
+    """Content key of a FlatScene: the bytes of every array the device copy is made from.  Two scenes with the same key
+    upload the same blob, so a caller that re-flattens an unchanged scene list may skip the upload (``update(...,
+    skip_unchanged=True)``: the sub-millisecond frame entries do; the frame / env paths re-upload every time)."""
+    small = getattr(fs, "small", None)
+    return (tuple(getattr(fs, name).tobytes() for name in _DESC_F), tuple(getattr(fs, name).tobytes() for name in _DESC_I),
+            None if small is None else small.tobytes(), fs.bg.tobytes())
+
+
 class DeviceScene:
     """A flattened scene resident in HBM (``rt_scene``): one per GPU / rank."""
 
@@ -378,13 +387,23 @@ class DeviceScene:
         self.handle = h.value
         self.n = int(d.n)
         self.flat = fs
+        self._sig = None
 
-    def update(self, fs, stream=None):
-        """Re-flatten after the Python scene was mutated (the reference's scenes are mutable lists)."""
+    def update(self, fs, stream=None, skip_unchanged=False):
+        """Re-flatten after the Python scene was mutated (the reference's scenes are mutable lists).  -> True if the scene
+        was uploaded; with ``skip_unchanged`` an upload whose content equals the resident one is skipped (False)."""
+        if skip_unchanged:
+            sig = scene_signature(fs)
+            if sig == self._sig:
+                return False
+            self._sig = sig
+        else:
+            self._sig = None
         d, keep = make_desc(fs)
         check(lib().rt_scene_update(self.handle, C.byref(d), stream))
         self.n = int(d.n)
         self.flat = fs
+        return True
 
     def build_lbvh(self, huge_radius=50.0, stream=None):
         check(lib().rt_lbvh_build(self.handle, float(huge_radius), stream))

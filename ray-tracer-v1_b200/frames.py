@@ -26,15 +26,19 @@ class FrameContext:
         self.d2h_bytes = 0          # bytes of the last read-back
 
     # ---- scene -----------------------------------------------------------------------------------------------
-    def set_scene(self, fs, lbvh=None):
-        """(Re)upload the flattened scene; allocations are reused when the census is unchanged."""
+    def set_scene(self, fs, lbvh=None, skip_unchanged=False):
+        """(Re)upload the flattened scene; allocations are reused when the census is unchanged.  ``skip_unchanged``: a
+        scene whose flattened content equals the resident one is not uploaded again (``h2d_bytes`` = 0 for that frame)."""
+        uploaded = True
         if self.scene is None:
             self.scene = nat.DeviceScene(fs, self.device)
+            if skip_unchanged:
+                self.scene._sig = nat.scene_signature(fs)
         else:
-            self.scene.update(fs)
+            uploaded = self.scene.update(fs, skip_unchanged=skip_unchanged)
         n, nG, nP, nL = fs.radius.shape[0], fs.g_strength.shape[0], fs.p_strength.shape[0], fs.l_index.shape[0]
-        self.h2d_bytes = (16 + 32) * (3 * n + 2 * (nG + nP + nL)) + 2 * 4 * (n + nG + 2 * nP + nL) + n
-        if lbvh or (lbvh is None and self.scene.n > 256):
+        self.h2d_bytes = ((16 + 32) * (3 * n + 2 * (nG + nP + nL)) + 2 * 4 * (n + nG + 2 * nP + nL) + n) if uploaded else 0
+        if uploaded and (lbvh or (lbvh is None and self.scene.n > 256)):
             self.scene.build_lbvh()
         return self.scene
 

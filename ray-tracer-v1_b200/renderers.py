@@ -62,7 +62,7 @@ def render_whitted(fs, camera, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0,
     context: a ``FrameContext`` to render through -- its scene handle, HBM buffers, pinned host image and resident
     direction grid are reused from frame to frame (the render entries keep one); None = a throw-away scene handle."""
     if context is not None and not return_raw:
-        context.set_scene(fs)
+        context.set_scene(fs, skip_unchanged=True)      # the same scene list rendered again: nothing to upload
         view, _ = context.render_whitted(_xyz(camera), X, Y, spp=spp, max_bounces=max_bounces,
                                          shadow_max_bounces=shadow_max_bounces, miss=miss, seed=seed, prenorm=prenorm,
                                          precision=_precision(precision))
@@ -325,9 +325,10 @@ class SimplifiedFBRenderer:
         self._renders += 1
         fs = flatten_scene(self.scene)                                      # re-flattened: the scene list is mutable
         if self._sc is None:
-            self._sc = nat.DeviceScene(fs, self.device)                     # persistent handle, re-uploaded per call
+            self._sc = nat.DeviceScene(fs, self.device)                     # persistent handle
+            self._sc._sig = nat.scene_signature(fs)
         else:
-            self._sc.update(fs)
+            self._sc.update(fs, skip_unchanged=True)                        # re-uploaded when the list was mutated
         sc = self._sc
         p = sc.simple_params(width, height, cam=(0.0, 0.0, 1.0), sun_pos=_xyz(self.sun_position),
                              sun_col=self.sun_color.getList(), sun_id=7, max_bounces=self.max_bounces, seed=seed)

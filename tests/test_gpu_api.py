@@ -195,6 +195,16 @@ def test_render_entry_points(rt, orc):
             colour, stats, strategies = exp._trace_custom_traditional(ray, balls, 0)
             assert colour.getList() == [float(v) for v in z["rgb"][yi, xi]] and strategies == ['traditional_mimic']
             assert stats['light_hits'] == int(sum(colour.getList()) / 3 > 10)
+        # an unchanged scene list is not uploaded again (content key), a mutated one is: same image twice, then the image
+        # a fresh experiment renders of the mutated list
+        _, again = exp.render_custom_scene(balls, "traditional", None)
+        assert np.array_equal(again, z["image"]) and exp._context().h2d_bytes == 0
+        balls[1].centre = Vector(0.4, 0.1, -2.5)
+        _, moved = exp.render_custom_scene(balls, "traditional", None)
+        assert exp._context().h2d_bytes > 0 and not np.array_equal(moved, z["image"])
+        fresh = CustomSceneExperiment(output_dir=tmp, precision="f64")
+        fresh.config.update(image_width=320, image_height=240, samples_per_pixel=1, max_bounces=1)
+        assert np.array_equal(fresh.render_custom_scene(balls, "traditional", None)[1], moved)
         # render_true_original: 601x601 notebook grid; compare its centre crop rows with the 121-grid golden's geometry
         full = exp.render_true_original(scenes.build_balls_in_space(as_rendered=False).spheres, None)
         assert full.shape == (601, 601, 3) and full.max() <= 1.0 and full.min() >= 0.0
