@@ -352,6 +352,8 @@ def main():
     ap.add_argument("--spp", type=int, default=SPP)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the per-shape table and the sustained run")
+    ap.add_argument("--flush-mib", type=int, default=256, help="size of the L2 flush between timed steps (diagnostic; 0 = none)")
+    ap.add_argument("--debug-ranks", action="store_true", help="every rank prints its own per-step times to stderr")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -379,7 +381,7 @@ def main():
     r = ShardedPathRenderer(device=local)
     r.set_scene(fs)
     cam = spec.camera
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")     # > 126 MB L2
+    flush = torch.empty(max(args.flush_mib, 1) << 20, dtype=torch.uint8, device="cuda")     # default 256 MiB > 126 MB L2
 
     def barrier():
         if world > 1:
@@ -408,26 +410,22 @@ def main():
     peak_clock.start()
     fp32_peak, _ = nat.measure_fp32_peak(local, 25)
     peak_clock = peak_clock.stop()
-    for i in range(args.warmup):
-        step(1000 + i)
-    barrier()
-
-    # ---- device-timed steps (inputs resident in HBM); L2 flushed, untimed, between steps
-    sampler = ClockSampler(local)
-    sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     counters = torch.zeros(8, dtype=torch.int64, device="cuda")
     launches = 0
-    barrier()
-    for i in range(args.steps):
+
+    def one_step(i, ev_i, kev_i):
+        """One step of the benchmark: [L2 flush, untimed] [event] the frame [event] [counters].  The warm-up steps run this
+        very function, so nothing in the timed region is a first use (the first `counters += r.stats` alone loads a
+        torch kernel module: 15 ms of idle GPU after which the next two frames of every rank ran 3-5 % slow)."""
+        nonlocal launches, counters
         # L2 flush between the timed steps (untimed: outside the step's event pair).  The K steps are bracketed by a
         # barrier + synchronize on both sides, not individually: inside, the frame protocol itself keeps the ranks together
-        flush.zero_()
-        ev[i][0].record()
+        if args.flush_mib:
+            flush.zero_()
+        ev_i[0].record()
         # the step, with the dominant kernel bracketed separately for the roofline
         if fused:
-            r.render_fused(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, kernel_events=kev[i], in_kernel=in_kernel)
+            r.render_fused(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, mode=args.mode, kernel_events=kev_i, in_kernel=in_kernel)
             launches += r.launches
         else:
             r._ensure(W, H)
@@ -435,9 +433,9 @@ def main():
             smp = sample_ranges(spp, world)[rank] if args.mode == "samples" else (0, spp)
             r.stats.zero_()
             p = r.scene.path_params(cam, W, H, spp, DEPTH, THRESHOLD, seed=i, fov=FOV, rows=rows, samples=smp)
-            kev[i][0].record()
+            kev_i[0].record()
             r.scene.render_path(p, r.accum, nat.F32, stats=r.stats)
-            kev[i][1].record()
+            kev_i[1].record()
             if args.mode == "tiles":
                 r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32, rows=rows)
                 launches += 2
@@ -451,12 +449,32 @@ def main():
                 if rank == 0:
                     r.scene.resolve(r.accum, W, H, spp, r.image, nat.F32)
                     launches += 1
-        ev[i][1].record()
+        ev_i[1].record()
         counters += r.stats
+
+    mk_ev = lambda: (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))      # noqa: E731
+    for i in range(args.warmup):
+        one_step(1000 + i, mk_ev(), mk_ev())
+    barrier()
+
+    # ---- device-timed steps (inputs resident in HBM); L2 flushed, untimed, between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [mk_ev() for _ in range(args.steps)]
+    kev = [mk_ev() for _ in range(args.steps)]
+    counters.zero_()
+    launches = 0
+    barrier()
+    for i in range(args.steps):
+        one_step(i, ev[i], kev[i])
     barrier()
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     kern_ms = [a.elapsed_time(b) for a, b in kev]
+    if args.debug_ranks:
+        gaps = [ev[i][1].elapsed_time(ev[i + 1][0]) for i in range(args.steps - 1)]
+        print(f"[rank {rank}] step ms {' '.join(f'{v:.3f}' for v in step_ms)} | kernel ms {' '.join(f'{v:.3f}' for v in kern_ms)} "
+              f"| gap (flush) ms {' '.join(f'{v:.3f}' for v in gaps)}", file=sys.stderr, flush=True)
     t = torch.tensor([sum(step_ms), sum(kern_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -598,7 +616,7 @@ def main():
                        + ("(ONE path-kernel launch per rank and frame: epilogue stores/reductions over NVLink peer memory, epoch "
                           "protocol, band resolve and collection inside the launch)" if fused and in_kernel else
                           "(path-kernel epilogue over NVLink peer memory, flag / resolve launches around it)" if fused else "(NCCL)"),
-                       "l2": "flushed between steps (256 MiB memset, untimed); inputs are a 3 KB scene",
+                       "l2": (f"flushed between steps ({args.flush_mib} MiB memset, untimed)" if args.flush_mib else "NOT flushed (diagnostic run)") + "; inputs are a 3 KB scene",
                        "ray_definition": "one nearest-hit query over the scene (SURVEY 8d)"},
             "rays_ref_compatible_per_s": rays_ref / (total_ms * 1e-3) / 1e6,
             "rays_per_pixel_sample": rays_ref / (args.steps * W * H * spp),
