@@ -636,10 +636,11 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     pp.regenerate = (p->schedule & 1) != 0;
     pp.primary_cull = (p->schedule & 2) == 0;
     pp.sink = RT_SINK_ACCUM; pp.tile_step = 1; pp.world = 1; pp.spp_total = p->s1 - p->s0;
-    pp.ksplit_log2 = 0;
+    pp.ksplit_log2 = 0; pp.ksplit2_log2 = 0; pp.fine_pixels = 0; pp.gx2 = pp.gy2 = pp.stripe2 = 0;
     if (sink && sink->mode != RT_SINK_ACCUM) {
         if (!pp.int_fold) return fail(RT_ERR_UNSUPPORTED, "fused sinks need integer colours and <= 65536 samples per launch");
         pp.sink = sink->mode;
+        pp.timed_out = sink->timed_out;          // read under the frame protocol only (and by the RT_TRACE_WARPS development build)
         if (sink->mode == RT_SINK_IMAGE) {
             if (!sink->image || sink->tile_step < 1 || sink->tile_first < 0) return fail(RT_ERR_INVALID, "bad image sink");
             pp.image = sink->image; pp.tile_step = sink->tile_step;
@@ -705,6 +706,16 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             const int per_lane = view.bvh.nodes > 0 ? 2 : 8;
             while (lk < 3 && (ns >> (lk + 1)) >= per_lane) ++lk;
             while (lk < 5 && (pixels << lk) / 32 < want && (ns >> (lk + 1)) >= 2) ++lk;
+            // the LAST work units of the launch are finer (more lanes per pixel, every lane still keeps >= 2 samples):
+            // 1.5 coarse units' worth of pixels per resident warp, so that the drain of the launch is a fine unit long
+            // instead of a coarse one (brute-force scenes; with a hierarchy the units are short already)
+            int lk2 = lk + 2 < 5 ? lk + 2 : 5;
+            while (lk2 > lk && (ns >> lk2) < 2) --lk2;
+            static const bool no_fine = std::getenv("RT_B200_NO_FINE_TAIL") != nullptr;      // A/B switch for measurements
+            if (view.bvh.nodes == 0 && lk2 > lk && !no_fine) {
+                pp.ksplit2_log2 = lk2;
+                pp.fine_pixels = (int)(3LL * 32 * sms * (32 >> lk) / 2);
+            }
         }
         pp.ksplit_log2 = lk;
     }

@@ -314,6 +314,15 @@ __global__ void __launch_bounds__(256, RT_WHITTED_MIN_BLOCKS) whitted_heavy_kern
 // ------------------------------------------------------------------ epoch flags in peer memory (rt_path_sink::sync)
 // wait: system-scope acquire loads until the flag has reached the epoch (wrap-safe compare); gives up after
 // timeout_cycles and reports instead of hanging.  post: system-scope release store; the caller has fenced.
+// 1: a warp asks for its NEXT work unit before it traces the current one (the counter's latency is never waited for);
+// 0: when it is done.  Prefetching means that when the counter runs out every warp still owns TWO units, so the drain
+// of a launch is twice as long; with 8 warps per scheduler the ~1 us of the atomic is hidden anyway.
+#ifndef RT_PREFETCH_UNIT
+#define RT_PREFETCH_UNIT 0
+#endif
+#ifdef RT_TRACE_WARPS
+RT_DEV unsigned long long rt_globaltimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#endif
 RT_DEV void flag_wait(const unsigned *flag, unsigned epoch, long long timeout_cycles, int *timed_out) {
     const long long t0 = clock64();
     for (;;) {
@@ -431,13 +440,14 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     // (summed with shuffles at the end).  A warp then covers 32/k pixels -- pw x ph = 8x4, 8x2, 4x2, 2x2, 2x1, 1x1 --
     // and a CTA (4 x 2 warps) 256/k pixels: finer work units for small frames, row bands and sample ranges, so the
     // grid keeps tens of waves and the drain at the end of the launch stays short.
-    const int lk = pp.ksplit_log2, kk = 1 << lk;
-    const int pw_sh = lk == 0 ? 3 : lk == 1 ? 3 : lk == 2 ? 2 : lk <= 4 ? 1 : 0;
-    const int ph_sh = (5 - lk) - pw_sh;
+    //
+    // The work units of a launch come from TWO tile grids: the coarse one (ksplit_log2) over the first owned stripes and
+    // a fine one (ksplit2_log2: four times the lanes per pixel, a quarter of the samples per lane) over the last few.
+    // A coarse unit of the headline frame keeps a warp busy for ~160 us, and a launch whose last units are that long ends
+    // with every warp idle for 116 us on average (tools/debug/warp_trace.py) -- nothing in a 17-ms frame, 5 % of the
+    // 2.2-ms share of one of 8 GPUs; with the fine units last the drain is a quarter of that.  Sums are integers: the
+    // frame does not depend on which lanes traced which samples.
     const int w_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
-    const int sub = lane_ & (kk - 1), pl = lane_ >> lk;
-    // CTA rows: cth = 2 << ph_sh of them; tile_step > 1: this launch owns every tile_step-th 8-row stripe from y0
-    const int cth_sh = ph_sh + 1, cps_sh = 3 - cth_sh;                 // CTA rows per stripe = 1 << cps_sh
     unsigned n_rays = 0, n_inter = 0, n_light = 0, n_small = 0, n_query = 0, n_tests = 0, n_boxes = 0;
     const V3<T> cam = mk<T>(pp.cam[0], pp.cam[1], pp.cam[2]);
     const int ns = pp.s1 - pp.s0;
@@ -450,16 +460,36 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     // inside the loop).  The first units are static (CTA c, warp w -> unit 8c + w); the counter hands out the rest.
     // The fetch for the NEXT unit is issued before the current one is traced, so its latency is never waited for.
     // pp.sched = {next, done}: the last warp of the launch to finish resets both, so no memset precedes a launch.
-    const unsigned n_units = (unsigned)(pp.gx * pp.gy) << 3, first_dyn = (unsigned)gridDim.x << 3;
+    const unsigned n_coarse = (unsigned)(pp.gx * pp.gy) << 3, n_units = n_coarse + ((unsigned)(pp.gx2 * pp.gy2) << 3);
+    const unsigned first_dyn = (unsigned)gridDim.x << 3;
+#ifdef RT_TRACE_WARPS
+    const unsigned long long rt_trace_t0 = rt_globaltimer();
+    unsigned long long rt_trace_last = 0, rt_trace_unit = 0;
+#endif
     for (unsigned unit = ((unsigned)blockIdx.x << 3) + (unsigned)w_; unit < n_units;) {
     unsigned nxt = 0;
+#if RT_PREFETCH_UNIT
     if (lane_ == 0) nxt = first_dyn + atomicAdd(pp.sched, 1u);
+#endif
     RT_ASSERT(unit < n_units);
-    const int tile = (int)(unit >> 3), wt = (int)(unit & 7u);      // wt: the warp's place in the 4 x 2 warp tile
-    const int by = tile / pp.gx, bx = tile - by * pp.gx;
+#ifdef RT_TRACE_WARPS
+    rt_trace_last = rt_globaltimer(); rt_trace_unit = unit;
+#endif
+    const bool fine = unit >= n_coarse;                            // warp-uniform
+    const unsigned u_ = fine ? unit - n_coarse : unit;
+    const int lk = fine ? pp.ksplit2_log2 : pp.ksplit_log2, kk = 1 << lk;
+    const int gx_ = fine ? pp.gx2 : pp.gx, stripe0 = fine ? pp.stripe2 : 0;
+    const int pw_sh = lk == 0 ? 3 : lk == 1 ? 3 : lk == 2 ? 2 : lk <= 4 ? 1 : 0;
+    const int ph_sh = (5 - lk) - pw_sh;
+    const int sub = lane_ & (kk - 1), pl = lane_ >> lk;
+    // CTA rows: cth = 2 << ph_sh of them; tile_step > 1: this launch owns every tile_step-th 8-row stripe from y0
+    const int cth_sh = ph_sh + 1, cps_sh = 3 - cth_sh;                 // CTA rows per stripe = 1 << cps_sh
+    const int tile = (int)(u_ >> 3), wt = (int)(u_ & 7u);          // wt: the warp's place in the 4 x 2 warp tile
+    const int by = tile / gx_, bx = tile - by * gx_;
+    const int ys = pp.y0 + (((by >> cps_sh) + stripe0) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
+                   ((wt >> 2) << ph_sh);                           // first row of the warp's pixel block
     const int x = (((bx << 2) + (wt & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
-    const int y = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
-                  ((wt >> 2) << ph_sh) + (pl >> pw_sh);
+    const int y = ys + (pl >> pw_sh);
     const bool has_pixel = x < pp.W && y < pp.y1;
     const uint32_t pixel = (uint32_t)(y * pp.W + x);
     // integer-valued sums: exact in uint32 (int fold: colours <= 65535, samples per launch <= 65536) / in double
@@ -470,7 +500,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     if constexpr (kMode == 3 && !kRegen && RT_PRIMARY_CULL) if (pp.primary_cull) {
         const int bw = 1 << pw_sh, bh = 1 << ph_sh;   // the warp's pixel block
         const int x0 = ((bx << 2) + (wt & 3)) << pw_sh;
-        const int y0 = pp.y0 + ((by >> cps_sh) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) + ((wt >> 2) << ph_sh);
+        const int y0 = ys;
         const V3<T> d0 = path_camera_ray<T>(pp, x0, y0, T(0.5) * T(bw), T(0.5) * T(bh));
         const float ex = 0.5f * (float)bw * (2.f / (float)pp.W) * (float)pp.aspect * (float)pp.half_w;
         const float ey = 0.5f * (float)bh * (2.f / (float)pp.H) * (float)pp.half_h;
@@ -683,8 +713,18 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
             accum[o] = out;
         }
     }
+#if !RT_PREFETCH_UNIT
+    if (lane_ == 0) nxt = first_dyn + atomicAdd(pp.sched, 1u);
+#endif
     unit = __shfl_sync(0xffffffffu, nxt, 0);
     }   // work units of this warp
+#ifdef RT_TRACE_WARPS
+    // development build (tools/debug/warp_trace.py): when every warp entered its unit loop and when it left it, in ns
+    if (pp.timed_out && !pp.sync && lane_ == 0) {
+        unsigned long long *tr = reinterpret_cast<unsigned long long *>(pp.timed_out) + 4 * ((size_t)blockIdx.x * 8 + w_);
+        tr[0] = rt_trace_t0; tr[1] = rt_globaltimer(); tr[2] = rt_trace_last; tr[3] = rt_trace_unit;
+    }
+#endif
     bool sync = false;
     if constexpr (!M<T>::exact && kIntFold) sync = pp.sync != 0;
     if (lane_ == 0) {
@@ -1539,8 +1579,25 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     const unsigned gy = step > 1 ? (unsigned)((tiles + step - 1) / step) * (8 / cth) : (unsigned)((rows + cth - 1) / cth);
     PathDev<T> ppl = pp;                                          // + the tile grid the persistent CTAs walk
     ppl.gx = (pp.W + ctw - 1) / ctw; ppl.gy = (int)gy;
+    ppl.gx2 = ppl.gy2 = ppl.stripe2 = 0;
+    // fine grid over the last owned stripes (see path_kernel): at most half of them, whole 8-row stripes
+    const int lk2 = pp.ksplit2_log2;
+    if (lk2 > lk && lk2 <= 5 && pp.fine_pixels > 0) {
+        const int owned = (tiles + step - 1) / step;                              // 8-row stripes of this launch
+        int fs = (int)(((long long)pp.fine_pixels + 8LL * pp.W - 1) / (8LL * pp.W));
+        if (fs > owned / 2) fs = owned / 2;
+        if (fs >= 1) {
+            const int pw2 = lk2 == 0 ? 3 : lk2 == 1 ? 3 : lk2 == 2 ? 2 : lk2 <= 4 ? 1 : 0, ph2 = (5 - lk2) - pw2;
+            const int ctw2 = 4 << pw2, cth2 = 2 << ph2;
+            const int sb = owned - fs, rows_a = sb * 8;                            // (tile_step == 1: rows of the coarse part)
+            ppl.stripe2 = sb;
+            ppl.gy = step > 1 ? sb * (8 / cth) : (rows_a + cth - 1) / cth;
+            ppl.gx2 = (pp.W + ctw2 - 1) / ctw2;
+            ppl.gy2 = step > 1 ? fs * (8 / cth2) : (rows - rows_a + cth2 - 1) / cth2;
+        }
+    }
     ppl.sched = sched;
-    const long long tiles_total = (long long)ppl.gx * ppl.gy;
+    const long long tiles_total = (long long)ppl.gx * ppl.gy + (long long)ppl.gx2 * ppl.gy2;
     dim3 grid(1), block(256);
     using v4 = typename M<T>::v4;
     const size_t extra = 256 * sizeof(double);                   // div255 table of the integer fold

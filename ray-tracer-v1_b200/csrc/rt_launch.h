@@ -31,6 +31,11 @@ template <typename T> struct PathDev {
     T inv_W, inv_H;              // product build: 1/W, 1/H (the parity build divides like the reference)
     T mirror_threshold;
     int gx, gy;                          // tile grid of the launch (set by launch_path)
+    // second ("fine") tile grid over the last owned stripes of the launch: same pixels-per-CTA logic with MORE lanes per
+    // pixel (ksplit2_log2 > ksplit_log2), i.e. work units a quarter as long, handed out after the coarse ones so that
+    // the drain at the end of the launch is a quarter as long (gx2 * gy2 = 0: none).  Set by launch_path from
+    // ksplit2_log2 / fine_pixels, which the API fills in.
+    int gx2, gy2, stripe2, ksplit2_log2, fine_pixels;
     unsigned *sched;                     // {next work unit, warps done}: zero between launches (self-resetting)
     uint32_t k0, k1;
     uint32_t rk[20];                     // Philox round keys k0 + r*W0, k1 + r*W1 (constant-bank operands of the rounds)

@@ -610,6 +610,18 @@ def test_sample_split_gives_the_same_frame(nat):
         sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2, ksplit=8), sink)
     want = np.minimum(1.0, np.floor(ref[..., :3].astype(np.float64) / spp) / 255.0).astype(np.float32)
     assert np.array_equal(img.cpu().numpy(), want)
+    # automatic split: the last owned stripes of a launch are traced by FINER work units (more lanes per pixel) than the
+    # first ones -- two tile grids in one launch; three ranks' interleaved stripes, ragged last stripe
+    img.zero_()
+    for r in range(3):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step, sink.image = nat.SINK_IMAGE, r, 3, img.data_ptr()
+        sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2), sink)
+    assert np.array_equal(img.cpu().numpy(), want)
+    big = sc.path_params(spec.camera, 640, 360, 16, 6, 0.0, seed=4)               # coarse k = 2, fine k = 8 over the last stripes
+    _, auto, st_auto = sc.render_path_host(big, nat.F32)
+    _, flat, st_flat = sc.render_path_host(sc.path_params(spec.camera, 640, 360, 16, 6, 0.0, seed=4, ksplit=2), nat.F32)
+    assert np.array_equal(auto, flat) and np.array_equal(st_auto[:5], st_flat[:5])
     sc.close()
 
 
