@@ -458,7 +458,8 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     // counter, so the scene staging, the div255 table and the statistics flush are paid once per CTA instead of once
     // per tile, the load balances at warp granularity, and the eight warps of a CTA drift apart freely (no barrier
     // inside the loop).  The first units are static (CTA c, warp w -> unit 8c + w); the counter hands out the rest.
-    // The fetch for the NEXT unit is issued before the current one is traced, so its latency is never waited for.
+    // A warp asks for its next unit when it has finished the current one (RT_PREFETCH_UNIT: asking before tracing hid the
+    // counter's latency but left every warp with two units in hand when the counter ran out -- twice the drain).
     // pp.sched = {next, done}: the last warp of the launch to finish resets both, so no memset precedes a launch.
     const unsigned n_coarse = (unsigned)(pp.gx * pp.gy) << 3, n_units = n_coarse + ((unsigned)(pp.gx2 * pp.gy2) << 3);
     const unsigned first_dyn = (unsigned)gridDim.x << 3;
