@@ -87,6 +87,11 @@ int rt_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes,
 int rt_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes, void *stream);
 int rt_memset_dev(int device, void *dst_dev, int value, size_t bytes, void *stream);
 int rt_stream_sync(int device, void *stream);
+/* a non-blocking stream (e.g. for copies that overlap the next kernel); rt_stream_wait_stream: everything enqueued on
+ * `waiter` after the call runs after everything enqueued on `waited` before it (NULL = the default stream). */
+int rt_stream_create(int device, void **out_stream);
+int rt_stream_destroy(int device, void *stream);
+int rt_stream_wait_stream(int device, void *waiter, void *waited);
 /* FP32 roofline denominator: dependent-free FFMA loop on every SM, timed with CUDA events (synchronous). */
 int rt_measure_fp32_peak(int device, int repeats, double *tflops_out, double *ms_out);
 

@@ -107,6 +107,9 @@ SIGNATURES = {
     "rt_memcpy_d2h": (C.c_int, [C.c_int, vp, vp, C.c_size_t, vp]),
     "rt_memset_dev": (C.c_int, [C.c_int, vp, C.c_int, C.c_size_t, vp]),
     "rt_stream_sync": (C.c_int, [C.c_int, vp]),
+    "rt_stream_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "rt_stream_destroy": (C.c_int, [C.c_int, vp]),
+    "rt_stream_wait_stream": (C.c_int, [C.c_int, vp, vp]),
     "rt_measure_fp32_peak": (C.c_int, [C.c_int, C.c_int, c_dp, c_dp]),
     "rt_scene_create": (C.c_int, [C.c_int, C.POINTER(SceneDesc), C.POINTER(vp)]),
     "rt_scene_update": (C.c_int, [vp, C.POINTER(SceneDesc), vp]),

@@ -403,6 +403,32 @@ RT_EXPORT int rt_stream_sync(int device, void *stream) {
     return RT_OK;
 }
 
+// a second stream for copies that overlap the next kernel, and "stream A waits for what stream B holds now"
+RT_EXPORT int rt_stream_create(int device, void **out_stream) {
+    if (!out_stream) return fail(RT_ERR_INVALID, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaStream_t s = nullptr;
+    CU(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    *out_stream = s;
+    return RT_OK;
+}
+RT_EXPORT int rt_stream_destroy(int device, void *stream) {
+    if (!stream) return RT_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaStreamDestroy(S(stream)));
+    return RT_OK;
+}
+RT_EXPORT int rt_stream_wait_stream(int device, void *waiter, void *waited) {
+    CU(cudaSetDevice(device));
+    cudaEvent_t e = nullptr;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    cudaError_t rc = cudaEventRecord(e, S(waited));
+    if (rc == cudaSuccess) rc = cudaStreamWaitEvent(S(waiter), e, 0);
+    cudaEventDestroy(e);                      // released once the recorded work has completed
+    if (rc != cudaSuccess) return cuda_fail(rc, "rt_stream_wait_stream");
+    return RT_OK;
+}
+
 RT_EXPORT int rt_measure_fp32_peak(int device, int repeats, double *tflops_out, double *ms_out) {
     CU(cudaSetDevice(device));
     cudaDeviceProp p;

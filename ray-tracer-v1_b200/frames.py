@@ -73,6 +73,9 @@ class FrameContext:
         p = self.scene.path_params(cam, W, H, spp, max_bounces, mirror_threshold, seed=seed, fov=fov, rows=rows,
                                    samples=samples)
         self.stats.fill(0, stream)
+        bands = self._bands(W, p.y0, p.y1, p.s1 - p.s0) if (resolve and read_back) else None
+        if bands:
+            return self._render_path_banded(p, bands, W, H, precision, stream)
         self.scene.render_path(p, self.accum, precision, stats=self.stats, stream=stream)
         self.launches = 1
         if resolve:
@@ -81,6 +84,47 @@ class FrameContext:
         if not read_back:
             return None, None
         return self.read_back(W, H, (p.y0, p.y1), stream)
+
+    # a frame whose image takes longer to copy out than a launch costs is rendered in row bands: band b is copied to the
+    # pinned host image (copy stream) while band b + 1 renders.  Pixels are keyed by (pixel, sample), so the frame is the
+    # same bit for bit (tested); every extra launch costs ~30 us of drain, every band hides its share of the copy.
+    BANDS = 4
+    BAND_MIN_IMAGE_BYTES = 8 << 20
+    BAND_MIN_SAMPLES = 24 << 20          # pixel-samples: below ~10 ms of kernel the split is not worth its launches
+
+    def _bands(self, W, y0, y1, ns):
+        rows = y1 - y0
+        if self.BANDS < 2 or rows * W * 12 < self.BAND_MIN_IMAGE_BYTES or rows * W * ns < self.BAND_MIN_SAMPLES:
+            return None
+        stripes = (rows + 7) // 8
+        cuts = [y0 + 8 * ((stripes * k) // self.BANDS) for k in range(self.BANDS)] + [y1]
+        return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+
+    def _render_path_banded(self, p, bands, W, H, precision, stream):
+        L = nat.lib()
+        if getattr(self, "_copy_stream", None) is None:
+            cs = nat.vp()
+            nat.check(L.rt_stream_create(self.device, C.byref(cs)))
+            self._copy_stream = cs
+        cs = self._copy_stream
+        self._ring_at = (self._ring_at + 1) % self.HOST_RING
+        self.host_image = self.host_ring[self._ring_at]
+        ns, y0, y1 = p.s1 - p.s0, p.y0, p.y1
+        self.launches = 0
+        for (a, b) in bands:
+            p.y0, p.y1 = a, b
+            self.scene.render_path(p, self.accum, precision, stats=self.stats, stream=stream)
+            self.scene.resolve(self.accum, W, H, ns, self.image, precision, rows=(a, b), stream=stream)
+            self.launches += 2
+            nat.check(L.rt_stream_wait_stream(self.device, cs, stream))
+            off, nbytes = a * W * 12, (b - a) * W * 12
+            nat.check(L.rt_memcpy_d2h(self.device, self.host_image.ptr + off, self.image.ptr + off, nbytes, cs))
+        p.y0, p.y1 = y0, y1
+        nat.check(L.rt_memcpy_d2h(self.device, self.host_stats.ptr, self.stats.ptr, 64, stream))
+        nat.check(L.rt_stream_sync(self.device, stream))
+        nat.check(L.rt_stream_sync(self.device, cs))
+        self.d2h_bytes = (y1 - y0) * W * 12 + 64
+        return self.host_image.array, self.host_stats.array
 
     def render_whitted(self, cam, X, Y, spp=1, max_bounces=1, shadow_max_bounces=0, miss=None, seed=0, prenorm=False,
                        precision=nat.F32, rows=None, samples=None, read_back=True, stream=None):
@@ -115,6 +159,9 @@ class FrameContext:
             if b is not None:
                 b.free()
         self.host_ring = []
+        if getattr(self, "_copy_stream", None) is not None:
+            nat.lib().rt_stream_destroy(self.device, self._copy_stream)
+            self._copy_stream = None
         self.accum = self.image = self.stats = self.hit = self.host_image = self.host_stats = None
         self._key = None
         if self.scene is not None:

@@ -165,3 +165,25 @@ def test_c5_full_size_equals_oracle(rt, orc, flavour):
     # measured on the B200: see profiles/parity_r2.txt (gate = 3x the measured drop-out rate)
     gate(f"C5 {flavour} 65,536 envs FP32 episodes leaving the FP64 trajectory", 1 - follows.mean(), 1 - GATE_ENV_FOLLOW[flavour])
     e64.close(); e32.close()
+
+
+def test_banded_read_back_is_the_same_frame(rt):
+    """TraditionalRenderer.render of a large frame renders in row bands so that band b is copied to the host while band
+    b + 1 renders (FrameContext.BANDS): same image, same counters as the single launch."""
+    from ray_tracer_v1_b200 import scenes
+    from ray_tracer_v1_b200.renderers import ComplexTraditionalRenderer
+    spec = scenes.build_complex()
+    out = {}
+    for bands in (4, 1, 3):
+        r = ComplexTraditionalRenderer(seed=3)
+        r.scene, r.light_sources = spec.spheres, [s for s in spec.spheres if s.material.emitive]
+        r.small_lights = [s for s in r.light_sources if s.radius < 0.5]
+        r.render(64, 36, samples_per_pixel=1, max_bounces=5)            # creates the context
+        r._ctx.BANDS = bands
+        img = r.render(1920, 1080, samples_per_pixel=16, max_bounces=5).copy()
+        assert (r._ctx.launches == 2 * bands), (bands, r._ctx.launches)
+        out[bands] = (img, dict(r.stats))
+    for bands in (4, 3):
+        assert np.array_equal(out[bands][0], out[1][0])
+        for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits"):
+            assert out[bands][1][k] == out[1][1][k], k
