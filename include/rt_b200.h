@@ -300,7 +300,14 @@ typedef struct rt_path_sink {
                                          "ranks" share ONE device (tests) */
     int32_t spp_total;                /* sync + SCATTER_ADD: samples per pixel of the whole frame (the band resolve
                                          divides by it; p->s0/s1 is only this rank's range) */
-    int32_t reserved_;
+    int32_t col_split;                /* IMAGE, != 0: 2-D interleave instead of whole stripes -- the launch covers in EVERY
+                                         8-row stripe s the column segment (tile_first + s) mod tile_step of tile_step
+                                         equal segments (W a multiple of tile_step).  Every rank then holds the same
+                                         number of pixels whatever H is (1080 rows are 135 stripes: 17 or 16 per rank of
+                                         8), and a diagonal share of the picture.  A segment must hold whole work units
+                                         (8 pixels wide for launches of >= 64 samples, up to 32 for short ones): if it
+                                         does not, the launch renders whole stripes as without col_split -- every rank
+                                         of a frame decides the same from the same W, H, samples and tile_step */
 } rt_path_sink;
 #define RT_FLAG_WORDS 64
 /* sync = 1 -- one launch per rank and frame, no other kernel and no host round trip on the data path:

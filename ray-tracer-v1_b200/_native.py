@@ -80,7 +80,7 @@ class PathSink(C.Structure):
                 ("image", C.c_void_p), ("accum", C.c_void_p * RT_MAX_PEERS), ("band_y", C.c_int32 * (RT_MAX_PEERS + 1)),
                 ("sync", C.c_int32), ("rank", C.c_int32), ("epoch", C.c_uint32), ("go_epoch", C.c_uint32),
                 ("flags", C.c_void_p * RT_MAX_PEERS), ("timed_out", C.c_void_p), ("timeout_ms", C.c_int32),
-                ("max_ctas", C.c_int32), ("spp_total", C.c_int32), ("reserved_", C.c_int32)]
+                ("max_ctas", C.c_int32), ("spp_total", C.c_int32), ("col_split", C.c_int32)]
 
 
 FLAG_WORDS = 64

@@ -662,6 +662,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     pp.regenerate = (p->schedule & 1) != 0;
     pp.primary_cull = (p->schedule & 2) == 0;
     pp.sink = RT_SINK_ACCUM; pp.tile_step = 1; pp.world = 1; pp.spp_total = p->s1 - p->s0;
+    pp.col_step = 1; pp.col_first = 0; pp.seg_w = p->W;
     pp.ksplit_log2 = 0; pp.ksplit2_log2 = 0; pp.fine_pixels = 0; pp.gx2 = pp.gy2 = pp.stripe2 = 0;
     if (sink && sink->mode != RT_SINK_ACCUM) {
         if (!pp.int_fold) return fail(RT_ERR_UNSUPPORTED, "fused sinks need integer colours and <= 65536 samples per launch");
@@ -671,6 +672,12 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             if (!sink->image || sink->tile_step < 1 || sink->tile_first < 0) return fail(RT_ERR_INVALID, "bad image sink");
             pp.image = sink->image; pp.tile_step = sink->tile_step;
             pp.y0 = sink->tile_first * 8; pp.y1 = p->H;
+            if (sink->col_split && sink->tile_step > 1) {
+                if (p->W % sink->tile_step != 0) return fail(RT_ERR_INVALID, "col_split: W must be a multiple of tile_step");
+                if (sink->tile_first >= sink->tile_step) return fail(RT_ERR_INVALID, "col_split: tile_first must be < tile_step");
+                pp.col_step = sink->tile_step; pp.col_first = sink->tile_first; pp.seg_w = p->W / sink->tile_step;
+                pp.tile_step = 1; pp.y0 = 0;              // every stripe, one column segment of each
+            }
             if (p->s0 != 0) return fail(RT_ERR_INVALID, "an image sink resolves in the kernel: the launch must cover all samples");
         } else if (sink->mode == RT_SINK_SCATTER_ADD) {
             if (sink->world < 1 || sink->world > RT_MAX_PEERS) return fail(RT_ERR_INVALID, "bad world size");
@@ -714,6 +721,8 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     // sample split (automatic): k lanes per pixel so that a lane keeps about 8 samples -- measured best at 8, 16, 32 and
     // 64 samples per launch (k = 1, 2, 4, 8: tighter camera-ray cones against per-unit overhead) -- and, for small frames,
     // more lanes per pixel until there are ~4 warp tiles per resident warp (every lane keeps >= 2 samples)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    pp.ksplit_log2 = 0; pp.ksplit2_log2 = 0; pp.fine_pixels = 0;
     if (pp.int_fold && p->ksplit != 0 && !xr) {
         static int sm_cache[64] = {0};
         int sms = sc->device >= 0 && sc->device < 64 ? sm_cache[sc->device] : 0;
@@ -723,7 +732,7 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
         }
         const long long want = 4LL * 32 * sms;                 // warp tiles: 4 per resident warp (32 warps per SM)
         const int rows = pp.y1 - pp.y0, step = pp.tile_step > 1 ? pp.tile_step : 1, ns = p->s1 - p->s0;
-        const long long pixels = (long long)pp.W * ((rows + step - 1) / step);
+        const long long pixels = (long long)pp.seg_w * ((rows + step - 1) / step);
         int lk = 0;
         if (p->ksplit > 0) { while ((1 << (lk + 1)) <= p->ksplit && lk < 5) ++lk; }
         else {
@@ -744,6 +753,16 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
             }
         }
         pp.ksplit_log2 = lk;
+    }
+    // 2-D interleave: a column segment must hold whole work units of both tile grids (32 / 16 / 8 / 4 pixels wide for
+    // 1-2 / 4 / 8-16 / 32 lanes per pixel); if it does not, the launch falls back to whole stripes and the split is
+    // chosen again for that geometry.  Every rank of a frame decides the same from the same numbers.
+    if (pp.col_step <= 1) break;
+    auto unit_w = [](int lk) { return 4 << (lk == 0 ? 3 : lk == 1 ? 3 : lk == 2 ? 2 : lk <= 4 ? 1 : 0); };
+    const int wa = unit_w(pp.ksplit_log2), wb = pp.ksplit2_log2 > pp.ksplit_log2 ? unit_w(pp.ksplit2_log2) : wa;
+    if (pp.seg_w % wa == 0 && pp.seg_w % wb == 0) break;
+    pp.col_step = 1; pp.col_first = 0; pp.seg_w = p->W;
+    pp.tile_step = sink->tile_step; pp.y0 = sink->tile_first * 8;
     }
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
     unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);      // {next unit, warps done, CTAs resolved, -}

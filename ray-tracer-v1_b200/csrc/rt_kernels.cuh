@@ -489,7 +489,10 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     const int by = tile / gx_, bx = tile - by * gx_;
     const int ys = pp.y0 + (((by >> cps_sh) + stripe0) * pp.tile_step << 3) + ((by & ((1 << cps_sh) - 1)) << cth_sh) +
                    ((wt >> 2) << ph_sh);                           // first row of the warp's pixel block
-    const int x = (((bx << 2) + (wt & 3)) << pw_sh) + (pl & ((1 << pw_sh) - 1));
+    // 2-D interleave: in stripe s the launch owns the column segment (col_first + s) mod col_step
+    const int xs = (pp.col_step > 1 ? ((pp.col_first + (by >> cps_sh) + stripe0) % pp.col_step) * pp.seg_w : 0) +
+                   (((bx << 2) + (wt & 3)) << pw_sh);             // first column of the warp's pixel block
+    const int x = xs + (pl & ((1 << pw_sh) - 1));
     const int y = ys + (pl >> pw_sh);
     const bool has_pixel = x < pp.W && y < pp.y1;
     const uint32_t pixel = (uint32_t)(y * pp.W + x);
@@ -500,7 +503,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
     bool first_trip = false;                          // warp-uniform: every live lane is about to trace its camera ray
     if constexpr (kMode == 3 && !kRegen && RT_PRIMARY_CULL) if (pp.primary_cull) {
         const int bw = 1 << pw_sh, bh = 1 << ph_sh;   // the warp's pixel block
-        const int x0 = ((bx << 2) + (wt & 3)) << pw_sh;
+        const int x0 = xs;
         const int y0 = ys;
         const V3<T> d0 = path_camera_ray<T>(pp, x0, y0, T(0.5) * T(bw), T(0.5) * T(bh));
         const float ex = 0.5f * (float)bw * (2.f / (float)pp.W) * (float)pp.aspect * (float)pp.half_w;
@@ -1579,13 +1582,13 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     // stripes of 8 rows (8 / cth CTA rows each); without interleaving the last stripe may be cut short
     const unsigned gy = step > 1 ? (unsigned)((tiles + step - 1) / step) * (8 / cth) : (unsigned)((rows + cth - 1) / cth);
     PathDev<T> ppl = pp;                                          // + the tile grid the persistent CTAs walk
-    ppl.gx = (pp.W + ctw - 1) / ctw; ppl.gy = (int)gy;
+    ppl.gx = (pp.seg_w + ctw - 1) / ctw; ppl.gy = (int)gy;         // seg_w = W unless the launch holds one column segment per stripe
     ppl.gx2 = ppl.gy2 = ppl.stripe2 = 0;
     // fine grid over the last owned stripes (see path_kernel): at most half of them, whole 8-row stripes
     const int lk2 = pp.ksplit2_log2;
     if (lk2 > lk && lk2 <= 5 && pp.fine_pixels > 0) {
         const int owned = (tiles + step - 1) / step;                              // 8-row stripes of this launch
-        int fs = (int)(((long long)pp.fine_pixels + 8LL * pp.W - 1) / (8LL * pp.W));
+        int fs = (int)(((long long)pp.fine_pixels + 8LL * pp.seg_w - 1) / (8LL * pp.seg_w));
         if (fs > owned / 2) fs = owned / 2;
         if (fs >= 1) {
             const int pw2 = lk2 == 0 ? 3 : lk2 == 1 ? 3 : lk2 == 2 ? 2 : lk2 <= 4 ? 1 : 0, ph2 = (5 - lk2) - pw2;
@@ -1593,7 +1596,7 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
             const int sb = owned - fs, rows_a = sb * 8;                            // (tile_step == 1: rows of the coarse part)
             ppl.stripe2 = sb;
             ppl.gy = step > 1 ? sb * (8 / cth) : (rows_a + cth - 1) / cth;
-            ppl.gx2 = (pp.W + ctw2 - 1) / ctw2;
+            ppl.gx2 = (pp.seg_w + ctw2 - 1) / ctw2;
             ppl.gy2 = step > 1 ? fs * (8 / cth2) : (rows - rows_a + cth2 - 1) / cth2;
         }
     }

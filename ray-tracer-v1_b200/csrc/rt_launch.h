@@ -46,6 +46,8 @@ template <typename T> struct PathDev {
     // fused multi-GPU sinks (rt_path_sink, include/rt_b200.h); sink == 0: accum only
     int ksplit_log2;             // 2^ksplit_log2 lanes share a pixel and split its samples (integer fold only)
     int sink, tile_step, world, spp_total;
+    int col_step, col_first, seg_w;      // 2-D interleave (rt_path_sink::col_split): col_step > 1: in stripe s this launch
+                                         // covers columns [seg, seg + seg_w), seg = ((col_first + s) % col_step) * seg_w
     float *image;
     float4 *peer_accum[16];
     int band_y[17];

@@ -618,6 +618,34 @@ def test_sample_split_gives_the_same_frame(nat):
         sink.mode, sink.tile_first, sink.tile_step, sink.image = nat.SINK_IMAGE, r, 3, img.data_ptr()
         sc.render_path_sink(sc.path_params(spec.camera, W, H, spp, 6, 0.0, seed=2), sink)
     assert np.array_equal(img.cpu().numpy(), want)
+    # 2-D interleave (rt_path_sink::col_split): rank r renders column segment (r + s) mod 4 of every stripe s
+    W2, H2 = 256, 45
+    _, ref2, _ = sc.render_path_host(sc.path_params(spec.camera, W2, H2, spp, 6, 0.0, seed=2, ksplit=0), nat.F32)
+    img2 = torch.zeros((H2, W2, 3), dtype=torch.float32, device="cuda")
+    for k in (-1, 8):
+        img2.zero_()
+        for r in range(4):
+            sink = nat.PathSink()
+            sink.mode, sink.tile_first, sink.tile_step, sink.image, sink.col_split = nat.SINK_IMAGE, r, 4, img2.data_ptr(), 1
+            sc.render_path_sink(sc.path_params(spec.camera, W2, H2, spp, 6, 0.0, seed=2, ksplit=k), sink)
+            if r == 0:                    # one rank alone: exactly its diagonal of segments is written
+                got = img2.cpu().numpy().any(axis=2)
+                for srow in range(0, H2, 8):
+                    seg = (srow // 8) % 4
+                    assert got[srow:srow + 8, seg * 64:(seg + 1) * 64].any() and not np.delete(got[srow:srow + 8], np.s_[seg * 64:(seg + 1) * 64], axis=1).any()
+        want2 = np.minimum(1.0, np.floor(ref2[..., :3].astype(np.float64) / spp) / 255.0).astype(np.float32)
+        assert np.array_equal(img2.cpu().numpy(), want2), k
+    sink = nat.PathSink()
+    sink.mode, sink.tile_first, sink.tile_step, sink.image, sink.col_split = nat.SINK_IMAGE, 0, 3, img2.data_ptr(), 1
+    with pytest.raises(Exception):        # 256 is not a multiple of 3
+        sc.render_path_sink(sc.path_params(spec.camera, W2, H2, spp, 6, 0.0, seed=2), sink)
+    # a segment too narrow for the work units of the launch (256 / 16 = 16 pixels, units 32 wide at k = 1): whole stripes
+    img2.zero_()
+    for r in range(16):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step, sink.image, sink.col_split = nat.SINK_IMAGE, r, 16, img2.data_ptr(), 1
+        sc.render_path_sink(sc.path_params(spec.camera, W2, H2, spp, 6, 0.0, seed=2, ksplit=1), sink)
+    assert np.array_equal(img2.cpu().numpy(), want2)
     big = sc.path_params(spec.camera, 640, 360, 16, 6, 0.0, seed=4)               # coarse k = 2, fine k = 8 over the last stripes
     _, auto, st_auto = sc.render_path_host(big, nat.F32)
     _, flat, st_flat = sc.render_path_host(sc.path_params(spec.camera, 640, 360, 16, 6, 0.0, seed=4, ksplit=2), nat.F32)

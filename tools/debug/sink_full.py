@@ -41,3 +41,12 @@ for world in (1, 2, 4, 8):
         t = timed(lambda: sc.render_path_sink(p, sink, stats=stats), 6)
         tot += t; parts.append(t)
     print(f"sink, {world} interleaved share(s): sum {tot:.4f} ms, max {max(parts):.4f}, shares {' '.join(f'{v:.3f}' for v in parts)}", flush=True)
+for world in (2, 4, 8):
+    tot, parts = 0.0, []
+    for r in range(world):
+        sink = nat.PathSink()
+        sink.mode, sink.tile_first, sink.tile_step, sink.world, sink.col_split = nat.SINK_IMAGE, r, world, world, 1
+        sink.image = image.data_ptr()
+        t = timed(lambda: sc.render_path_sink(p, sink, stats=stats), 6)
+        tot += t; parts.append(t)
+    print(f"sink, {world} shares, 2-D interleave (col_split): sum {tot:.4f} ms, max {max(parts):.4f}, shares {' '.join(f'{v:.3f}' for v in parts)}", flush=True)
