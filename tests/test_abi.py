@@ -88,3 +88,29 @@ def test_scene_descriptor_marshalling_is_faithful():
                     got = np.ctypeslib.as_array(C.cast(getattr(d, name), C.POINTER(ct)), shape=(want.size,))
                     assert np.array_equal(got, want), name
         assert [d.bg[0], d.bg[1], d.bg[2]] == [float(v) for v in np.asarray(fs.bg).reshape(3)]
+
+
+def test_host_side_frame_logic():
+    """Host logic that decides what crosses PCIe and in how many launches, no GPU needed: the content key that lets the
+    sub-millisecond frame entries skip the upload of an unchanged scene, and the row bands of the pipelined read-back."""
+    import ray_tracer_v1_b200 as pkg
+    from ray_tracer_v1_b200 import _native as native, scenes
+    from ray_tracer_v1_b200.frames import FrameContext
+    spheres = scenes.build_balls_in_space(as_rendered=False).spheres
+    a, b = pkg.flatten_scene(spheres), pkg.flatten_scene(spheres)
+    assert native.scene_signature(a) == native.scene_signature(b)             # re-flattened, unchanged
+    spheres[1].centre = pkg.Vector(0.4, 0.1, -2.5)
+    assert native.scene_signature(pkg.flatten_scene(spheres)) != native.scene_signature(a)
+    spheres[1].centre = a_centre = pkg.Vector(*a.centre[1])
+    spheres[2].colour = pkg.Colour(1, 2, 3)
+    assert native.scene_signature(pkg.flatten_scene(spheres)) != native.scene_signature(a)
+    assert a_centre.x == a.centre[1][0]
+    # bands: stripe-aligned, contiguous, covering [y0, y1); small or short frames stay one launch
+    ctx = FrameContext.__new__(FrameContext)
+    bands = ctx._bands(1920, 0, 1080, 64)
+    assert len(bands) == FrameContext.BANDS and bands[0][0] == 0 and bands[-1][1] == 1080
+    assert all(b0 % 8 == 0 for b0, _ in bands) and all(x[1] == y[0] for x, y in zip(bands[:-1], bands[1:]))
+    assert max(b1 - b0 for b0, b1 in bands) - min(b1 - b0 for b0, b1 in bands) <= 8
+    assert ctx._bands(1920, 0, 1080, 4) is None and ctx._bands(320, 0, 240, 4096) is None
+    ragged = ctx._bands(1920, 3, 1077, 64)
+    assert ragged[0][0] == 3 and ragged[-1][1] == 1077 and all(x[1] == y[0] for x, y in zip(ragged[:-1], ragged[1:]))
