@@ -1359,12 +1359,16 @@ __global__ void __launch_bounds__(256) env_reshade_kernel(SceneDev<T> sc, EnvDev
 // goes to final_obs (optional), the observation returned is the first one of the new episode, whose start pixel is
 // Philox(env, episode number) under the key (k0, k1) -- no host round trip and no second launch per step, and the
 // lanes of finished episodes go straight back to work.
-template <typename T, int kMode, typename R, bool kAuto>
-__global__ void __maxnreg__(RT_ENV_REGS) env_step_kernel(SceneDev<T> sc, EnvDev<T> e, const float *actions, float *obs,
+// kFlav: the env flavour as a compile-time constant (0 RL) or -1 = read e.flavour: the fused launch of a small RL scene
+// carries one reward model and one set of termination rules (16.2 -> 15.8 us per 65,536-env step).
+template <typename T, int kMode, typename R, bool kAuto, int kFlav = -1>
+__global__ void __maxnreg__(RT_ENV_REGS) env_step_kernel(SceneDev<T> sc, EnvDev<T> e_param, const float *actions, float *obs,
                                                                 R *reward, uint8_t *terminated, uint8_t *truncated,
                                                                 int *reason, R *info, float *final_obs, int *pixels_out,
                                                                 uint32_t k0, uint32_t k1, unsigned long long *stats) {
     RT_MODE_DECL;
+    EnvDev<T> e = e_param;
+    if constexpr (kFlav >= 0) e.flavour = kFlav;
     extern __shared__ __align__(32) unsigned char smem[];
     __shared__ __align__(16) float s_rows[RT_ENV_BLOCK * 18];
     Staged<T> S;
@@ -1735,8 +1739,15 @@ cudaError_t launch_env_step(const SceneDev<T> &sc, const EnvDev<T> &e, const flo
     const size_t sm = mode != 2 ? smem_for(sc) : 0;
     cudaError_t e__ = cudaSuccess;
     switch (mode) {
-        case 0: e__ = allow_smem(env_step_kernel<T, 0, R, kAuto>, sm); if (e__ != cudaSuccess) return e__;
-                env_step_kernel<T, 0, R, kAuto><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
+        case 0:
+            if (kAuto && e.flavour == 0) {
+                e__ = allow_smem(env_step_kernel<T, 0, R, kAuto, 0>, sm); if (e__ != cudaSuccess) return e__;
+                env_step_kernel<T, 0, R, kAuto, 0><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats);
+            } else {        // (the FB flavour specialised the same way measured SLOWER: 16.5 against 14.7 us per step)
+                e__ = allow_smem(env_step_kernel<T, 0, R, kAuto>, sm); if (e__ != cudaSuccess) return e__;
+                env_step_kernel<T, 0, R, kAuto><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats);
+            }
+            break;
         case 1: e__ = allow_smem(env_step_kernel<T, 1, R, kAuto>, sm); if (e__ != cudaSuccess) return e__;
                 env_step_kernel<T, 1, R, kAuto><<<grid, block, sm, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
         default: env_step_kernel<T, 2, R, kAuto><<<grid, block, 0, st>>>(sc, e, actions, obs, reward, terminated, truncated, reason, info, final_obs, pixels_out, k0, k1, stats); break;
