@@ -90,7 +90,7 @@ struct rt_env {
 template <typename T> static size_t scene_blob_bytes(int n, int nG, int nP, int nL) {
     const size_t v = sizeof(typename M<T>::v4);
     size_t b = v * (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n + 2 * (size_t)nG + 2 * (size_t)nP + 2 * (size_t)nL +
-                    3 * (size_t)((nL + 1) / 2));
+                    RT_LPK_STRIDE * (size_t)((nL + 1) / 2));
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
     return (b + 255) & ~size_t(255);
 }
@@ -113,7 +113,7 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, unsigned ch
     v4 *p_col = p; p += nP;
     v4 *l_pos = p; p += nL;
     v4 *l_col = p; p += nL;
-    v4 *lpk = p; p += 3 * ((nL + 1) / 2);    // light pairs for the packed direct-light loop, rt_trace.cuh
+    v4 *lpk = p; p += RT_LPK_STRIDE * ((nL + 1) / 2);    // light pairs for the packed direct-light loop, rt_trace.cuh
     int *q = reinterpret_cast<int *>(p);
     int *ids = q; q += n;
     int *g_func = q; q += nG;
@@ -161,17 +161,25 @@ template <typename T> static void pack_scene(const rt_scene_desc *s, unsigned ch
         l_col[i].w = (T)0;
         l_index[i] = s->l_index[i];
     }
-    // pair j = lights (2j, 2j+1): lpk[3j] = 128*(x0 x1 y0 y1), lpk[3j+1] = (128*z0 128*z1 R0 R1), lpk[3j+2] = (G0 G1 B0 B1)
-    // with (R,G,B) = colour * 0.3 * 16384 (direct_light_pk saturates dn/d^3 / 16384 to [0,1]); the odd slot of the
-    // last pair is a black light at the origin
-    for (int i = 0; i < 2 * ((nL + 1) / 2); ++i) {
-        const bool real = i < nL;
-        const double x = real ? s->l_centre[3 * i] : 0.0, y = real ? s->l_centre[3 * i + 1] : 0.0, z = real ? s->l_centre[3 * i + 2] : 0.0;
+    // pair j = lights (2j, 2j+1): lpk[4j] = 128*(x0 x1 y0 y1), lpk[4j+1] = (128*z0 128*z1 R0 R1), lpk[4j+2] = (G0 G1 B0 B1),
+    // lpk[4j+3] = (|A0|^2 |A1|^2 0 0), A = the rounded 128 * centre as stored, with (R,G,B) = colour * 0.3 * 16384
+    // (direct_light_pk saturates dn/d^3 / 16384 to [0,1]); the odd slot of the last pair is a black light at (128,0,0)/128
+    // -- not at the origin, so that |A - 128 p|^2 cannot vanish for a hit point at the origin
+    // An odd light count: light 0 sits ALONE in pair 0 (slot 1 = the filler) and lights 1.. fill the pairs behind it, so
+    // that direct_light_pkc can shade the single light with scalar instructions at a compile-time address.
+    const bool odd = (nL & 1) != 0;
+    for (int slot = 0; slot < 2 * ((nL + 1) / 2); ++slot) {
+        const int li = !odd ? slot : slot == 0 ? 0 : slot == 1 ? -1 : slot - 1;      // light held by this slot (-1: filler)
+        const bool real = li >= 0 && li < nL;
+        const int i = slot;
+        const double x = real ? s->l_centre[3 * li] : 1.0, y = real ? s->l_centre[3 * li + 1] : 0.0, z = real ? s->l_centre[3 * li + 2] : 0.0;
         const double k = 0.3 * 16384.0;
-        const double r = real ? s->l_colour[3 * i] * k : 0.0, g = real ? s->l_colour[3 * i + 1] * k : 0.0, b = real ? s->l_colour[3 * i + 2] * k : 0.0;
-        v4 *t = lpk + 3 * (i / 2);
-        if (i & 1) { t[0].y = (T)(128.0 * x); t[0].w = (T)(128.0 * y); t[1].y = (T)(128.0 * z); t[1].w = (T)r; t[2].y = (T)g; t[2].w = (T)b; }
-        else { t[0].x = (T)(128.0 * x); t[0].z = (T)(128.0 * y); t[1].x = (T)(128.0 * z); t[1].z = (T)r; t[2].x = (T)g; t[2].z = (T)b; }
+        const double r = real ? s->l_colour[3 * li] * k : 0.0, g = real ? s->l_colour[3 * li + 1] * k : 0.0, b = real ? s->l_colour[3 * li + 2] * k : 0.0;
+        v4 *t = lpk + RT_LPK_STRIDE * (i / 2);
+        const T ax = (T)(128.0 * x), ay = (T)(128.0 * y), az = (T)(128.0 * z);
+        const T aa = (T)((double)ax * (double)ax + (double)ay * (double)ay + (double)az * (double)az);
+        if (i & 1) { t[0].y = ax; t[0].w = ay; t[1].y = az; t[1].w = (T)r; t[2].y = (T)g; t[2].w = (T)b; t[3].y = aa; t[3].w = (T)0; }
+        else { t[0].x = ax; t[0].z = ay; t[1].x = az; t[1].z = (T)r; t[2].x = (T)g; t[2].z = (T)b; t[3].x = aa; t[3].z = (T)0; }
     }
 }
 
@@ -191,7 +199,7 @@ template <typename T> static void bind_view(SceneBufs<T> &b, const rt_scene_desc
     v.p_col = p; p += nP;
     v.l_pos = p; p += nL;
     v.l_col = p; p += nL;
-    v.lpk = p; p += 3 * ((nL + 1) / 2);
+    v.lpk = p; p += RT_LPK_STRIDE * ((nL + 1) / 2);
     int *q = reinterpret_cast<int *>(p);
     v.ids = q; q += n;
     v.g_func = q; q += nG;
@@ -274,7 +282,7 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
             const float4 *v = reinterpret_cast<const float4 *>(hf);
             std::memcpy(sc->pkc.q, v + n_pad, (size_t)n_pad * sizeof(float4));
             const size_t lpk_at = 2 * (size_t)n_pad + 2 * (size_t)s->n + 2 * (size_t)s->nG + 2 * (size_t)s->nP + 2 * (size_t)s->nL;
-            std::memcpy(sc->pkc.l, v + lpk_at, 3 * (size_t)((s->nL + 1) / 2) * sizeof(float4));
+            std::memcpy(sc->pkc.l, v + lpk_at, RT_LPK_STRIDE * (size_t)((s->nL + 1) / 2) * sizeof(float4));
         }
     }
     bind_view<float>(sc->f, s, sc->small_dev);

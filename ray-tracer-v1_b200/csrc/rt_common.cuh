@@ -176,7 +176,8 @@ struct PathRng {
 //   pk    sphere pairs (2j, 2j+1): (cx0 cx1 cy0 cy1), (cz0 cz1 w0 w1) with w = r^2 - |c|^2 (packed selection loop)
 //   col   r g b 1/r             g_vec x y z max_angle     g_col r g b strength
 //   p_pos x y z max_angle       p_col r g b strength      l_pos x y z -      l_col r g b -
-//   lpk   light pairs (2j, 2j+1): 128*(x0 x1 y0 y1), (128*z0 128*z1 R0 R1), (G0 G1 B0 B1), RGB = colour*0.3*16384
+//   lpk   light pairs (2j, 2j+1), RT_LPK_STRIDE = 4 vectors each: 128*(x0 x1 y0 y1), (128*z0 128*z1 R0 R1), (G0 G1 B0 B1),
+//         (|A0|^2 |A1|^2 - -) with A = 128 * centre; RGB = colour*0.3*16384
 template <typename T> struct SceneDev {
     using v4 = typename M<T>::v4;
     int n, nG, nP, nL;
@@ -197,8 +198,9 @@ template <typename T> struct SceneDev {
 // (LDCU.128) and FFMA2 takes them as uniform operands, so no vector register, no register-file read port and no
 // shared-memory load is spent on warp-uniform scene data.
 #define RT_PKC_MAX 64                    /* spheres */
-#define RT_LPKC_MAX 32                   /* Algorithm-B light spheres (the `lpk` light-pair array, 3 vectors per pair) */
-struct PkConst { ulonglong2 q[RT_PKC_MAX]; ulonglong2 l[3 * RT_LPKC_MAX / 2]; };
+#define RT_LPKC_MAX 32                   /* Algorithm-B light spheres (the `lpk` light-pair array, 4 vectors per pair) */
+#define RT_LPK_STRIDE 4                  /* float4 vectors per light pair */
+struct PkConst { ulonglong2 q[RT_PKC_MAX]; ulonglong2 l[RT_LPK_STRIDE * RT_LPKC_MAX / 2]; };
 struct PkNone {};
 
 // sphere arrays as the tracing functions see them (shared-memory staged or global)

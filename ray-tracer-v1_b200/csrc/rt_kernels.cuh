@@ -33,7 +33,7 @@ template <typename T> __host__ __device__ inline size_t scene_smem_bytes(int n, 
     const size_t v = sizeof(typename M<T>::v4);
     size_t b = 0;
     b += (2 * (size_t)((n + 7) & ~7) + 2 * (size_t)n) * v;  // sph (padded to 8), pk (sphere pairs), mat, col
-    b += 2 * (size_t)nG * v + 2 * (size_t)nP * v + 2 * (size_t)nL * v + 3 * (size_t)((nL + 1) / 2) * v;
+    b += 2 * (size_t)nG * v + 2 * (size_t)nP * v + 2 * (size_t)nL * v + RT_LPK_STRIDE * (size_t)((nL + 1) / 2) * v;
     b = align32<T>(b);
     b += sizeof(int) * ((size_t)n + nG + 2 * (size_t)nP + nL);
     return align32<T>(b);
@@ -63,7 +63,7 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
         v4 *p_col = p; p += sc.nP;
         v4 *l_pos = p; p += sc.nL;
         v4 *l_col = p; p += sc.nL;
-        v4 *lpk = p; p += 3 * ((sc.nL + 1) / 2);
+        v4 *lpk = p; p += RT_LPK_STRIDE * ((sc.nL + 1) / 2);
         size_t off = align32<T>((size_t)(reinterpret_cast<unsigned char *>(p) - smem));
         int *q = reinterpret_cast<int *>(smem + off);
         int *ids = q; q += sc.n;
@@ -78,7 +78,7 @@ template <typename T, bool kShared> RT_DEV void stage_scene(const SceneDev<T> &s
         coop_copy(p_pos, sc.p_pos, sc.nP); coop_copy(p_col, sc.p_col, sc.nP);
         coop_copy(p_id, sc.p_id, sc.nP); coop_copy(p_func, sc.p_func, sc.nP);
         coop_copy(l_pos, sc.l_pos, sc.nL); coop_copy(l_col, sc.l_col, sc.nL); coop_copy(l_index, sc.l_index, sc.nL);
-        coop_copy(lpk, sc.lpk, 3 * ((sc.nL + 1) / 2));
+        coop_copy(lpk, sc.lpk, RT_LPK_STRIDE * ((sc.nL + 1) / 2));
         __syncthreads();
         S.g.sv.sph = sph; S.g.sv.pk = pk; S.g.sv.mat = mat; S.g.sv.col = col; S.g.sv.ids = ids;
         S.la.g_vec = g_vec; S.la.g_col = g_col; S.la.g_func = g_func;
@@ -605,7 +605,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                         if constexpr (kMode != 3) st.idx[depth] = (uint32_t)i;
                         if constexpr (M<T>::exact) st.direct[depth] = direct_light<T>(S.lb, i, h.p, h.n);
                         else if constexpr (kMode == 3)       // one stack word per level: sphere index above the 24 colour bits
-                            st.direct[depth] = direct_light_pkc(pkc, (S.lb.nL + 1) >> 1, h.p, h.n) | ((uint32_t)i << 24);
+                            st.direct[depth] = direct_light_pkc(pkc, S.lb.nL, h.p, h.n) | ((uint32_t)i << 24);
                         else st.direct[depth] = direct_light_pk(S.lb.lpk, (S.lb.nL + 1) >> 1, h.p, h.n);
                         depth++;
                         n_rays++;                                                    // the recursive call ...

@@ -642,7 +642,12 @@ RT_DEV uint32_t direct_light(const LightsB<T> &lb, int hit_idx, V3<T> p, V3<T> n
 }
 
 // FP32 product form of direct_light over the light-pair array (SceneDev::lpk), branch-free, two lights per FP32
-// instruction.  Positions are stored times 128 and colours times 0.3 * 16384, so with tl' = 128 (l - p):
+// instruction.  Positions are stored times 128 (A = 128 l, with |A|^2 beside them) and colours times 0.3 * 16384, so
+// with tl' = A - p', p' = 128 p:
+//     tl'.tl' = |A|^2 + |p'|^2 - 2 A.p'      (1 FADD2 + 3 FFMA2 per pair: the per-hit terms are packed once)
+//     n.tl'   = n.A - n.p'                    (3 FFMA2)
+// -- 7 packed operations per pair instead of the 9 of (A - p') first; the cancellation costs < 1e-6 of the squared
+// distance for a light a few units away (|A|^2 ~ 1e6, FP32) and 3e-4 for one 0.3 away, where the contribution saturates --
 //     s' = sat(n.tl' * rsqrt(tl'.tl')^3) = sat(cos / d^2 / 16384),     x = colour' * s' = colour * cos * 0.3 / d^2
 // and a contribution that saturates is >= 255 on every channel with colour >= 0.052, i.e. the final min(255, .)
 // hides the clamp.  cos <= 0 saturates to 0 (chandelier.py:470: `if cos_angle > 0`); the self test of
@@ -652,6 +657,9 @@ RT_DEV f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : 
 RT_DEV f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 RT_DEV float mul_sat(float a, float b) { float d; asm("mul.rn.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b)); return d; }
 RT_DEV uint32_t direct_light_pk(const float4 *lpk, int n_pairs, V3<float> p, V3<float> n) {
+    // array form (large scenes: hundreds of lights read through L1): tl' = A - p' first, 9 packed operations and THREE
+    // vector loads per pair -- the expanded form of direct_light_pkc needs the fourth vector (|A|^2), and here the loads,
+    // not the arithmetic, are what a pair costs (measured: 222 -> 242 ms per frame of the 1e5-sphere scene with it)
     const float qx = -128.f * p.x, qy = -128.f * p.y, qz = -128.f * p.z;
     const f32x2 px = pack2(qx, qx), py = pack2(qy, qy), pz = pack2(qz, qz);
     const f32x2 nx = pack2(n.x, n.x), ny = pack2(n.y, n.y), nz = pack2(n.z, n.z);
@@ -660,7 +668,7 @@ RT_DEV uint32_t direct_light_pk(const float4 *lpk, int n_pairs, V3<float> p, V3<
     const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(lpk);
 #pragma unroll 2
     for (int j = 0; j < n_pairs; ++j) {
-        const ulonglong2 A = q[3 * j], B = q[3 * j + 1], C = q[3 * j + 2];
+        const ulonglong2 A = q[RT_LPK_STRIDE * j], B = q[RT_LPK_STRIDE * j + 1], C = q[RT_LPK_STRIDE * j + 2];
         const f32x2 tx = add2(A.x, px), ty = add2(A.y, py), tz = add2(B.x, pz);
         const f32x2 qq = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
         const f32x2 dn = fma2(tz, nz, fma2(ty, ny, mul2(tx, nx)));
@@ -683,20 +691,38 @@ RT_DEV uint32_t direct_light_pk(const float4 *lpk, int n_pairs, V3<float> p, V3<
 }
 
 // direct_light_pk over the light pairs in the kernel parameter block (PkConst::l): fully unrolled, uniform operands.
-RT_DEV uint32_t direct_light_pkc(const PkConst &pkc, int n_pairs, V3<float> p, V3<float> n) {
-    const float qx = -128.f * p.x, qy = -128.f * p.y, qz = -128.f * p.z;
-    const f32x2 px = pack2(qx, qx), py = pack2(qy, qy), pz = pack2(qz, qz);
+// An ODD number of lights (3 in the complex scene, 21 in the chandelier) leaves one light without a partner: the host
+// packs it FIRST (pair 0 = light 0 + a black filler, rt_api.cu pack_scene) and it is evaluated here with scalar
+// instructions -- half the issue cycles of a packed pair whose second lane would shade the filler.
+RT_DEV float fma_rz(float a, float b, float c) { float d; asm("fma.rz.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c)); return d; }
+RT_DEV uint32_t direct_light_pkc(const PkConst &pkc, int n_lights, V3<float> p, V3<float> n) {
+    const int n_pairs = (n_lights + 1) >> 1;
+    const bool odd = (n_lights & 1) != 0;
+    const float qx = 128.f * p.x, qy = 128.f * p.y, qz = 128.f * p.z;                      // p' = 128 p
+    const float pp_ = fmaf(qz, qz, fmaf(qy, qy, qx * qx)), np_ = fmaf(n.z, qz, fmaf(n.y, qy, n.x * qx));
+    const f32x2 px = pack2(-2.f * qx, -2.f * qx), py = pack2(-2.f * qy, -2.f * qy), pz = pack2(-2.f * qz, -2.f * qz);
     const f32x2 nx = pack2(n.x, n.x), ny = pack2(n.y, n.y), nz = pack2(n.z, n.z);
+    const f32x2 pp2 = pack2(pp_, pp_), nnp = pack2(-np_, -np_);
     const f32x2 magic = pack2(8388608.f, 8388608.f);
     unsigned a0 = 0u, a1 = 0u, a2 = 0u;
 #pragma unroll
     for (int j = 0; j < RT_LPKC_MAX / 2; ++j) {
         if (j >= n_pairs) break;                      // ONE exit (a guard per pair costs a taken branch per skipped pair)
-        {
-            const ulonglong2 A = pkc.l[3 * j], B = pkc.l[3 * j + 1], C = pkc.l[3 * j + 2];
-            const f32x2 tx = add2(A.x, px), ty = add2(A.y, py), tz = add2(B.x, pz);
-            const f32x2 qq = fma2(tz, tz, fma2(ty, ty, mul2(tx, tx)));
-            const f32x2 dn = fma2(tz, nz, fma2(ty, ny, mul2(tx, nx)));
+        if (j == 0 && odd) {                          // (j is a compile-time constant in every unrolled copy)
+            const ulonglong2 A = pkc.l[0], B = pkc.l[1], C = pkc.l[2];
+            float x, y, z, R, G, Bl, AA, u_;
+            unpack2(A.x, x, u_); unpack2(A.y, y, u_); unpack2(B.x, z, u_); unpack2(B.y, R, u_);
+            unpack2(C.x, G, u_); unpack2(C.y, Bl, u_); unpack2(pkc.l[3].x, AA, u_);
+            const float qq = fmaf(z, -2.f * qz, fmaf(y, -2.f * qy, fmaf(x, -2.f * qx, AA + pp_)));
+            const float dn = fmaf(z, n.z, fmaf(y, n.y, fmaf(x, n.x, -np_)));
+            const float inv = M<float>::rsqrt(qq);
+            const float s = mul_sat(dn * inv, inv * inv);
+            a0 += __float_as_uint(fma_rz(R, s, 8388608.f)); a1 += __float_as_uint(fma_rz(G, s, 8388608.f));
+            a2 += __float_as_uint(fma_rz(Bl, s, 8388608.f));
+        } else {
+            const ulonglong2 A = pkc.l[RT_LPK_STRIDE * j], B = pkc.l[RT_LPK_STRIDE * j + 1], C = pkc.l[RT_LPK_STRIDE * j + 2];
+            const f32x2 qq = fma2(B.x, pz, fma2(A.y, py, fma2(A.x, px, add2(pkc.l[RT_LPK_STRIDE * j + 3].x, pp2))));
+            const f32x2 dn = fma2(B.x, nz, fma2(A.y, ny, fma2(A.x, nx, nnp)));
             float q0, q1;
             unpack2(qq, q0, q1);
             const f32x2 inv = pack2(M<float>::rsqrt(q0), M<float>::rsqrt(q1));
@@ -711,7 +737,7 @@ RT_DEV uint32_t direct_light_pkc(const PkConst &pkc, int n_pairs, V3<float> p, V
             a0 += r_lo + r_hi; a1 += g_lo + g_hi; a2 += b0 + b1;
         }
     }
-    const unsigned bias = 2u * (unsigned)n_pairs * 0x4B000000u;          // bits of 2^23, once per light
+    const unsigned bias = (unsigned)n_lights * 0x4B000000u;              // bits of 2^23, once per light evaluated
     a0 = min(a0 - bias, 255u); a1 = min(a1 - bias, 255u); a2 = min(a2 - bias, 255u);
     return a0 | (a1 << 8) | (a2 << 16);
 }
