@@ -521,7 +521,9 @@ def main():
         barrier()
         t0 = time.perf_counter()
         pending, checksum = None, 0.0
+        marks = []
         for i in range(args.steps):
+            marks.append(time.perf_counter() - t0)
             # the reference-facing objects (54 Sphere / Material / Colour instances) are re-flattened EVERY frame, as the
             # drop-in classes do (scenes are mutable lists: SURVEY 8b) -- host work that overlaps the previous frame's render
             fs_i = rtb.flatten_scene(spec.spheres, background_colour=spec.background)
@@ -533,8 +535,12 @@ def main():
             pending = img
         if pending is not None:
             checksum += float(pending.result()[0, 0, 0])
+        marks.append(time.perf_counter() - t0)
         barrier()
         e2e_s = time.perf_counter() - t0
+        if args.debug_ranks:
+            print(f"[rank {rank}] e2e host marks (ms since start, one per step issue, then after the last read): "
+                  f"{' '.join(f'{1e3 * v:.2f}' for v in marks)} | total {1e3 * e2e_s:.2f}", file=sys.stderr, flush=True)
         te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.all_reduce(e2e_q, op=dist.ReduceOp.SUM)

@@ -266,9 +266,12 @@ class ShardedPathRenderer:
         cs.wait_event(ready)
         with torch.cuda.stream(cs):
             self.host_images[slot].copy_(src, non_blocking=True)
+            # the frame is on the host once the COPY is done: the event must not sit behind the release launch, which
+            # (a kernel) cannot start while the next frame's persistent kernel holds every SM -- it would report the
+            # frame a whole frame late and stall a caller that reads frame f before it issues frame f + 2
+            self._copied[slot].record(cs)
             if release is not None:
                 release(cs.cuda_stream)
-            self._copied[slot].record(cs)
         self.d2h_bytes = self.host_images[slot].numel() * 4
         return PendingFrame(self.host_images[slot], self._copied[slot])
 
