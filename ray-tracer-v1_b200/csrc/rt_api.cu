@@ -865,9 +865,42 @@ RT_EXPORT int rt_peer_free(int device, void *ptr_dev) {
     CU(cudaFree(ptr_dev));
     return RT_OK;
 }
+// A flag write that needs no SM: the driver's stream memory operation (cuStreamWriteValue32, default flags = a system
+// fence before the write), fetched through the runtime so that libcuda is not linked.  A release LAUNCH queued behind a
+// copy cannot start while another stream's persistent kernel holds every SM; the memory operation can.
+typedef int (*rt_write_value32_fn)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+static rt_write_value32_fn stream_write_value32() {
+    static rt_write_value32_fn fn = []() -> rt_write_value32_fn {
+        // opt-in (RT_B200_MEMOPS=1): bit-identical frames in every protocol variant at 2 GPUs, but no measurable gain
+        // there (the release is off the critical path once the frame-on-host event no longer waits for it) and not
+        // exercised at 8 GPUs, so the release stays a one-warp kernel by default
+        if (!std::getenv("RT_B200_MEMOPS")) return nullptr;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return reinterpret_cast<rt_write_value32_fn>(p);
+    }();
+    return fn;
+}
+
 RT_EXPORT int rt_peer_signal(int device, uint32_t *const *flag_ptrs, int32_t n, uint32_t epoch, void *stream) {
     if (!flag_ptrs || n < 1 || n > 32) return fail(RT_ERR_INVALID, "bad arguments");
     CU(cudaSetDevice(device));
+    for (int i = 0; i < n; ++i) if (!flag_ptrs[i]) return fail(RT_ERR_INVALID, "NULL flag pointer");
+    if (rt_write_value32_fn wr = stream_write_value32()) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(S(stream), &cap) == cudaSuccess && cap == cudaStreamCaptureStatusNone) {
+            int done = 0;
+            for (; done < n; ++done)
+                if (wr(S(stream), (unsigned long long)(uintptr_t)flag_ptrs[done], epoch, 0u) != 0) break;
+            if (done == n) return RT_OK;
+            if (done > 0) return fail(RT_ERR_CUDA, "cuStreamWriteValue32 failed part-way through a signal");
+            // first write refused (address kind not supported by this driver): the kernel below does the job
+        }
+    }
     PeerFlagTable tab;
     std::memset(&tab, 0, sizeof tab);
     for (int i = 0; i < n; ++i) {
