@@ -496,6 +496,7 @@ class WorkingFBRenderer:
                       'fb_success': 0, 'render_time': 0, 'rays_per_second': 0}
         self.device, self.precision, self.seed = device, precision, seed
         self._renders = 0
+        self._ctx = None            # persistent FrameContext of the agent-less frames
 
     def set_render_settings(self, width=200, height=150, max_bounces=3, samples_per_pixel=4):
         self.image_width, self.image_height = width, height
@@ -511,7 +512,23 @@ class WorkingFBRenderer:
         self._renders += 1
         fs = flatten_scene(self.scene, background_colour=Colour(2, 2, 5), light_sources=self.light_sources,
                            small_lights=self.small_lights)
-        use = self.fb_loaded and self.fb_agent is not None
+        use = self.fb_loaded and self.fb_agent is not None and self.fb_usage_prob > 0
+        if not use:
+            # no agent (the state the reference is in without a checkpoint, :436-437) or fb_usage_prob = 0: every bounce is
+            # the traditional one and the wavefront's frame equals the fused path kernel's bit for bit
+            # (tests/test_gpu_parity.py::test_wavefront_fb_renderer), so the frame goes through that single launch
+            if self._ctx is None:
+                self._ctx = FrameContext(self.device)
+            self._ctx.set_scene(fs)
+            view, st = self._ctx.render_path(_xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
+                                             self.mirror_threshold, seed=seed, fov=self.fov,
+                                             precision=_precision(self.precision))
+            for i, k in enumerate(('total_rays', 'total_intersections', 'light_hits', 'small_light_hits')):
+                self.stats[k] = int(st[i])
+            self.stats['render_time'] = time.time() - start
+            if self.stats['render_time'] > 0:
+                self.stats['rays_per_second'] = self.stats['total_rays'] / self.stats['render_time']
+            return view.copy()
         image, _, st = render_path_wavefront(fs, _xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
                                              self.mirror_threshold, policy=_batched_policy(self.fb_agent) if use else None,
                                              fb_usage_prob=self.fb_usage_prob if use else 0.0, seed=seed, fov=self.fov,

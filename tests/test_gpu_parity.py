@@ -834,6 +834,21 @@ def test_wavefront_fb_renderer(rt, nat, orc):
     r.fb_loaded, r.fb_usage_prob = True, prob
     img = r.render(W, H, spp, depth)
     assert np.array_equal(img, z["image"]) and r.stats["fb_used"] == int(z["stats"][4]) and r.stats["fb_success"] == r.stats["fb_used"]
+    # without an agent (the reference without a checkpoint) the class renders the traditional frame through the fused
+    # path kernel: same image and counters as ComplexTraditionalRenderer with the same seed, in both precisions
+    for name in ("f64", "f32"):
+        plain = rt.WorkingFBRenderer(camera_position=rt.Vector(*spec.camera), precision=name, seed=seed)
+        trad = rt.ComplexTraditionalRenderer(precision=name, seed=seed)
+        for q in (plain, trad):
+            q.scene, q.light_sources, q.small_lights = spec.spheres, r.light_sources, r.small_lights
+        trad.camera_position = plain.camera_position
+        a, b = plain.render(W, H, spp, depth), trad.render(W, H, spp, depth)
+        assert np.array_equal(a, b), name
+        assert all(plain.stats[k] == trad.stats[k] for k in ("total_rays", "total_intersections", "light_hits", "small_light_hits"))
+        assert plain.stats["fb_used"] == 0 and plain.stats["total_rays"] > 0
+        # an agent with fb_usage_prob = 0 asks nothing of it either
+        plain.fb_agent, plain.fb_loaded, plain.fb_usage_prob = r.fb_agent, True, 0.0
+        assert np.array_equal(plain.render(W, H, spp, depth), b), name
 
 
 # ------------------------------------------------------------------ full-size properties of C2 and C4
