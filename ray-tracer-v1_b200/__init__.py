@@ -19,10 +19,12 @@ __version__ = "0.1.0"
 
 _LAZY = {
     "Ray": "ray", "Intersection": "ray",
-    "TraditionalRenderer": "renderers", "CustomSceneExperiment": "renderers", "SimplifiedFBRenderer": "renderers",
+    "TraditionalRenderer": "renderers", "ComplexTraditionalRenderer": "renderers", "CustomSceneExperiment": "renderers",
+    "SimplifiedFBRenderer": "renderers", "save_png": "renderers",
     "WorkingFBRenderer": "renderers", "render_path_wavefront": "renderers",
     "render_whitted": "renderers", "render_path": "renderers",
-    "RayTracerEnv": "ray_tracer_env", "BatchedRayTracerEnv": "ray_tracer_env",
+    "RayTracerEnv": "ray_tracer_env", "BatchedRayTracerEnv": "ray_tracer_env", "FBRayTracerEnv": "ray_tracer_env",
+    "AdaptiveRewardRayTracerEnv": "ray_tracer_env", "RayTracerVecEnv": "ray_tracer_env",
     "generate_trajectories": "fb_trajectories", "generate_trajectory": "fb_trajectories", "TrajectoryBatch": "fb_trajectories",
     "NativeLibraryError": "_native", "DeviceScene": "_native",
 }

@@ -190,6 +190,9 @@ class BatchedRayTracerEnv:
             self.seed = int(seed)
         if mask is None or self.handle is None:
             self._ensure()            # full reset: the scene list may have been mutated since (re-flatten + upload)
+            # a captured step_auto launch has the scene's device pointers, its census and the seed baked into its
+            # parameter block: re-captured at the next step_auto(graph=True)
+            self._graph = None
         torch = self.torch
         pix = None
         if options is not None and "pixels" in options:

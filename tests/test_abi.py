@@ -114,3 +114,17 @@ def test_host_side_frame_logic():
     assert ctx._bands(1920, 0, 1080, 4) is None and ctx._bands(320, 0, 240, 4096) is None
     ragged = ctx._bands(1920, 3, 1077, 64)
     assert ragged[0][0] == 3 and ragged[-1][1] == 1077 and all(x[1] == y[0] for x, y in zip(ragged[:-1], ragged[1:]))
+
+
+def test_package_exports_resolve():
+    """Every name the package advertises lazily imports without a GPU (the classes only touch the library when they trace),
+    and the reference's entry-point names are among them."""
+    import ray_tracer_v1_b200 as pkg
+    for name in pkg._LAZY:
+        assert getattr(pkg, name) is not None, name
+    for name in ("Ray", "Intersection", "TraditionalRenderer", "ComplexTraditionalRenderer", "WorkingFBRenderer",
+                 "CustomSceneExperiment", "SimplifiedFBRenderer", "RayTracerEnv", "FBRayTracerEnv",
+                 "AdaptiveRewardRayTracerEnv", "RayTracerVecEnv", "BatchedRayTracerEnv"):
+        assert name in pkg._LAZY, name
+    with pytest.raises(AttributeError):
+        pkg.no_such_name
