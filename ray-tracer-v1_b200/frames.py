@@ -87,8 +87,14 @@ class FrameContext:
 
     # a frame whose image takes longer to copy out than a launch costs is rendered in row bands: band b is copied to the
     # pinned host image (copy stream) while band b + 1 renders.  Pixels are keyed by (pixel, sample), so the frame is the
-    # same bit for bit (tested); every extra launch costs ~30 us of drain, every band hides its share of the copy.
-    BANDS = 4
+    # same bit for bit (tested); every extra launch costs ~30 us of drain, every band hides its share of the copy.  The
+    # bands taper (BAND_WEIGHTS): a band's copy hides behind the NEXT band's render, so only the last band's copy is paid.
+    # Only the LAST band's copy is exposed and every extra launch costs its drain, so: two bands, the last one 1/16 of the
+    # rows.  Measured through ComplexTraditionalRenderer.render(1920, 1080, 64, 5) (tools/debug/bands_ab.py,
+    # profiles/bands_ab_r2.txt): one launch 17.53 ms, four equal bands 17.33, (11,10,8,3) 17.25, (6,5,2) 17.23, (7,1) 17.20,
+    # (15,1) 17.17, (23,1) 17.16 (kept at 15:1 -- the first band's 23 MB copy still hides at the smallest banded frames).
+    BANDS = 2
+    BAND_WEIGHTS = (15, 1)
     BAND_MIN_IMAGE_BYTES = 8 << 20
     BAND_MIN_SAMPLES = 24 << 20          # pixel-samples: below ~10 ms of kernel the split is not worth its launches
 
@@ -97,7 +103,8 @@ class FrameContext:
         if self.BANDS < 2 or rows * W * 12 < self.BAND_MIN_IMAGE_BYTES or rows * W * ns < self.BAND_MIN_SAMPLES:
             return None
         stripes = (rows + 7) // 8
-        cuts = [y0 + 8 * ((stripes * k) // self.BANDS) for k in range(self.BANDS)] + [y1]
+        w = self.BAND_WEIGHTS if len(self.BAND_WEIGHTS) == self.BANDS else (1,) * self.BANDS
+        cuts = [y0 + 8 * ((stripes * sum(w[:k])) // sum(w)) for k in range(self.BANDS)] + [y1]
         return [(a, b) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
 
     def _render_path_banded(self, p, bands, W, H, precision, stream):
