@@ -482,6 +482,7 @@ class WorkingFBRenderer:
     ``TraditionalRenderer`` (``fb_usage_prob = 0``, as the reference does when no model is given)."""
 
     mirror_threshold = 0.9
+    reuse_output = True         # agent-less frames: see TraditionalRenderer.render
 
     def __init__(self, model_path=None, scene_small_lights=None, camera_position=None, device=0, precision="f32", seed=None):
         if model_path is not None:
@@ -528,7 +529,7 @@ class WorkingFBRenderer:
             self.stats['render_time'] = time.time() - start
             if self.stats['render_time'] > 0:
                 self.stats['rays_per_second'] = self.stats['total_rays'] / self.stats['render_time']
-            return view.copy()
+            return view if self.reuse_output else view.copy()      # as TraditionalRenderer.render: a view of the pinned ring
         image, _, st = render_path_wavefront(fs, _xyz(self.camera_position), width, height, samples_per_pixel, max_bounces,
                                              self.mirror_threshold, policy=_batched_policy(self.fb_agent) if use else None,
                                              fb_usage_prob=self.fb_usage_prob if use else 0.0, seed=seed, fov=self.fov,
