@@ -71,6 +71,7 @@ struct rt_scene {
     cudaEvent_t staged = nullptr;
     LbvhStorage bvh;              // rt_lbvh_build.h
     bool int_colours = false;     // every colour is an integer in [0, 65535]: the path kernel may fold in integers
+    bool byte_colours = false;    // ... and <= 255: the fold may come from a byte table (PathDev::fold_tab)
     mutable unsigned *sched_dev = nullptr; // RT_SCHED_SLOTS x 4 work counters of the persistent path kernel (zero at rest)
     mutable std::atomic<unsigned> sched_next{0}; // launches rotate through the slots, so launches in flight never share a pair
     PkConst pkc;                  // host copy of the FP32 sphere pairs of a small scene (path kernel parameter block)
@@ -248,6 +249,9 @@ static int upload_scene(rt_scene *sc, const rt_scene_desc *s, cudaStream_t st) {
         const double c = s->colour[i];
         if (!(c >= 0.0 && c <= 65535.0 && c == std::floor(c))) sc->int_colours = false;
     }
+    sc->byte_colours = sc->int_colours;
+    for (int i = 0; i < 3 * s->n && sc->byte_colours; ++i)
+        if (s->colour[i] > 255.0) sc->byte_colours = false;
     // pack into the pinned staging area and copy from there: nothing below waits for the stream
     const size_t n_small = (size_t)(s->n > 0 ? s->n : 1);
     const size_t need = sc->f.bytes + sc->d.bytes + ((n_small + 255) & ~size_t(255));
@@ -771,6 +775,12 @@ static int render_path_t(const rt_scene *sc, const SceneDev<T> &view, const rt_p
     if (pp.seg_w % wa == 0 && pp.seg_w % wb == 0) break;
     pp.col_step = 1; pp.col_first = 0; pp.seg_w = p->W;
     pp.tile_step = sink->tile_step; pp.y0 = sink->tile_first * 8;
+    }
+    {   // table fold (parameter-block kernel only): worth its per-CTA build (n * 768 entries) from ~4 M pixel-samples up
+        static const bool no_tab = std::getenv("RT_B200_NO_FOLD_TAB") != nullptr;              // A/B switch for measurements
+        const int step = pp.tile_step > 1 ? pp.tile_step : 1;
+        const long long work = (long long)pp.seg_w * ((pp.y1 - pp.y0 + step - 1) / step) * (p->s1 - p->s0);
+        pp.fold_tab = !no_tab && pp.int_fold && sc->byte_colours && !xr && work >= (4LL << 20);
     }
     if (!sc->sched_dev) return fail(RT_ERR_INVALID, "scene has no scheduler counters (upload failed?)");
     unsigned *sched = sc->sched_dev + 4 * (sc->sched_next.fetch_add(1u) % RT_SCHED_SLOTS);      // {next unit, warps done, CTAs resolved, -}

@@ -417,6 +417,23 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         S.lb.nL = sc.nL; S.lb.l_pos = sc.l_pos; S.lb.l_col = sc.l_col; S.lb.l_index = sc.l_index; S.lb.lpk = sc.lpk;
         S.la.nG = 0; S.la.nP = 0;
         __syncthreads();
+        if constexpr (kIntFold && !kRegen && !M<T>::exact) {
+            if (pp.fold_tab) {
+                // fold table: entry [sphere][channel][tot] = int(albedo * (tot / 255.0)), the very product the fold evaluates
+                // (fold_path_int), computed once per CTA -- four entries per 32-bit store
+                uint32_t *tab = reinterpret_cast<uint32_t *>(smem);
+                const float *colf = reinterpret_cast<const float *>(s_col);
+                for (int q = threadIdx.x; q < sc.n * 192; q += blockDim.x) {
+                    const int row = q >> 6, t0 = (q & 63) << 2, sph = row / 3, ch = row - 3 * sph;
+                    const double a = (double)colf[4 * sph + ch];
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v |= ((uint32_t)__double2int_rz(__dmul_rn(a, s_div255[t0 + j])) & 255u) << (8 * j);
+                    tab[q] = v;
+                }
+                __syncthreads();
+            }
+        }
     } else {
         div255 = reinterpret_cast<double *>(smem);
         for (int k = threadIdx.x; k < 256; k += blockDim.x) div255[k] = __ddiv_rn((double)k, 255.0);
@@ -638,7 +655,8 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                     pend = false;
                     if constexpr (kIntFold) {
                         int c[3] = {leaf0, leaf1, leaf2};
-                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from, s_base + 32u * RT_PKC_MAX);
+                        fold_path_int<T, kMode == 3>(S.g, st, depth, div255, c, fold_from, s_base + 32u * RT_PKC_MAX,
+                                                     (kMode == 3 && pp.fold_tab) ? (unsigned)__cvta_generic_to_shared(smem) : 0u);
                         a0 += (unsigned)c[0]; a1 += (unsigned)c[1]; a2 += (unsigned)c[2];
                     } else {
                         double c[3] = {lf0, lf1, lf2};
@@ -1612,7 +1630,9 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     int mode = mode_for(sc, extra);
     // small brute-force FP32 scenes: sphere pairs through the parameter block (kMode 3)
     if (mode == 0 && sizeof(T) == 4 && pkc && ((sc.n + 7) & ~7) <= RT_PKC_MAX && sc.nL <= RT_LPKC_MAX) mode = 3;
-    const size_t sm = mode == 3 ? 0 : (mode != 2 ? smem_for(sc) : 0) + extra;      // kMode 3 uses static shared arrays
+    if (mode != 3 || !pp.int_fold || pp.regenerate) ppl.fold_tab = 0;
+    // kMode 3 uses static shared arrays; its dynamic part is the fold table [n][3][256] bytes
+    const size_t sm = mode == 3 ? (ppl.fold_tab ? (size_t)sc.n * 768 : 0) : (mode != 2 ? smem_for(sc) : 0) + extra;
     cudaError_t e = cudaSuccess;
 #define RT_PATH_CASE(M_, F_, R_)                                                                                   \
     { e = allow_smem(path_kernel<T, M_, F_, R_>, sm); if (e != cudaSuccess) return e;                              \

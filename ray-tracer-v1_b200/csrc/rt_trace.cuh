@@ -597,8 +597,27 @@ RT_DEV void fold_path(const Geo<T> &g, const PathStack &st, int depth, double c[
 // kPacked: the level's sphere index rides in bits 24-31 of `direct` (scenes of <= 256 spheres), st.idx is not used.
 template <typename T, bool kPacked = false>
 RT_DEV void fold_path_int(const Geo<T> &g, const PathStack &st, int depth, const double *div255, int c[3], int k0 = 0,
-                          unsigned col_base = 0) {            // kPacked: shared-window address of the colour array
+                          unsigned col_base = 0,              // kPacked: shared-window address of the colour array
+                          unsigned tab = 0) {                 // kPacked: shared-window address of the fold table, or 0
     RT_ASSERT(depth >= 0 && depth <= RT_PATH_MAX_DEPTH);
+    if constexpr (kPacked && !M<T>::exact) {
+        if (tab) {
+            // every colour <= 255: int(albedo * (tot / 255.0)) was tabulated per (sphere, channel, tot) when the CTA started
+            // (path_kernel) with the same double product, so a level is one byte load per channel
+            for (int k = depth - 1; k >= k0; --k) {
+                const uint32_t d = st.direct[k];
+                RT_ASSERT((int)(d >> 24) < g.sv.n);
+                const unsigned row = tab + 768u * (d >> 24);
+                const unsigned a0 = row + (unsigned)min(255, (int)(d & 255u) + c[0]);
+                const unsigned a1 = row + (unsigned)min(255, (int)__byte_perm(d, 0u, 0x4441u) + c[1]);
+                const unsigned a2 = row + (unsigned)min(255, (int)__byte_perm(d, 0u, 0x4442u) + c[2]);
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(c[0]) : "r"(a0));
+                asm volatile("ld.shared.u8 %0, [%1+256];" : "=r"(c[1]) : "r"(a1));
+                asm volatile("ld.shared.u8 %0, [%1+512];" : "=r"(c[2]) : "r"(a2));
+            }
+            return;
+        }
+    }
     for (int k = depth - 1; k >= k0; --k) {
         const uint32_t d = st.direct[k];
         RT_ASSERT((int)(kPacked ? (d >> 24) : st.idx[k]) < g.sv.n);
