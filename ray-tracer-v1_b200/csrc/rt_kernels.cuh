@@ -1642,7 +1642,8 @@ cudaError_t launch_path(const SceneDev<T> &sc, const PathDev<T> &pp, void *accum
     if (mode == 3) {
         if constexpr (sizeof(T) == 4) {
 #define RT_PATH_CASE3(F_, R_)                                                                                      \
-    { e = allow_smem(path_kernel<T, 3, F_, R_>, sm); if (e != cudaSuccess) return e;                               \
+    { e = allow_smem(path_kernel<T, 3, F_, R_>, sm ? sm + 8192 : 0); /* + the static arrays: opt in above 48 KB in all */ \
+      if (e != cudaSuccess) return e;                                                                              \
       grid.x = persistent_ctas(path_kernel<T, 3, F_, R_>, sm, tiles_total);                                        \
       if (pp.max_ctas > 0 && grid.x > (unsigned)pp.max_ctas) grid.x = (unsigned)pp.max_ctas;                        \
       path_kernel<T, 3, F_, R_><<<grid, block, sm, st>>>(sc, ppl, (v4 *)accum, stats, *pkc); }

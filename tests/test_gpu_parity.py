@@ -191,6 +191,32 @@ def test_primary_candidate_lists_change_nothing(nat):
     sc.close()
 
 
+def test_fold_table_equals_double_fold(nat):
+    """Launches of >= 4 M pixel-samples of a scene whose colours are <= 255 fold through the per-CTA byte table
+    int(albedo * (tot / 255.0)) (PathDev::fold_tab), smaller launches through the double product itself: the frame
+    rendered whole (table) equals the same frame rendered in row bands below the threshold (double product) bit for bit.
+    The complex scene (54 spheres) and a 60-sphere scene, whose table + static arrays need opt-in shared memory; a
+    scene with a colour above 255 never uses the table and still folds exactly like the FP64 build's integers allow."""
+    from ray_tracer_v1_b200 import scenes
+    z, fs_c = load_golden("path_complex_48x27")
+    W, H, spp = 512, 512, 16                                   # 4,194,304 pixel-samples: at the threshold
+    for fs, cam, thr in ((fs_c, z["cam"], float(z["mirror_threshold"])),
+                         (scenes.build_many_spheres_flat(54, seed=5, emissive_fraction=0.1), (0.0, 2.0, 0.0), 0.0)):
+        assert float(np.max(fs.colour)) <= 255.0
+        sc = nat.DeviceScene(fs)
+        _, whole, st_w = sc.render_path_host(sc.path_params(cam, W, H, spp, 5, thr, seed=3), nat.F32)
+        banded, st_b = np.zeros_like(whole), np.zeros(8, np.uint64)
+        for y0 in range(0, H, 64):
+            _, part, st = sc.render_path_host(sc.path_params(cam, W, H, spp, 5, thr, seed=3, rows=(y0, y0 + 64)), nat.F32)
+            assert not part[:y0].any() and not part[y0 + 64:].any()
+            banded += part
+            st_b += st
+        assert np.array_equal(whole, banded)
+        assert np.array_equal(st_w[:5], st_b[:5])
+        assert whole[..., :3].max() > 0 and len(np.unique(whole[..., 0])) > 100
+        sc.close()
+
+
 def test_parameter_block_loop_at_its_limits(nat):
     """64 spheres / 32 lights is the largest scene whose sphere and light pairs ride in the kernel parameter block; one
     more sphere falls back to the shared-memory loop.  Both sizes: FP32 against the FP64 parity build, and (64 spheres)
