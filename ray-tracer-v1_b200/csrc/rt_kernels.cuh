@@ -559,6 +559,7 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 }
             }
             rng.begin(pixel, (uint32_t)smp, pp.k0, pp.k1);
+            if constexpr (kMode == 3 && !kRegen && RT_PRIMARY_CULL) if (pp.primary_cull) n_tests += (unsigned)__popcll(cand);
             uint32_t wa, wb;
             if (RT_PHILOX_RK) rng.pair_rk(0u, wa, wb, pp.rk); else rng.pair(0u, wa, wb);
             D = path_camera_ray<T>(pp, x, y, u01<T>(wa), u01<T>(wb));
@@ -589,8 +590,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
                 if constexpr (kMode == 3) {
                     // one LDS.128 for the winner's (centre, r) -- shared by the robust distance and the normal -- and one
                     // for its (1/r, reflective, emissive) record
-                    if (!kRegen && RT_PRIMARY_CULL && primary_trip && pp.primary_cull) n_tests += (unsigned)__popcll(cand);
-                    else n_tests += (unsigned)S.g.sv.n;
+                    // sphere tests: the lock-step kernel counts the camera rays' candidates once per sample (start_sample)
+                    // and derives the full-scene queries at the end of the launch (no counter update per trip)
+                    if constexpr (kRegen) n_tests += (unsigned)S.g.sv.n;
                     if (i >= 0) {
                         float4 w, hr;
                         lds_v4x2<16 * RT_PKC_MAX>(s_base + 16u * (unsigned)i, w, hr);      // (centre, r) and (1/r, reflective, emissive)
@@ -805,7 +807,15 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         flush_stats(stats, STAT_LIGHT, n_light);
         flush_stats(stats, STAT_SMALL, n_small);
         flush_stats(stats, STAT_QUERIES, n_query);
-        flush_stats(stats, STAT_SPHERE_TESTS, n_tests);
+        unsigned long long tests = n_tests;
+        if constexpr (kMode == 3 && !kRegen) {
+            // every query but the camera rays' (when those walk their candidate lists) tests the whole scene; a camera
+            // ray is a trace call that no hit caused: n_rays - (n_inter - n_light)
+            unsigned n_prim = 0u;
+            if (RT_PRIMARY_CULL && pp.primary_cull) n_prim = n_rays - (n_inter - n_light);
+            tests += (unsigned long long)(n_query - min(n_prim, n_query)) * (unsigned)sc.n;
+        }
+        flush_stats(stats, STAT_SPHERE_TESTS, tests);
         flush_stats(stats, STAT_AABB_TESTS, n_boxes);
     }
 }
