@@ -117,6 +117,9 @@ RT_DEV void flush_stats(unsigned long long *stats, int slot, unsigned long long 
 #ifndef RT_PATH_MIN_BLOCKS_PKC
 #define RT_PATH_MIN_BLOCKS_PKC 4   /* kMode 3 needs 72 registers unconstrained: 4 CTAs/SM at 64 measured 2.2 % faster (no spills) */
 #endif
+#ifndef RT_SBASE_OPAQUE
+#define RT_SBASE_OPAQUE 0   /* A/B (negative): base kept in a register saves the 3 uniform instructions per winner fetch, measured SLOWER: 16.60 vs 16.45 ms */
+#endif
 #ifndef RT_DEFER_FOLD
 #define RT_DEFER_FOLD 1        /* lock-step schedule: fold once per sample and warp (A/B: see DESIGN.md) */
 #endif
@@ -395,6 +398,9 @@ path_kernel(SceneDev<T> sc, PathDev<T> pp, typename M<T>::v4 *accum, unsigned lo
         __shared__ __align__(16) double s_div255[256];
         float4 *const s_sph = s_all, *const s_hit = s_all + RT_PKC_MAX, *const s_col = s_all + 2 * RT_PKC_MAX, *const s_cw = s_all + 3 * RT_PKC_MAX;
         s_base = (unsigned)__cvta_generic_to_shared(s_all);
+#if RT_SBASE_OPAQUE
+        asm volatile("" : "+r"(s_base));       // keep the base in a register: not re-derived from SR_CgaCtaId at every use
+#endif
         const int n_pad = (sc.n + 7) & ~7;
         const float *pkf = reinterpret_cast<const float *>(sc.pk);       // pair j: cx0 cx1 cy0 cy1 | cz0 cz1 w0 w1
         for (int i = threadIdx.x; i < n_pad; i += blockDim.x) {
